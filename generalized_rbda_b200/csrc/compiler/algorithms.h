@@ -1,0 +1,892 @@
+// Device-side model compiler, part 1: the cluster-tree algorithms evaluated symbolically.
+//
+// Each routine runs ONE evaluation of the algorithm over sym::Sym scalars for a given
+// ClusterTreeModel; the resulting expression DAG is the per-state program that compiler/emit.h
+// turns into a straight-line sm_100a kernel body (one state per thread).
+//
+// What is computed (reference, all under /root/reference):
+//   kinematics   TreeModel::forwardKinematics                 src/Dynamics/TreeModel.cpp:7-32
+//                per-type updateKinematics                    src/Dynamics/ClusterJoints/*.cpp
+//                GenericImplicit K, G, k, g                   GenericJoint.cpp:58-91
+//   ID           recursiveNewtonEulerAlgorithm                TreeModel.cpp:35-57,174-212
+//   FD           updateArticulatedBodies + forwardDynamics    ClusterTreeDynamics.cpp:85-191
+//   H            compositeRigidBodyAlgorithm                  TreeModel.cpp:116-160
+//   FK outputs   getPosition/getOrientation/get*Velocity      ClusterTreeModel.cpp:319-373
+//
+// How it is restructured for the GPU (not a translation):
+//   * every cluster type (Revolute, RevoluteWithRotor, RevolutePair(WithRotor), Generic, ...) is the
+//     same object here — revolute bodies on a spanning tree plus G (constant or from phi) — so the
+//     per-type dispatch of the reference disappears at model-compile time;
+//   * ID and H run on the spanning tree at body level and are projected with G (tau = G^T tau_s,
+//     H = G^T H_s G), which is algebraically identical to the cluster recursion (S = X_intra S_s G)
+//     but never forms the 6N x n motion subspace;
+//   * FD is the cluster (constraint-embedded) ABA. X^T Ia X is evaluated as
+//     sum_i X_i^T IA_ii X_i - W D^-1 W^T with W = X^T U (6 x n) instead of the reference's dense
+//     6N x 6N products; rigid 10-parameter inertias are kept as long as possible;
+//   * D^-1 is an unrolled LDL^T (D = S^T IA S is SPD); the reference uses ColPivHouseholderQR.
+#pragma once
+#include <map>
+#include "../host/model.h"
+#include "spatial_sym.h"
+
+namespace grbda
+{
+    namespace compiler
+    {
+        // Input arrays of a generated kernel
+        enum InputArray
+        {
+            IN_Q = 0,  // nq  positions (spanning coordinates for implicit clusters)
+            IN_YD = 1, // nv  independent velocities
+            IN_AUX = 2 // nv  ydd (ID) or tau (FD)
+        };
+
+        // second-order Taylor scalar over Sym for phi derivatives (K = dphi/dq, k = -qd^T H qd)
+        struct Taylor2
+        {
+            Sym c0, c1, c2;
+            Taylor2() {}
+            Taylor2(double x) : c0(x), c1(0.0), c2(0.0) {}
+            Taylor2(const Sym &a, const Sym &b, const Sym &c) : c0(a), c1(b), c2(c) {}
+        };
+        inline Taylor2 operator+(const Taylor2 &a, const Taylor2 &b) { return {a.c0 + b.c0, a.c1 + b.c1, a.c2 + b.c2}; }
+        inline Taylor2 operator-(const Taylor2 &a, const Taylor2 &b) { return {a.c0 - b.c0, a.c1 - b.c1, a.c2 - b.c2}; }
+        inline Taylor2 operator-(const Taylor2 &a) { return {-a.c0, -a.c1, -a.c2}; }
+        inline Taylor2 operator*(const Taylor2 &a, const Taylor2 &b)
+        {
+            return {a.c0 * b.c0, a.c0 * b.c1 + a.c1 * b.c0, a.c0 * b.c2 + a.c1 * b.c1 + a.c2 * b.c0};
+        }
+        inline Taylor2 operator/(const Taylor2 &a, const Taylor2 &b)
+        {
+            // only division by a constant occurs in constraint functions
+            if (!b.c0.isConst() || !b.c1.isZero() || !b.c2.isZero())
+                throw std::runtime_error("phi: division by a non-constant is not supported");
+            return {a.c0 / b.c0, a.c1 / b.c0, a.c2 / b.c0};
+        }
+        inline Taylor2 sin(const Taylor2 &a)
+        {
+            const Sym s = sym::sin(a.c0), c = sym::cos(a.c0);
+            return {s, c * a.c1, c * a.c2 - Sym(0.5) * s * a.c1 * a.c1};
+        }
+        inline Taylor2 cos(const Taylor2 &a)
+        {
+            const Sym s = sym::sin(a.c0), c = sym::cos(a.c0);
+            return {c, -(s * a.c1), -(s * a.c2) - Sym(0.5) * c * a.c1 * a.c1};
+        }
+
+        // Unrolled LDL^T of a small SPD matrix
+        struct LDLT
+        {
+            int n = 0;
+            std::vector<Sym> L;    // n x n, unit lower (only i > j used)
+            std::vector<Sym> dinv; // 1 / d_j
+
+            void factor(const std::vector<Sym> &D, int n_)
+            {
+                n = n_;
+                L.assign(n * n, Sym(0.0));
+                dinv.assign(n, Sym(0.0));
+                std::vector<Sym> d(n);
+                for (int j = 0; j < n; j++)
+                {
+                    Sym dj = D[j * n + j];
+                    for (int k = 0; k < j; k++)
+                        dj = dj - L[j * n + k] * L[j * n + k] * d[k];
+                    d[j] = dj;
+                    dinv[j] = Sym(1.0) / dj;
+                    for (int i = j + 1; i < n; i++)
+                    {
+                        Sym lij = D[i * n + j];
+                        for (int k = 0; k < j; k++)
+                            lij = lij - L[i * n + k] * L[j * n + k] * d[k];
+                        L[i * n + j] = lij * dinv[j];
+                    }
+                }
+            }
+            std::vector<Sym> solve(std::vector<Sym> b) const
+            {
+                for (int i = 0; i < n; i++)
+                    for (int k = 0; k < i; k++)
+                        b[i] = b[i] - L[i * n + k] * b[k];
+                for (int i = 0; i < n; i++)
+                    b[i] = b[i] * dinv[i];
+                for (int i = n - 1; i >= 0; i--)
+                    for (int k = i + 1; k < n; k++)
+                        b[i] = b[i] - L[k * n + i] * b[k];
+                return b;
+            }
+        };
+
+        // Inverse of a small regular (non symmetric) matrix, static pivot order.
+        inline std::vector<Sym> smallInverse(const std::vector<Sym> &A, int n)
+        {
+            std::vector<Sym> inv(n * n);
+            if (n == 1)
+                inv[0] = Sym(1.0) / A[0];
+            else if (n == 2)
+            {
+                const Sym idet = Sym(1.0) / (A[0] * A[3] - A[1] * A[2]);
+                inv = {A[3] * idet, -(A[1] * idet), -(A[2] * idet), A[0] * idet};
+            }
+            else if (n == 3)
+            {
+                auto a = [&](int i, int j) { return A[3 * i + j]; };
+                std::vector<Sym> cof(9);
+                for (int i = 0; i < 3; i++)
+                    for (int j = 0; j < 3; j++)
+                    {
+                        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+                        cof[3 * i + j] = a(i1, j1) * a(i2, j2) - a(i1, j2) * a(i2, j1);
+                    }
+                const Sym idet = Sym(1.0) / (a(0, 0) * cof[0] + a(0, 1) * cof[1] + a(0, 2) * cof[2]);
+                for (int i = 0; i < 3; i++)
+                    for (int j = 0; j < 3; j++)
+                        inv[3 * i + j] = cof[3 * j + i] * idet;
+            }
+            else
+            {
+                // Gauss-Jordan without pivoting (structure known only symbolically)
+                std::vector<Sym> M = A;
+                for (int i = 0; i < n; i++)
+                    for (int j = 0; j < n; j++)
+                        inv[i * n + j] = Sym(i == j ? 1.0 : 0.0);
+                for (int k = 0; k < n; k++)
+                {
+                    if (M[k * n + k].isZero())
+                        throw std::runtime_error("constraint Jacobian K_d has a structurally zero pivot");
+                    const Sym ip = Sym(1.0) / M[k * n + k];
+                    for (int j = 0; j < n; j++)
+                    {
+                        M[k * n + j] = M[k * n + j] * ip;
+                        inv[k * n + j] = inv[k * n + j] * ip;
+                    }
+                    for (int i = 0; i < n; i++)
+                        if (i != k)
+                        {
+                            const Sym f = M[i * n + k];
+                            for (int j = 0; j < n; j++)
+                            {
+                                M[i * n + j] = M[i * n + j] - f * M[k * n + j];
+                                inv[i * n + j] = inv[i * n + j] - f * inv[k * n + j];
+                            }
+                        }
+                }
+            }
+            return inv;
+        }
+
+        class ModelCompiler
+        {
+        public:
+            explicit ModelCompiler(const ClusterTreeModel &model) : m_(model) {}
+
+            // ---------------------------------------------------------------------------------
+            // per-cluster constraint quantities
+            // ---------------------------------------------------------------------------------
+            struct ClusterKin
+            {
+                std::vector<Sym> q_s, qd_s, g; // spanning position / velocity, bias g (N)
+                std::vector<Sym> G;            // N x n
+                std::vector<Sym> K, k;         // nc x N, nc (implicit only)
+            };
+            struct BodyKin
+            {
+                Xf Xl;        // from the parent body (any cluster) to this body
+                Xf Xup;       // from the cluster-ancestor body to this body
+                int anc = -1; // global index of the cluster-ancestor body
+                SV v, vJ, cJ, avp;
+                std::vector<SV> S; // n columns of the cluster motion subspace rows of this body
+                Sym qd;            // spanning velocity of this body's joint (revolute)
+            };
+
+            // phi, K (nc x N) and optionally k for an implicit cluster at spanning position q_s
+            void implicitJacobian(const ClusterDesc &d, const std::vector<Sym> &q_s,
+                                  const std::vector<Sym> *qd_s, std::vector<Sym> &phi,
+                                  std::vector<Sym> &K, std::vector<Sym> *k) const
+            {
+                const int N = d.num_bodies, nc = d.num_constraints;
+                K.assign(nc * N, Sym(0.0));
+                for (int j = 0; j < N; j++)
+                {
+                    std::vector<Taylor2> qs(N);
+                    for (int i = 0; i < N; i++)
+                        qs[i] = Taylor2(q_s[i], Sym(i == j ? 1.0 : 0.0), Sym(0.0));
+                    const std::vector<Taylor2> p = d.phi.evaluate(qs);
+                    for (int i = 0; i < nc; i++)
+                        K[i * N + j] = p[i].c1;
+                    if (j == 0)
+                    {
+                        phi.resize(nc);
+                        for (int i = 0; i < nc; i++)
+                            phi[i] = p[i].c0;
+                    }
+                }
+                if (k && qd_s)
+                {
+                    std::vector<Taylor2> qs(N);
+                    for (int i = 0; i < N; i++)
+                        qs[i] = Taylor2(q_s[i], (*qd_s)[i], Sym(0.0));
+                    const std::vector<Taylor2> p = d.phi.evaluate(qs);
+                    k->resize(nc);
+                    for (int i = 0; i < nc; i++)
+                        (*k)[i] = -(Sym(2.0) * p[i].c2);
+                }
+            }
+
+            ClusterKin clusterConstraint(const ClusterTreeNode &c, bool with_velocity) const
+            {
+                const ClusterDesc &d = c.joint_;
+                const int N = d.num_bodies, n = d.num_velocities;
+                ClusterKin ck;
+                std::vector<Sym> y(d.num_positions), yd(n);
+                for (int i = 0; i < d.num_positions; i++)
+                    y[i] = Sym::input(IN_Q, c.position_index_ + i);
+                for (int i = 0; i < n; i++)
+                    yd[i] = with_velocity ? Sym::input(IN_YD, c.velocity_index_ + i) : Sym(0.0);
+                ck.G.assign(N * n, Sym(0.0));
+                ck.g.assign(N, Sym(0.0));
+                if (d.type == ClusterType::Explicit)
+                {
+                    // q_span = gamma(y) = G y   (LoopConstraint.cpp:48-52)
+                    for (int i = 0; i < N * n; i++)
+                        ck.G[i] = Sym(d.G[i]);
+                    ck.q_s.assign(N, Sym(0.0));
+                    for (int i = 0; i < N; i++)
+                        for (int j = 0; j < n; j++)
+                            ck.q_s[i] = ck.q_s[i] + ck.G[i * n + j] * y[j];
+                }
+                else
+                {
+                    ck.q_s = y;
+                    std::vector<int> ind, dep;
+                    for (int i = 0; i < N; i++)
+                        (d.independent[i] ? ind : dep).push_back(i);
+                    const int nc = d.num_constraints;
+                    std::vector<Sym> phi;
+                    implicitJacobian(d, ck.q_s, nullptr, phi, ck.K, nullptr);
+                    std::vector<Sym> Kd(nc * nc);
+                    for (int i = 0; i < nc; i++)
+                        for (int j = 0; j < nc; j++)
+                            Kd[i * nc + j] = ck.K[i * N + dep[j]];
+                    const std::vector<Sym> Kd_inv = smallInverse(Kd, nc);
+                    // G = P [1; -Kd^-1 Ki]   (GenericJoint.cpp:70-85)
+                    for (int j = 0; j < n; j++)
+                        ck.G[ind[j] * n + j] = Sym(1.0);
+                    for (int i = 0; i < nc; i++)
+                        for (int j = 0; j < n; j++)
+                        {
+                            Sym s(0.0);
+                            for (int l = 0; l < nc; l++)
+                                s = s + Kd_inv[i * nc + l] * ck.K[l * N + ind[j]];
+                            ck.G[dep[i] * n + j] = -s;
+                        }
+                    if (with_velocity)
+                    {
+                        ck.qd_s.assign(N, Sym(0.0));
+                        for (int i = 0; i < N; i++)
+                            for (int j = 0; j < n; j++)
+                                ck.qd_s[i] = ck.qd_s[i] + ck.G[i * n + j] * yd[j];
+                        // k = -Kdot qd, g = P [0; Kd^-1 k]   (GenericJoint.cpp:60-68,87-91)
+                        std::vector<Sym> K2;
+                        implicitJacobian(d, ck.q_s, &ck.qd_s, phi, K2, &ck.k);
+                        for (int i = 0; i < nc; i++)
+                        {
+                            Sym s(0.0);
+                            for (int l = 0; l < nc; l++)
+                                s = s + Kd_inv[i * nc + l] * ck.k[l];
+                            ck.g[dep[i]] = s;
+                        }
+                    }
+                }
+                if (ck.qd_s.empty())
+                {
+                    ck.qd_s.assign(N, Sym(0.0));
+                    for (int i = 0; i < N; i++)
+                        for (int j = 0; j < n; j++)
+                            ck.qd_s[i] = ck.qd_s[i] + ck.G[i * n + j] * yd[j];
+                }
+                return ck;
+            }
+
+            // ---------------------------------------------------------------------------------
+            // kinematics of every body (forward pass)
+            // ---------------------------------------------------------------------------------
+            void kinematics(bool with_velocity, bool with_subspace)
+            {
+                const int Nb = m_.getNumBodies();
+                bk_.assign(Nb, BodyKin());
+                ck_.clear();
+                for (const ClusterTreeNode &c : m_.clusters())
+                {
+                    const ClusterDesc &d = c.joint_;
+                    const int n = d.num_velocities;
+                    if (d.type == ClusterType::FreeQuaternion || d.type == ClusterType::FreeRollPitchYaw)
+                    {
+                        // Joints::Free (Joint.h:61-68); Xtree ignored (FreeJoint.cpp:45)
+                        BodyKin &b = bk_[c.first_body_];
+                        const int pi = c.position_index_;
+                        V3 p{{Sym::input(IN_Q, pi), Sym::input(IN_Q, pi + 1), Sym::input(IN_Q, pi + 2)}};
+                        M3 E;
+                        if (d.type == ClusterType::FreeQuaternion)
+                            E = quaternionToRotationMatrix(Sym::input(IN_Q, pi + 3), Sym::input(IN_Q, pi + 4),
+                                                           Sym::input(IN_Q, pi + 5), Sym::input(IN_Q, pi + 6));
+                        else
+                        {
+                            const Sym r = Sym::input(IN_Q, pi + 3), pt = Sym::input(IN_Q, pi + 4),
+                                      yw = Sym::input(IN_Q, pi + 5);
+                            E = mul(mul(coordinateRotation(ori::CoordinateAxis::X, sym::sin(r), sym::cos(r)),
+                                        coordinateRotation(ori::CoordinateAxis::Y, sym::sin(pt), sym::cos(pt))),
+                                    coordinateRotation(ori::CoordinateAxis::Z, sym::sin(yw), sym::cos(yw)));
+                        }
+                        b.Xl.E = E;
+                        b.Xl.r = p;
+                        b.Xup = b.Xl;
+                        b.anc = -1;
+                        for (int i = 0; i < 6; i++)
+                            b.v[i] = with_velocity ? Sym::input(IN_YD, c.velocity_index_ + i) : Sym(0.0);
+                        b.vJ = b.v;
+                        if (with_subspace)
+                        {
+                            b.S.assign(6, SV());
+                            for (int k = 0; k < 6; k++)
+                                b.S[k][k] = Sym(1.0);
+                        }
+                        ck_.push_back(ClusterKin());
+                        continue;
+                    }
+
+                    ClusterKin ck = clusterConstraint(c, with_velocity);
+                    for (int i = 0; i < d.num_bodies; i++)
+                    {
+                        const Body &body = c.bodies_[i];
+                        BodyKin &b = bk_[body.index_];
+                        const int axis = (int)d.axes[i];
+                        const Sym s = sym::sin(ck.q_s[i]), co = sym::cos(ck.q_s[i]);
+                        // XJ * Xtree  (Joint.h:94-97)
+                        b.Xl.E = mul(coordinateRotation(d.axes[i], s, co), constM3(body.Xtree_.E));
+                        b.Xl.r = constV3(body.Xtree_.r);
+                        b.qd = ck.qd_s[i];
+                        SV sq; // s_i * qd_i
+                        sq[axis] = b.qd;
+                        const int p = body.parent_index_;
+                        const bool parent_in_cluster = p >= c.first_body_ && p >= 0 &&
+                                                       m_.getIndexOfClusterContainingBody(p) == c.index_;
+                        if (parent_in_cluster)
+                        {
+                            const BodyKin &pb = bk_[p];
+                            b.Xup = b.Xl * pb.Xup;
+                            b.anc = pb.anc;
+                            b.vJ = b.Xl.applyMotion(pb.vJ) + sq;
+                            // cJ_i = Xl cJ_p + vJ_i x (s_i qd_i) + s_i g_i  (GenericJoint.cpp:427-451)
+                            b.cJ = b.Xl.applyMotion(pb.cJ) + motionCross(b.vJ, sq);
+                        }
+                        else
+                        {
+                            b.Xup = b.Xl;
+                            b.anc = p;
+                            b.vJ = sq;
+                        }
+                        b.cJ[axis] = b.cJ[axis] + ck.g[i];
+                        b.v = (p >= 0 ? b.Xl.applyMotion(bk_[p].v) : SV()) + sq;
+                        b.avp = motionCross(b.v, b.vJ);
+                        if (with_subspace)
+                        {
+                            b.S.assign(n, SV());
+                            for (int k = 0; k < n; k++)
+                            {
+                                if (parent_in_cluster)
+                                    b.S[k] = b.Xl.applyMotion(bk_[p].S[k]);
+                                b.S[k][axis] = b.S[k][axis] + ck.G[i * n + k];
+                            }
+                        }
+                    }
+                    ck_.push_back(ck);
+                }
+            }
+
+            SV minusGravity() const
+            {
+                SV a;
+                for (int i = 0; i < 3; i++)
+                    a[3 + i] = Sym(-m_.getGravity()[i]);
+                return a;
+            }
+
+            // ---------------------------------------------------------------------------------
+            // forward kinematics outputs: per body p(3), R(9), [w_world; v_world](6)
+            // ---------------------------------------------------------------------------------
+            void forwardKinematics(std::vector<Sym> &p_out, std::vector<Sym> &R_out, std::vector<Sym> &v_out)
+            {
+                kinematics(true, false);
+                const int Nb = m_.getNumBodies();
+                std::vector<Xf> Xa(Nb);
+                for (int i = 0; i < Nb; i++)
+                {
+                    const int p = m_.bodies()[i].parent_index_;
+                    Xa[i] = p >= 0 ? bk_[i].Xl * Xa[p] : bk_[i].Xl;
+                    for (int k = 0; k < 3; k++)
+                        p_out.push_back(Xa[i].r[k]);
+                    for (int r = 0; r < 3; r++)
+                        for (int cc = 0; cc < 3; cc++)
+                            R_out.push_back(Xa[i].E(cc, r));
+                    const V3 w = mulT(Xa[i].E, bk_[i].v.ang()), vl = mulT(Xa[i].E, bk_[i].v.lin());
+                    for (int k = 0; k < 3; k++)
+                        v_out.push_back(w[k]);
+                    for (int k = 0; k < 3; k++)
+                        v_out.push_back(vl[k]);
+                }
+            }
+
+            // ---------------------------------------------------------------------------------
+            // inverse dynamics: spanning-tree RNEA + projection tau = G^T tau_s
+            // ---------------------------------------------------------------------------------
+            std::vector<Sym> inverseDynamics()
+            {
+                kinematics(true, false);
+                const int Nb = m_.getNumBodies(), nv = m_.getNumDegreesOfFreedom();
+                std::vector<SV> a(Nb), f(Nb);
+                std::vector<RigidInertia> I(Nb);
+                for (const ClusterTreeNode &c : m_.clusters())
+                {
+                    const ClusterDesc &d = c.joint_;
+                    const int n = d.num_velocities;
+                    std::vector<Sym> ydd(n);
+                    for (int k = 0; k < n; k++)
+                        ydd[k] = Sym::input(IN_AUX, c.velocity_index_ + k);
+                    const bool is_free = d.type == ClusterType::FreeQuaternion ||
+                                         d.type == ClusterType::FreeRollPitchYaw;
+                    for (int i = 0; i < d.num_bodies; i++)
+                    {
+                        const int bi = c.first_body_ + i;
+                        const Body &body = m_.bodies()[bi];
+                        const BodyKin &b = bk_[bi];
+                        const int p = body.parent_index_;
+                        SV ai = b.Xl.applyMotion(p >= 0 ? a[p] : minusGravity());
+                        if (is_free)
+                        {
+                            for (int k = 0; k < 6; k++)
+                                ai[k] = ai[k] + ydd[k];
+                        }
+                        else
+                        {
+                            // qdd_s = G ydd + g
+                            const ClusterKin &ck = ck_[c.index_];
+                            Sym qdd = ck.g[i];
+                            for (int k = 0; k < n; k++)
+                                qdd = qdd + ck.G[i * n + k] * ydd[k];
+                            const int axis = (int)d.axes[i];
+                            SV sq;
+                            sq[axis] = b.qd;
+                            ai[axis] = ai[axis] + qdd;
+                            ai = ai + motionCross(b.v, sq);
+                        }
+                        a[bi] = ai;
+                        I[bi] = RigidInertia::fromMatrix(body.inertia_.getMatrix());
+                        f[bi] = I[bi].apply(ai) + forceCross(b.v, I[bi].apply(b.v));
+                    }
+                }
+                std::vector<Sym> tau(nv, Sym(0.0));
+                for (int ci = m_.getNumClusters() - 1; ci >= 0; ci--)
+                {
+                    const ClusterTreeNode &c = m_.clusters()[ci];
+                    const ClusterDesc &d = c.joint_;
+                    const int n = d.num_velocities;
+                    const bool is_free = d.type == ClusterType::FreeQuaternion ||
+                                         d.type == ClusterType::FreeRollPitchYaw;
+                    for (int i = d.num_bodies - 1; i >= 0; i--)
+                    {
+                        const int bi = c.first_body_ + i;
+                        const int p = m_.bodies()[bi].parent_index_;
+                        if (is_free)
+                            for (int k = 0; k < 6; k++)
+                                tau[c.velocity_index_ + k] = f[bi][k];
+                        else
+                        {
+                            const ClusterKin &ck = ck_[c.index_];
+                            const Sym tau_s = f[bi][(int)d.axes[i]];
+                            for (int k = 0; k < n; k++)
+                                tau[c.velocity_index_ + k] = tau[c.velocity_index_ + k] + ck.G[i * n + k] * tau_s;
+                        }
+                        if (p >= 0)
+                            f[p] = f[p] + bk_[bi].Xl.applyForceTranspose(f[bi]);
+                    }
+                }
+                return tau;
+            }
+
+            // ---------------------------------------------------------------------------------
+            // mass matrix: spanning-tree CRBA + projection H = G^T H_s G   (row-major nv x nv)
+            // ---------------------------------------------------------------------------------
+            std::vector<Sym> massMatrix()
+            {
+                kinematics(false, false);
+                const int Nb = m_.getNumBodies(), nv = m_.getNumDegreesOfFreedom();
+                std::vector<RigidInertia> Ic(Nb);
+                for (int i = 0; i < Nb; i++)
+                    Ic[i] = RigidInertia::fromMatrix(m_.bodies()[i].inertia_.getMatrix());
+                for (int i = Nb - 1; i >= 0; i--)
+                {
+                    const int p = m_.bodies()[i].parent_index_;
+                    if (p >= 0)
+                        Ic[p] = Ic[p] + Ic[i].toParent(bk_[i].Xl);
+                }
+                // spanning dofs: body i owns dof columns sdof[i] .. (+6 for the free body, +1 else)
+                std::vector<int> sdof(Nb), sn(Nb);
+                int ns = 0;
+                for (const ClusterTreeNode &c : m_.clusters())
+                    for (int i = 0; i < c.joint_.num_bodies; i++)
+                    {
+                        const bool is_free = c.joint_.type == ClusterType::FreeQuaternion ||
+                                             c.joint_.type == ClusterType::FreeRollPitchYaw;
+                        sdof[c.first_body_ + i] = ns;
+                        sn[c.first_body_ + i] = is_free ? 6 : 1;
+                        ns += sn[c.first_body_ + i];
+                    }
+                auto axisOf = [&](int body) {
+                    const int ci = m_.getIndexOfClusterContainingBody(body);
+                    const ClusterTreeNode &c = m_.clusters()[ci];
+                    return (int)c.joint_.axes[body - c.first_body_];
+                };
+                std::vector<Sym> Hs(ns * ns, Sym(0.0));
+                for (int i = 0; i < Nb; i++)
+                    for (int k = 0; k < sn[i]; k++)
+                    {
+                        SV s;
+                        s[sn[i] == 6 ? k : axisOf(i)] = Sym(1.0);
+                        SV F = Ic[i].apply(s);
+                        const int col = sdof[i] + k;
+                        for (int l = 0; l < sn[i]; l++)
+                            Hs[(sdof[i] + l) * ns + col] = F[sn[i] == 6 ? l : axisOf(i)];
+                        int j = i;
+                        while (m_.bodies()[j].parent_index_ >= 0)
+                        {
+                            F = bk_[j].Xl.applyForceTranspose(F);
+                            j = m_.bodies()[j].parent_index_;
+                            for (int l = 0; l < sn[j]; l++)
+                            {
+                                const Sym h = F[sn[j] == 6 ? l : axisOf(j)];
+                                Hs[(sdof[j] + l) * ns + col] = h;
+                                Hs[col * ns + sdof[j] + l] = h;
+                            }
+                        }
+                    }
+                // projection with the block-diagonal G
+                std::vector<std::vector<std::pair<int, Sym>>> Gcol(nv); // independent dof -> (spanning dof, G)
+                for (const ClusterTreeNode &c : m_.clusters())
+                {
+                    const ClusterDesc &d = c.joint_;
+                    const bool is_free = d.type == ClusterType::FreeQuaternion ||
+                                         d.type == ClusterType::FreeRollPitchYaw;
+                    if (is_free)
+                    {
+                        for (int k = 0; k < 6; k++)
+                            Gcol[c.velocity_index_ + k].push_back({sdof[c.first_body_] + k, Sym(1.0)});
+                        continue;
+                    }
+                    const ClusterKin &ck = ck_[c.index_];
+                    for (int i = 0; i < d.num_bodies; i++)
+                        for (int k = 0; k < d.num_velocities; k++)
+                            if (!ck.G[i * d.num_velocities + k].isZero())
+                                Gcol[c.velocity_index_ + k].push_back(
+                                    {sdof[c.first_body_ + i], ck.G[i * d.num_velocities + k]});
+                }
+                std::vector<Sym> H(nv * nv, Sym(0.0));
+                for (int b = 0; b < nv; b++)
+                {
+                    // t = H_s G[:, b]
+                    std::vector<Sym> t(ns, Sym(0.0));
+                    for (auto &e : Gcol[b])
+                        for (int r = 0; r < ns; r++)
+                            t[r] = t[r] + Hs[r * ns + e.first] * e.second;
+                    for (int a = 0; a <= b; a++)
+                    {
+                        Sym s(0.0);
+                        for (auto &e : Gcol[a])
+                            s = s + e.second * t[e.first];
+                        H[a * nv + b] = s;
+                        H[b * nv + a] = s;
+                    }
+                }
+                return H;
+            }
+
+            // ---------------------------------------------------------------------------------
+            // forward dynamics: constraint-embedded (cluster) articulated-body algorithm
+            // ---------------------------------------------------------------------------------
+            std::vector<Sym> forwardDynamics()
+            {
+                kinematics(true, true);
+                const int Nb = m_.getNumBodies(), nv = m_.getNumDegreesOfFreedom(), Nc = m_.getNumClusters();
+
+                // articulated inertia: rigid accumulator + general symmetric accumulator on the
+                // diagonal; general blocks (i < j) off the diagonal within a cluster
+                std::vector<RigidInertia> rigid(Nb);
+                std::vector<SymInertia> gen(Nb);
+                std::vector<char> has_gen(Nb, 0);
+                std::map<std::pair<int, int>, M6> offdiag;
+                std::vector<SV> pA(Nb);
+                for (int i = 0; i < Nb; i++)
+                {
+                    rigid[i] = RigidInertia::fromMatrix(m_.bodies()[i].inertia_.getMatrix());
+                    // pA = v x* (I v)   (ClusterTreeDynamics.cpp:95-98)
+                    pA[i] = forceCross(bk_[i].v, rigid[i].apply(bk_[i].v));
+                }
+                auto IAdiag = [&](int i) {
+                    SymInertia I = SymInertia::fromRigid(rigid[i]);
+                    return has_gen[i] ? I + gen[i] : I;
+                };
+                auto applyIA = [&](int i, const SV &x) {
+                    SV y = rigid[i].apply(x);
+                    if (has_gen[i])
+                        y = y + gen[i].apply(x);
+                    return y;
+                };
+
+                struct ClusterABA
+                {
+                    std::vector<std::vector<SV>> U; // [body][column]
+                    LDLT ldl;
+                    std::vector<Sym> u;
+                };
+                std::vector<ClusterABA> aba(Nc);
+
+                for (int ci = Nc - 1; ci >= 0; ci--)
+                {
+                    const ClusterTreeNode &c = m_.clusters()[ci];
+                    const int N = c.joint_.num_bodies, n = c.joint_.num_velocities, b0 = c.first_body_;
+                    ClusterABA &A = aba[ci];
+                    // c_i = cJ + avp
+                    std::vector<SV> cb(N);
+                    for (int i = 0; i < N; i++)
+                        cb[i] = bk_[b0 + i].cJ + bk_[b0 + i].avp;
+                    // U = IA S
+                    A.U.assign(N, std::vector<SV>(n));
+                    for (int i = 0; i < N; i++)
+                        for (int k = 0; k < n; k++)
+                        {
+                            SV y = applyIA(b0 + i, bk_[b0 + i].S[k]);
+                            for (int j = 0; j < N; j++)
+                            {
+                                if (j == i)
+                                    continue;
+                                auto it = offdiag.find({b0 + std::min(i, j), b0 + std::max(i, j)});
+                                if (it == offdiag.end())
+                                    continue;
+                                y = y + (i < j ? it->second.apply(bk_[b0 + j].S[k])
+                                               : it->second.applyTranspose(bk_[b0 + j].S[k]));
+                            }
+                            A.U[i][k] = y;
+                        }
+                    // D = S^T U, u = tau - S^T pA
+                    std::vector<Sym> D(n * n);
+                    A.u.assign(n, Sym(0.0));
+                    for (int k = 0; k < n; k++)
+                    {
+                        for (int l = k; l < n; l++)
+                        {
+                            Sym s(0.0);
+                            for (int i = 0; i < N; i++)
+                                s = s + dot(bk_[b0 + i].S[k], A.U[i][l]);
+                            D[k * n + l] = s;
+                            D[l * n + k] = s;
+                        }
+                        Sym s = Sym::input(IN_AUX, c.velocity_index_ + k);
+                        for (int i = 0; i < N; i++)
+                            s = s - dot(bk_[b0 + i].S[k], pA[b0 + i]);
+                        A.u[k] = s;
+                    }
+                    A.ldl.factor(D, n);
+
+                    if (c.parent_index_ < 0)
+                        continue;
+
+                    // z = D^-1 (u - U^T c)
+                    std::vector<Sym> t = A.u;
+                    for (int k = 0; k < n; k++)
+                        for (int i = 0; i < N; i++)
+                            t[k] = t[k] - dot(A.U[i][k], cb[i]);
+                    const std::vector<Sym> z = A.ldl.solve(t);
+                    // pa_i = pA_i + sum_j IA_ij c_j + U_i z ; parent pA += X_i^T pa_i
+                    for (int i = 0; i < N; i++)
+                    {
+                        SV pa = pA[b0 + i] + applyIA(b0 + i, cb[i]);
+                        for (int j = 0; j < N; j++)
+                        {
+                            if (j == i)
+                                continue;
+                            auto it = offdiag.find({b0 + std::min(i, j), b0 + std::max(i, j)});
+                            if (it == offdiag.end())
+                                continue;
+                            pa = pa + (i < j ? it->second.apply(cb[j]) : it->second.applyTranspose(cb[j]));
+                        }
+                        for (int k = 0; k < n; k++)
+                            pa = pa + z[k] * A.U[i][k];
+                        const int anc = bk_[b0 + i].anc;
+                        pA[anc] = pA[anc] + bk_[b0 + i].Xup.applyForceTranspose(pa);
+                    }
+                    // parent IA += X^T IA X - W D^-1 W^T,   W_a = sum_{i -> a} X_i^T U_i
+                    std::map<int, std::vector<SV>> W;
+                    for (int i = 0; i < N; i++)
+                    {
+                        const int anc = bk_[b0 + i].anc;
+                        auto &Wa = W[anc];
+                        if (Wa.empty())
+                            Wa.assign(n, SV());
+                        for (int k = 0; k < n; k++)
+                            Wa[k] = Wa[k] + bk_[b0 + i].Xup.applyForceTranspose(A.U[i][k]);
+                        // diagonal blocks
+                        rigid[anc] = rigid[anc] + rigid[b0 + i].toParent(bk_[b0 + i].Xup);
+                        if (has_gen[b0 + i])
+                        {
+                            const SymInertia G = gen[b0 + i].toParent(bk_[b0 + i].Xup);
+                            gen[anc] = has_gen[anc] ? gen[anc] + G : G;
+                            has_gen[anc] = 1;
+                        }
+                    }
+                    // off-diagonal blocks of this cluster
+                    for (auto &kv : offdiag)
+                    {
+                        const int i = kv.first.first, j = kv.first.second;
+                        if (i < b0 || i >= b0 + N)
+                            continue;
+                        const int a = bk_[i].anc, b = bk_[j].anc;
+                        const M6 M = transformBlock(bk_[i].Xup, kv.second, bk_[j].Xup);
+                        addBlock(a, b, M, gen, has_gen, offdiag);
+                    }
+                    // V_a = W_a D^-1 (columns), then -(V_a W_b^T)
+                    std::map<int, std::vector<SV>> V;
+                    for (auto &kv : W)
+                    {
+                        std::vector<SV> Va(n);
+                        for (int r = 0; r < 6; r++)
+                        {
+                            std::vector<Sym> row(n);
+                            for (int k = 0; k < n; k++)
+                                row[k] = kv.second[k][r];
+                            const std::vector<Sym> x = A.ldl.solve(row);
+                            for (int k = 0; k < n; k++)
+                                Va[k][r] = x[k];
+                        }
+                        V[kv.first] = Va;
+                    }
+                    for (auto &ka : W)
+                        for (auto &kb : W)
+                        {
+                            const int a = ka.first, b = kb.first;
+                            if (a > b)
+                                continue;
+                            M6 M;
+                            for (int r = 0; r < 6; r++)
+                                for (int s = (a == b ? r : 0); s < 6; s++)
+                                {
+                                    Sym e(0.0);
+                                    for (int k = 0; k < n; k++)
+                                        e = e + V[a][k][r] * kb.second[k][s];
+                                    M(r, s) = -e;
+                                    if (a == b)
+                                        M(s, r) = -e;
+                                }
+                            if (a == b)
+                                addSymmetric(a, M, gen, has_gen);
+                            else
+                                addBlock(a, b, M, gen, has_gen, offdiag);
+                        }
+                }
+
+                // forward pass: accelerations (ClusterTreeDynamics.cpp:132-152)
+                std::vector<Sym> ydd_out(nv);
+                std::vector<SV> a(Nb);
+                for (int ci = 0; ci < Nc; ci++)
+                {
+                    const ClusterTreeNode &c = m_.clusters()[ci];
+                    const int N = c.joint_.num_bodies, n = c.joint_.num_velocities, b0 = c.first_body_;
+                    const ClusterABA &A = aba[ci];
+                    const bool is_free = c.joint_.type == ClusterType::FreeQuaternion ||
+                                         c.joint_.type == ClusterType::FreeRollPitchYaw;
+                    std::vector<SV> at(N);
+                    for (int i = 0; i < N; i++)
+                    {
+                        const BodyKin &b = bk_[b0 + i];
+                        at[i] = b.Xup.applyMotion(b.anc >= 0 ? a[b.anc] : minusGravity()) + b.cJ + b.avp;
+                    }
+                    std::vector<Sym> ydd;
+                    if (is_free)
+                    {
+                        // S = 1: ydd = D^-1 (u - D a') = D^-1 u - a'
+                        ydd = A.ldl.solve(A.u);
+                        for (int k = 0; k < 6; k++)
+                            ydd[k] = ydd[k] - at[0][k];
+                    }
+                    else
+                    {
+                        std::vector<Sym> t = A.u;
+                        for (int k = 0; k < n; k++)
+                            for (int i = 0; i < N; i++)
+                                t[k] = t[k] - dot(A.U[i][k], at[i]);
+                        ydd = A.ldl.solve(t);
+                    }
+                    for (int k = 0; k < n; k++)
+                        ydd_out[c.velocity_index_ + k] = ydd[k];
+                    for (int i = 0; i < N; i++)
+                    {
+                        SV ai = at[i];
+                        for (int k = 0; k < n; k++)
+                            ai = ai + ydd[k] * bk_[b0 + i].S[k];
+                        a[b0 + i] = ai;
+                    }
+                }
+                return ydd_out;
+            }
+
+            const std::vector<BodyKin> &bodyKinematics() const { return bk_; }
+            const std::vector<ClusterKin> &clusterKinematics() const { return ck_; }
+
+        private:
+            static SymInertia symFromM6(const M6 &M)
+            {
+                SymInertia I;
+                int k = 0;
+                for (int i = 0; i < 3; i++)
+                    for (int j = i; j < 3; j++)
+                    {
+                        I.A.a[k] = M(i, j);
+                        I.C.a[k] = M(3 + i, 3 + j);
+                        k++;
+                    }
+                for (int i = 0; i < 3; i++)
+                    for (int j = 0; j < 3; j++)
+                        I.B(i, j) = M(i, 3 + j);
+                return I;
+            }
+            static void addSymmetric(int a, const M6 &M, std::vector<SymInertia> &gen, std::vector<char> &has_gen)
+            {
+                const SymInertia I = symFromM6(M);
+                gen[a] = has_gen[a] ? gen[a] + I : I;
+                has_gen[a] = 1;
+            }
+            // add block M at (a, b) of the articulated inertia (a != b: off-diagonal, stored for a < b;
+            // a == b: M + M^T because both (i, j) and (j, i) land on the same diagonal block)
+            static void addBlock(int a, int b, const M6 &M, std::vector<SymInertia> &gen,
+                                 std::vector<char> &has_gen, std::map<std::pair<int, int>, M6> &offdiag)
+            {
+                if (a == b)
+                {
+                    addSymmetric(a, M + M.transposed(), gen, has_gen);
+                    return;
+                }
+                const std::pair<int, int> key{std::min(a, b), std::max(a, b)};
+                const M6 Mk = a < b ? M : M.transposed();
+                auto it = offdiag.find(key);
+                if (it == offdiag.end())
+                    offdiag[key] = Mk;
+                else
+                    it->second = it->second + Mk;
+            }
+
+            const ClusterTreeModel &m_;
+            std::vector<BodyKin> bk_;
+            std::vector<ClusterKin> ck_;
+        };
+
+    } // namespace compiler
+} // namespace grbda

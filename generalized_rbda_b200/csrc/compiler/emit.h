@@ -1,0 +1,254 @@
+// Device-side model compiler, part 2: turn the expression DAG of one algorithm into
+//   (a) a straight-line CUDA body (one state per thread) consumed by kernels/batched_kernel.cuh,
+//   (b) a flat "tape" (the same program as plain arrays) for introspection and for the CPU-side
+//       compiler self-tests in tests/ (a numpy interpreter replays it against the oracle),
+//   (c) exact operation counts of the emitted program.
+#pragma once
+#include <cstdio>
+#include <sstream>
+#include <string>
+#include "sym.h"
+
+namespace grbda
+{
+    namespace compiler
+    {
+        struct ProgramStats
+        {
+            long n_nodes = 0, n_add = 0, n_mul = 0, n_div = 0, n_sqrt = 0, n_sin = 0, n_cos = 0,
+                 n_neg = 0, n_select = 0, n_inputs = 0, n_fusable = 0;
+            // flops with every add / mul / div / sqrt counted once (an FMA counts 2)
+            long flops() const { return n_add + n_mul + n_div + n_sqrt; }
+        };
+
+        struct Tape
+        {
+            std::vector<int32_t> op, a, b, c, e;
+            std::vector<double> val;
+            std::vector<std::vector<int32_t>> outputs; // per output array: tape index per element
+        };
+
+        struct Program
+        {
+            std::string name;
+            int n_in[3] = {0, 0, 0};
+            std::vector<std::vector<sym::Sym>> outputs; // up to 3 output arrays
+        };
+
+        class Emitter
+        {
+        public:
+            Emitter(const sym::Graph &g, const Program &p) : g_(g), p_(p) { analyse(); }
+
+            const ProgramStats &stats() const { return stats_; }
+
+            Tape tape() const
+            {
+                Tape t;
+                std::vector<int32_t> remap(g_.nodes.size(), -1);
+                for (size_t i = 0; i < g_.nodes.size(); i++)
+                    if (live_[i])
+                    {
+                        const sym::Node &n = g_.nodes[i];
+                        remap[i] = (int32_t)t.op.size();
+                        t.op.push_back(n.op);
+                        const bool leaf = n.op == sym::OP_CONST || n.op == sym::OP_INPUT;
+                        t.a.push_back(leaf ? n.a : (n.a >= 0 ? remap[n.a] : -1));
+                        t.b.push_back(leaf ? n.b : (n.b >= 0 ? remap[n.b] : -1));
+                        t.c.push_back(n.c >= 0 ? remap[n.c] : -1);
+                        t.e.push_back(n.e >= 0 ? remap[n.e] : -1);
+                        t.val.push_back(n.val);
+                    }
+                for (auto &arr : p_.outputs)
+                {
+                    std::vector<int32_t> o;
+                    for (auto &s : arr)
+                        o.push_back(remap[s.id]);
+                    t.outputs.push_back(o);
+                }
+                return t;
+            }
+
+            // Body text. Inputs are read through IN0(i)/IN1(i)/IN2(i), results written through
+            // OUT0(i, x)/OUT1/OUT2; `real` is the arithmetic type; KC(x) makes a literal of type real.
+            std::string cudaBody() const
+            {
+                std::ostringstream os;
+                std::vector<char> done(g_.nodes.size(), 0);
+                // node id -> list of (array, element) it must be stored to
+                std::vector<std::vector<std::pair<int, int>>> stores(g_.nodes.size());
+                for (size_t arr = 0; arr < p_.outputs.size(); arr++)
+                    for (size_t i = 0; i < p_.outputs[arr].size(); i++)
+                        stores[p_.outputs[arr][i].id].push_back({(int)arr, (int)i});
+
+                auto emitStores = [&](size_t id) {
+                    for (auto &st : stores[id])
+                        os << "OUT" << st.first << "(" << st.second << ", " << ref((int32_t)id) << ");\n";
+                };
+                for (size_t i = 0; i < g_.nodes.size(); i++)
+                {
+                    if (!live_[i])
+                        continue;
+                    const sym::Node &n = g_.nodes[i];
+                    if (n.op == sym::OP_CONST || n.op == sym::OP_NEG)
+                    {
+                        emitStores(i);
+                        continue;
+                    }
+                    if (done[i])
+                    {
+                        emitStores(i);
+                        continue;
+                    }
+                    switch (n.op)
+                    {
+                    case sym::OP_INPUT:
+                        os << "const real t" << i << " = IN" << n.a << "(" << n.b << ");\n";
+                        break;
+                    case sym::OP_ADD:
+                        os << "const real t" << i << " = " << ref(n.a) << " + " << ref(n.b) << ";\n";
+                        break;
+                    case sym::OP_SUB:
+                        os << "const real t" << i << " = " << ref(n.a) << " - " << ref(n.b) << ";\n";
+                        break;
+                    case sym::OP_MUL:
+                        os << "const real t" << i << " = " << ref(n.a) << " * " << ref(n.b) << ";\n";
+                        break;
+                    case sym::OP_DIV:
+                        os << "const real t" << i << " = " << ref(n.a) << " / " << ref(n.b) << ";\n";
+                        break;
+                    case sym::OP_SQRT:
+                        os << "const real t" << i << " = sqrt(" << ref(n.a) << ");\n";
+                        break;
+                    case sym::OP_SELECT_GT:
+                        os << "const real t" << i << " = (" << ref(n.a) << " > " << ref(n.b) << ") ? "
+                           << ref(n.c) << " : " << ref(n.e) << ";\n";
+                        break;
+                    case sym::OP_SIN:
+                    case sym::OP_COS:
+                    {
+                        // pair sin/cos of the same argument into one sincos
+                        const int32_t other = partner_[i];
+                        if (other >= 0 && live_[other])
+                        {
+                            const int32_t s = n.op == sym::OP_SIN ? (int32_t)i : other;
+                            const int32_t c = n.op == sym::OP_SIN ? other : (int32_t)i;
+                            os << "real t" << s << ", t" << c << "; grbda_sincos(" << ref(n.a) << ", &t" << s
+                               << ", &t" << c << ");\n";
+                            done[other] = 1;
+                        }
+                        else
+                            os << "const real t" << i << " = " << (n.op == sym::OP_SIN ? "sin(" : "cos(")
+                               << ref(n.a) << ");\n";
+                        break;
+                    }
+                    default:
+                        throw std::runtime_error("emit: unknown op");
+                    }
+                    done[i] = 1;
+                    emitStores(i);
+                }
+                return os.str();
+            }
+
+        private:
+            std::string ref(int32_t id) const
+            {
+                const sym::Node &n = g_.nodes[id];
+                if (n.op == sym::OP_CONST)
+                {
+                    char buf[64];
+                    std::snprintf(buf, sizeof(buf), "KC(%.17g)", n.val);
+                    return buf;
+                }
+                if (n.op == sym::OP_NEG)
+                    return "(-" + ref(n.a) + ")";
+                return "t" + std::to_string(id);
+            }
+
+            void analyse()
+            {
+                const size_t N = g_.nodes.size();
+                live_.assign(N, 0);
+                uses_.assign(N, 0);
+                partner_.assign(N, -1);
+                for (auto &arr : p_.outputs)
+                    for (auto &s : arr)
+                        live_[s.id] = 1;
+                for (long i = (long)N - 1; i >= 0; i--)
+                {
+                    if (!live_[i])
+                        continue;
+                    const sym::Node &n = g_.nodes[i];
+                    if (n.op == sym::OP_CONST || n.op == sym::OP_INPUT)
+                        continue;
+                    for (int32_t c : {n.a, n.b, n.c, n.e})
+                        if (c >= 0)
+                        {
+                            live_[c] = 1;
+                            uses_[c]++;
+                        }
+                }
+                std::unordered_map<int32_t, int32_t> sin_of, cos_of;
+                for (size_t i = 0; i < N; i++)
+                {
+                    if (!live_[i])
+                        continue;
+                    const sym::Node &n = g_.nodes[i];
+                    stats_.n_nodes++;
+                    switch (n.op)
+                    {
+                    case sym::OP_ADD:
+                    case sym::OP_SUB:
+                        stats_.n_add++;
+                        // a*b+c with a single-use product contracts into one FMA
+                        for (int32_t c : {n.a, n.b})
+                        {
+                            int32_t m = c;
+                            if (g_.nodes[m].op == sym::OP_NEG)
+                                m = g_.nodes[m].a;
+                            if (g_.nodes[m].op == sym::OP_MUL && uses_[m] == 1 && (m == c || uses_[c] == 1))
+                            {
+                                stats_.n_fusable++;
+                                break;
+                            }
+                        }
+                        break;
+                    case sym::OP_MUL: stats_.n_mul++; break;
+                    case sym::OP_DIV: stats_.n_div++; break;
+                    case sym::OP_SQRT: stats_.n_sqrt++; break;
+                    case sym::OP_NEG: stats_.n_neg++; break;
+                    case sym::OP_SELECT_GT: stats_.n_select++; break;
+                    case sym::OP_INPUT: stats_.n_inputs++; break;
+                    case sym::OP_SIN:
+                        stats_.n_sin++;
+                        sin_of[n.a] = (int32_t)i;
+                        break;
+                    case sym::OP_COS:
+                        stats_.n_cos++;
+                        cos_of[n.a] = (int32_t)i;
+                        break;
+                    default: break;
+                    }
+                }
+                for (auto &kv : sin_of)
+                {
+                    auto it = cos_of.find(kv.first);
+                    if (it != cos_of.end())
+                    {
+                        partner_[kv.second] = it->second;
+                        partner_[it->second] = kv.second;
+                    }
+                }
+            }
+
+            const sym::Graph &g_;
+            const Program &p_;
+            std::vector<char> live_;
+            std::vector<int> uses_;
+            std::vector<int32_t> partner_;
+            ProgramStats stats_;
+        };
+
+    } // namespace compiler
+} // namespace grbda
