@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Headline benchmark: forward + inverse dynamics evaluations per second, TelloWithArms
+(37 bodies, 15 clusters, nq 33, nv 24), 2^20 independent states per GPU, FP64.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+  python bench.py --impl reference ...                     (the CPU path on the box's host cores)
+
+A step = one pass of the hot path over one batch of synthetic states: forwardDynamics
+(constraint-embedded ABA) followed by inverseDynamics (cluster RNEA) of the resulting accelerations.
+`value` counts fwd+inv PAIRS per second summed over all GPUs, inputs resident in HBM; `e2e` is the
+same pass through the host-buffer entry point (pinned host memory -> H2D -> kernels -> D2H).
+The batch is sharded by global state index (weak scaling: 2^20 states per GPU, no collective on the
+data path; the only collective is the final timing / checksum gather).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fwd+inv dynamics evals/s (Tello, batch 2^20)"
+UNIT = "fwd+inv state evaluations/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i] == "Active" for s in self.samples)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_baseline(model_name, seconds_target=12.0, threads=0):
+    """The oracle (CPU restatement of the reference path) on the host cores, bounded sample."""
+    from oracle import binding
+    o = binding.OracleModel(model_name)
+    cores = binding.max_threads() if threads <= 0 else threads
+    n = 256 * cores
+    q, yd, tau = o.generate_states(n)
+    t0 = time.perf_counter()
+    ydd = o.forward_dynamics(q, yd, tau, threads=cores)
+    o.inverse_dynamics(q, yd, ydd, threads=cores)
+    dt = time.perf_counter() - t0
+    # scale the sample to about seconds_target of CPU work
+    n2 = int(max(n, min(1 << 18, n * seconds_target / max(dt, 1e-6))))
+    q, yd, tau = o.generate_states(n2)
+    t0 = time.perf_counter()
+    ydd = o.forward_dynamics(q, yd, tau, threads=cores)
+    o.inverse_dynamics(q, yd, ydd, threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": n2 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d states, forwardDynamics + inverseDynamics, %d threads, %.1f s" % (n2, cores, dt)}, o
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores. The
+    reference itself cannot be built here (Eigen / CasADi / urdfdom absent), so this is
+    the oracle port, all host threads, a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import binding
+    o = binding.OracleModel(args.model)
+    cores = binding.max_threads()
+    n = args.ref_states
+    q, yd, tau = o.generate_states(n)
+    for _ in range(args.warmup):
+        o.inverse_dynamics(q[:256], yd[:256], o.forward_dynamics(q[:256], yd[:256], tau[:256]))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ydd = o.forward_dynamics(q, yd, tau, threads=cores)
+        o.inverse_dynamics(q, yd, ydd, threads=cores)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s forwardDynamics+inverseDynamics, %d-state sample per step (CPU)" % (args.model, n),
+                       "model": args.model, "batch_per_step": n},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d states x %d steps" % (n, args.steps)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--model", default="tello_with_arms")
+    ap.add_argument("--batch", type=int, default=1 << 20, help="states per GPU")
+    ap.add_argument("--ref-states", type=int, default=1 << 14)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import generalized_rbda_b200 as grbda
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    m = grbda.ClusterTreeModel.from_robot(args.model, device=local_rank)
+    B = args.batch
+    # contiguous shard of the global index range, generated on this GPU
+    q, yd, tau, flags = m.generateStates(B, first_index=rank * B)
+    ydd = torch.empty_like(tau)
+    tau_back = torch.empty_like(tau)
+    assert int(flags.sum()) == 0
+
+    def step():
+        m.forwardDynamics(q, yd, tau, out=ydd)
+        m.inverseDynamics(q, yd, ydd, out=tau_back)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = grbda.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = grbda.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    sampler.stop_flag = True
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # per-kernel timing of the dominant kernel (FD) and of ID, same stream, CUDA events
+    def time_kernel(fn, reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps * 1e-3
+
+    t_fd = time_kernel(lambda: m.forwardDynamics(q, yd, tau, out=ydd), args.steps)
+    t_id = time_kernel(lambda: m.inverseDynamics(q, yd, ydd, out=tau_back), args.steps)
+
+    # parity spot check + checksum gather (the only collective)
+    err = float(((tau_back - tau).abs().amax(1) / tau.abs().amax(1)).median())
+    cs = torch.tensor(list(grbda.checksum(ydd)), dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(cs)
+
+    e2e = None
+    if not args.no_e2e:
+        qh, ydh, tauh = (x.cpu().pin_memory() for x in (q, yd, tau))
+        yddh = torch.empty((B, m.nv), dtype=torch.float64).pin_memory()
+        tbh = torch.empty((B, m.nv), dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            m.dynamics_host(1, qh, ydh, tauh, yddh)
+            m.dynamics_host(0, qh, ydh, yddh, tbh)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(2, min(args.steps, 5))
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * n_e2e / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(2 * B * (m.nq + 2 * m.nv) * 8), "d2h_bytes_per_step": int(2 * B * m.nv * 8),
+               "steps": n_e2e, "api": "grbda_cuda_dynamics_host_f64 (pinned host buffers)"}
+        assert torch.equal(yddh, ydd.cpu())
+
+    if rank == 0:
+        peaks, peaks_kind = load_peaks()
+        fd_prog, id_prog = m.dump_program(grbda.ALGO_FD), m.dump_program(grbda.ALGO_ID)
+        fp64_peak = grbda.measure_fma_peak(local_rank, fp32=False, seconds=0.5)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "%s forwardDynamics + inverseDynamics, %d states per GPU, FP64" % (args.model, B),
+                           "model": args.model, "batch_per_gpu": B, "nq": m.nq, "nv": m.nv, "bodies": m.nb,
+                           "clusters": m.nc, "l2": "inputs (%.0f MB per step) larger than L2, no flush needed" %
+                           (B * (m.nq + 3 * m.nv) * 8 / 1e6), "sharding": "contiguous global-index shards, no NCCL on the data path"},
+                "gpu_launches": int(launches), "clocks": sampler.summary(),
+                "parity": {"median_rel_err_ID_of_FD": err, "checksum_ydd": [float(cs[0]), float(cs[1])]}}
+        if e2e:
+            line["e2e"] = e2e
+        cpu = None
+        if not args.no_cpu_baseline and world >= 1:
+            cpu, o = cpu_baseline(args.model)
+            line["cpu_baseline"] = cpu
+            f_alg_fd = o.count_flops(1)["flops_alg"]
+            f_alg_id = o.count_flops(0)["flops_alg"]
+        else:
+            f_alg_fd, f_alg_id = fd_prog["flops"], id_prog["flops"]
+        alg_bytes = (m.nq + 3 * m.nv) * 8
+        line["roofline"] = {
+            "kernel": "forwardDynamics (grbda_batched_kernel<double, Body fd>)",
+            "bound": "fp64", "unit": "TFLOP/s",
+            "achieved": f_alg_fd * B / t_fd / 1e12, "peak": fp64_peak / 1e12,
+            "frac": (f_alg_fd * B / t_fd) / fp64_peak,
+            "peak_source": "measured here: dependent-free DFMA loop (grbda_cuda_measure_fma_peak); "
+                           "MEASURED_PEAKS.json has no FP64 entry",
+            "flops_per_state_alg": f_alg_fd, "flops_per_state_executed": fd_prog["flops"],
+            "achieved_executed": fd_prog["flops"] * B / t_fd / 1e12,
+            "kernel_ms": t_fd * 1e3, "traffic": None,
+            "hbm": {"achieved": alg_bytes * B / t_fd / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": alg_bytes * B / t_fd / 1e9 / peaks["hbm_gbs"], "peak_source": peaks_kind,
+                    "bytes_per_state": alg_bytes},
+            "inverse_dynamics": {"kernel_ms": t_id * 1e3, "flops_per_state_alg": f_alg_id,
+                                 "flops_per_state_executed": id_prog["flops"],
+                                 "achieved": f_alg_id * B / t_id / 1e12, "frac": (f_alg_id * B / t_id) / fp64_peak,
+                                 "hbm_frac": alg_bytes * B / t_id / 1e9 / peaks["hbm_gbs"]}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

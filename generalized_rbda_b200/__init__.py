@@ -1,0 +1,315 @@
+"""generalized_rbda_b200 — batched ClusterTreeModel dynamics on B200 (sm_100a).
+
+Thin Python binding (ctypes) over the C ABI in include/grbda_cuda.h. PyTorch is used only for
+device memory, streams and torch.distributed plumbing; every kernel that runs is one of this
+repository's own generated sm_100a kernels inside libgrbda_cuda.so. There is no CPU fallback: if
+the shared library has not been built (python -m generalized_rbda_b200.build, or
+__graft_entry__.build()) importing this package raises.
+
+The class below mirrors the reference's model API
+(reference: include/grbda/Dynamics/ClusterTreeModel.h:23-228, TreeModel.h:15-143) with batched
+versions of inverseDynamics / forwardDynamics / getMassMatrix / forwardKinematics.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libgrbda_cuda.so")
+URDF_DIR = os.path.join(_HERE, "robot-models")
+
+if not os.path.exists(_LIB_PATH):
+    raise ImportError(
+        "generalized_rbda_b200: %s is missing — build it first "
+        "(python -m generalized_rbda_b200.build); there is no CPU fallback" % _LIB_PATH)
+
+os.environ.setdefault("GRBDA_URDF_DIR", URDF_DIR)
+_lib = C.CDLL(_LIB_PATH)
+
+ALGO_ID, ALGO_FD, ALGO_FK, ALGO_H, ALGO_PHI = 0, 1, 2, 3, 4
+ALGO_NAMES = ["id", "fd", "fk", "h", "phi"]
+
+_vp = C.c_void_p
+_i64 = C.c_int64
+_lib.grbda_cuda_last_error_string.restype = C.c_char_p
+_lib.grbda_cuda_version.restype = C.c_char_p
+_lib.grbda_cuda_model_hash.restype = C.c_uint64
+_lib.grbda_cuda_model_hash.argtypes = [_vp]
+_lib.grbda_cuda_launch_count.restype = _i64
+for _n in ("num_positions", "num_degrees_of_freedom", "num_bodies", "num_clusters"):
+    getattr(_lib, "grbda_cuda_" + _n).argtypes = [_vp]
+_lib.grbda_cuda_model_create_from_robot.argtypes = [C.c_char_p, C.c_int, C.POINTER(_vp)]
+_lib.grbda_cuda_model_create_from_urdf.argtypes = [C.c_char_p, C.c_int, C.POINTER(_vp)]
+_lib.grbda_cuda_model_create.argtypes = [_vp, C.c_int, C.POINTER(_vp)]
+_lib.grbda_cuda_model_destroy.argtypes = [_vp]
+_lib.grbda_cuda_cluster_info.argtypes = [_vp, C.c_int, _vp, _vp]
+_lib.grbda_cuda_body_info.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]
+_lib.grbda_cuda_cluster_G.argtypes = [_vp, C.c_int, _vp]
+_lib.grbda_cuda_dump_program.argtypes = [_vp, C.c_int, C.c_char_p, _vp]
+for _p in ("f64", "f32"):
+    getattr(_lib, "grbda_cuda_inverse_dynamics_" + _p).argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp]
+    getattr(_lib, "grbda_cuda_forward_dynamics_" + _p).argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp]
+    getattr(_lib, "grbda_cuda_mass_matrix_" + _p).argtypes = [_vp, _vp, _vp, _i64, _vp]
+    getattr(_lib, "grbda_cuda_forward_kinematics_" + _p).argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
+_lib.grbda_cuda_dynamics_host_f64.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _i64]
+_lib.grbda_cuda_generate_states.argtypes = [_vp, C.c_uint64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]
+_lib.grbda_cuda_constraint_violation_f64.argtypes = [_vp, _vp, _vp, _i64, _vp]
+_lib.grbda_cuda_checksum_f64.argtypes = [_vp, _i64, _vp, _vp]
+_lib.grbda_cuda_measure_fma_peak.argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double)]
+
+EXPORTED_SYMBOLS = [
+    "grbda_cuda_last_error_string", "grbda_cuda_version", "grbda_cuda_model_create",
+    "grbda_cuda_model_create_from_urdf", "grbda_cuda_model_create_from_robot", "grbda_cuda_model_destroy",
+    "grbda_cuda_num_positions", "grbda_cuda_num_degrees_of_freedom", "grbda_cuda_num_bodies",
+    "grbda_cuda_num_clusters", "grbda_cuda_model_hash", "grbda_cuda_cluster_info", "grbda_cuda_body_info",
+    "grbda_cuda_cluster_G", "grbda_cuda_dump_program",
+    "grbda_cuda_inverse_dynamics_f64", "grbda_cuda_inverse_dynamics_f32",
+    "grbda_cuda_forward_dynamics_f64", "grbda_cuda_forward_dynamics_f32",
+    "grbda_cuda_mass_matrix_f64", "grbda_cuda_mass_matrix_f32",
+    "grbda_cuda_forward_kinematics_f64", "grbda_cuda_forward_kinematics_f32",
+    "grbda_cuda_dynamics_host_f64", "grbda_cuda_generate_states", "grbda_cuda_constraint_violation_f64",
+    "grbda_cuda_checksum_f64", "grbda_cuda_measure_fma_peak", "grbda_cuda_launch_count",
+]
+
+DEFAULT_SEED = 0x6772626461  # "grbda"
+
+
+class GrbdaError(RuntimeError):
+    """Raised for every non-zero grbda_status (the reference throws std::runtime_error)."""
+
+    def __init__(self, status, message):
+        super().__init__("grbda_cuda status %d: %s" % (status, message))
+        self.status = status
+
+
+def _check(status):
+    if status != 0:
+        raise GrbdaError(status, _lib.grbda_cuda_last_error_string().decode())
+
+
+def lib():
+    return _lib
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def launch_count():
+    return int(_lib.grbda_cuda_launch_count())
+
+
+def measure_fma_peak(device=0, fp32=False, seconds=0.5):
+    out = C.c_double()
+    _check(_lib.grbda_cuda_measure_fma_peak(device, int(fp32), seconds, C.byref(out)))
+    return out.value
+
+
+def _ptr(t):
+    return None if t is None else _vp(t.data_ptr())
+
+
+def _stream():
+    import torch
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+class ClusterTreeModel:
+    """Batched counterpart of grbda::ClusterTreeModel.
+
+    Construct with from_robot(name) (the reference's robot classes / URDF+ files) or
+    from_urdf(path). device=None gives a host-only handle (sizes, topology, emitted programs).
+    """
+
+    def __init__(self, handle, device):
+        self._h = handle
+        self.device = device
+
+    @classmethod
+    def from_robot(cls, name, device=0):
+        h = _vp()
+        _check(_lib.grbda_cuda_model_create_from_robot(name.encode(), -1 if device is None else device, C.byref(h)))
+        return cls(h, device)
+
+    @classmethod
+    def from_urdf(cls, path, device=0):
+        h = _vp()
+        _check(_lib.grbda_cuda_model_create_from_urdf(path.encode(), -1 if device is None else device, C.byref(h)))
+        return cls(h, device)
+
+    @classmethod
+    def from_schedule(cls, schedule_ptr, device=0):
+        h = _vp()
+        _check(_lib.grbda_cuda_model_create(schedule_ptr, -1 if device is None else device, C.byref(h)))
+        return cls(h, device)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _lib.grbda_cuda_model_destroy(self._h)
+            self._h = None
+
+    # ---- sizes / topology (TreeModel.h:25-28) -------------------------------------------------
+    def getNumPositions(self):
+        return _lib.grbda_cuda_num_positions(self._h)
+
+    def getNumDegreesOfFreedom(self):
+        return _lib.grbda_cuda_num_degrees_of_freedom(self._h)
+
+    def getNumBodies(self):
+        return _lib.grbda_cuda_num_bodies(self._h)
+
+    def getNumClusters(self):
+        return _lib.grbda_cuda_num_clusters(self._h)
+
+    nq = property(getNumPositions)
+    nv = property(getNumDegreesOfFreedom)
+    nb = property(getNumBodies)
+    nc = property(getNumClusters)
+
+    @property
+    def hash(self):
+        return int(_lib.grbda_cuda_model_hash(self._h))
+
+    def clusters(self):
+        out = []
+        for c in range(self.nc):
+            info = (C.c_int32 * 8)()
+            name = C.create_string_buffer(64)
+            _check(_lib.grbda_cuda_cluster_info(self._h, c, info, name))
+            keys = ("parent", "num_bodies", "num_positions", "num_velocities", "position_index",
+                    "velocity_index", "type", "first_body")
+            d = dict(zip(keys, list(info)))
+            d["joint_type"] = name.value.decode()
+            if d["type"] == 2:
+                G = np.zeros((d["num_bodies"], d["num_velocities"]))
+                _check(_lib.grbda_cuda_cluster_G(self._h, c, G.ctypes.data_as(_vp)))
+                d["G"] = G
+            out.append(d)
+        return out
+
+    def bodies(self):
+        out = []
+        for b in range(self.nb):
+            info = (C.c_int32 * 4)()
+            name = C.create_string_buffer(64)
+            E, r, I = np.zeros((3, 3)), np.zeros(3), np.zeros((6, 6))
+            _check(_lib.grbda_cuda_body_info(self._h, b, name, info, E.ctypes.data_as(_vp),
+                                             r.ctypes.data_as(_vp), I.ctypes.data_as(_vp)))
+            out.append(dict(name=name.value.decode(), parent=info[0], cluster=info[1], sub_index=info[2],
+                            axis=info[3], E=E, r=r, inertia=I))
+        return out
+
+    def dump_program(self, algo, path=None):
+        counts = (C.c_int64 * 8)()
+        _check(_lib.grbda_cuda_dump_program(self._h, algo, path.encode() if path else None, counts))
+        keys = ("nodes", "add", "mul", "div", "sqrt", "sin", "cos", "fusable")
+        d = dict(zip(keys, [int(x) for x in counts]))
+        d["flops"] = d["add"] + d["mul"] + d["div"] + d["sqrt"]
+        return d
+
+    # ---- batched hot path (device tensors) ----------------------------------------------------
+    def _prep(self, t, n, dtype=None):
+        import torch
+        if not t.is_cuda:
+            raise ValueError("expected a CUDA tensor")
+        if dtype is not None and t.dtype != dtype:
+            raise ValueError("dtype mismatch: %s vs %s" % (t.dtype, dtype))
+        if t.dtype not in (torch.float64, torch.float32):
+            raise ValueError("float64 or float32 tensors are required")
+        if t.dim() != 2 or t.shape[1] != n or not t.is_contiguous():
+            raise ValueError("expected a contiguous [batch, %d] tensor, got %s" % (n, tuple(t.shape)))
+        return t
+
+    def _suffix(self, t):
+        import torch
+        return "f64" if t.dtype == torch.float64 else "f32"
+
+    def inverseDynamics(self, q, yd, ydd, out=None):
+        """tau[batch, nv] = ID(q, yd, ydd)   (ClusterTreeModel::inverseDynamics)"""
+        import torch
+        q = self._prep(q, self.nq)
+        yd, ydd = self._prep(yd, self.nv, q.dtype), self._prep(ydd, self.nv, q.dtype)
+        if out is None:
+            out = torch.empty_like(ydd)
+        fn = getattr(_lib, "grbda_cuda_inverse_dynamics_" + self._suffix(q))
+        _check(fn(self._h, _ptr(q), _ptr(yd), _ptr(ydd), _ptr(out), q.shape[0], _stream()))
+        return out
+
+    def forwardDynamics(self, q, yd, tau, out=None):
+        """ydd[batch, nv] = FD(q, yd, tau)   (ClusterTreeModel::forwardDynamics)"""
+        import torch
+        q = self._prep(q, self.nq)
+        yd, tau = self._prep(yd, self.nv, q.dtype), self._prep(tau, self.nv, q.dtype)
+        if out is None:
+            out = torch.empty_like(tau)
+        fn = getattr(_lib, "grbda_cuda_forward_dynamics_" + self._suffix(q))
+        _check(fn(self._h, _ptr(q), _ptr(yd), _ptr(tau), _ptr(out), q.shape[0], _stream()))
+        return out
+
+    def getMassMatrix(self, q, out=None):
+        """H[batch, nv, nv]   (ClusterTreeModel::getMassMatrix)"""
+        import torch
+        q = self._prep(q, self.nq)
+        if out is None:
+            out = torch.empty((q.shape[0], self.nv, self.nv), dtype=q.dtype, device=q.device)
+        fn = getattr(_lib, "grbda_cuda_mass_matrix_" + self._suffix(q))
+        _check(fn(self._h, _ptr(q), _ptr(out), q.shape[0], _stream()))
+        return out
+
+    def getBiasForceVector(self, q, yd):
+        """C[batch, nv] = ID(q, yd, 0)   (ClusterTreeModel::getBiasForceVector)"""
+        import torch
+        return self.inverseDynamics(q, yd, torch.zeros_like(yd))
+
+    def forwardKinematics(self, q, yd):
+        """(p[batch, nb, 3], R[batch, nb, 3, 3], v[batch, nb, 6]) per body: world position,
+        body-to-world rotation, [world angular; world linear] velocity of the body origin."""
+        import torch
+        q = self._prep(q, self.nq)
+        yd = self._prep(yd, self.nv, q.dtype)
+        B = q.shape[0]
+        p = torch.empty((B, self.nb, 3), dtype=q.dtype, device=q.device)
+        R = torch.empty((B, self.nb, 3, 3), dtype=q.dtype, device=q.device)
+        v = torch.empty((B, self.nb, 6), dtype=q.dtype, device=q.device)
+        fn = getattr(_lib, "grbda_cuda_forward_kinematics_" + self._suffix(q))
+        _check(fn(self._h, _ptr(q), _ptr(yd), _ptr(p), _ptr(R), _ptr(v), B, _stream()))
+        return p, R, v
+
+    # ---- host buffers (end-to-end path) ---------------------------------------------------------
+    def dynamics_host(self, algo, q, yd, in3, out):
+        """ID (algo=0) / FD (algo=1) on HOST arrays (numpy float64 or CPU torch tensors, ideally
+        pinned): H2D copy, kernel and D2H copy are pipelined inside the call."""
+        def hp(a):
+            return _vp(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
+        batch = q.shape[0]
+        _check(_lib.grbda_cuda_dynamics_host_f64(self._h, algo, hp(q), hp(yd), hp(in3), hp(out), batch))
+        return out
+
+    # ---- synthetic states / checks --------------------------------------------------------------
+    def generateStates(self, count, seed=DEFAULT_SEED, first_index=0, device=None):
+        """(q, yd, aux, flags): random valid states for global indices [first_index, first_index+count)."""
+        import torch
+        dev = torch.device("cuda", self.device if device is None else device)
+        q = torch.empty((count, self.nq), dtype=torch.float64, device=dev)
+        yd = torch.empty((count, self.nv), dtype=torch.float64, device=dev)
+        aux = torch.empty((count, self.nv), dtype=torch.float64, device=dev)
+        flags = torch.empty((count,), dtype=torch.int32, device=dev)
+        _check(_lib.grbda_cuda_generate_states(self._h, seed, first_index, count, _ptr(q), _ptr(yd), _ptr(aux),
+                                               _ptr(flags), _stream()))
+        return q, yd, aux, flags
+
+    def constraintViolation(self, q):
+        import torch
+        q = self._prep(q, self.nq, torch.float64)
+        out = torch.empty((q.shape[0],), dtype=torch.float64, device=q.device)
+        _check(_lib.grbda_cuda_constraint_violation_f64(self._h, _ptr(q), _ptr(out), q.shape[0], _stream()))
+        return out
+
+
+def checksum(x):
+    """(sum, sum of absolute values) of a float64 CUDA tensor, computed on the device."""
+    out = (C.c_double * 2)()
+    x = x.contiguous()
+    _check(_lib.grbda_cuda_checksum_f64(_ptr(x), x.numel(), out, _stream()))
+    return out[0], out[1]

@@ -1,0 +1,127 @@
+"""Build libgrbda_cuda.so in-tree.
+
+Steps (all outputs under generalized_rbda_b200/_build and generalized_rbda_b200/csrc/generated):
+  1. g++   host model library + the model compiler tool `grbda_modelc`
+  2. run   grbda_modelc for every model in MODELS -> csrc/generated/<model>_<algo>.cu
+  3. nvcc  -gencode arch=compute_100a,code=sm_100a -lineinfo every generated .cu and the runtime
+  4. link  generalized_rbda_b200/libgrbda_cuda.so
+Objects are cached by the hash of their (generated) source + flags, so re-builds are incremental.
+"""
+import concurrent.futures as cf
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+GEN = os.path.join(CSRC, "generated")
+BUILD = os.path.join(HERE, "_build")
+URDF_DIR = os.path.join(HERE, "robot-models")
+LIB = os.path.join(HERE, "libgrbda_cuda.so")
+
+# model name -> (algorithms, launch variants "BLOCK,MIN_BLOCKS,STAGED;...", build f32 variants)
+DEFAULT_VARIANTS = "128,2,1"
+MODELS = {
+    "tello_with_arms": ("id,fd,fk,h,phi,gen", "128,2,1;64,4,1;128,2,0;64,2,1", True),
+    "tello": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
+    "revolute_chain_with_rotor_2": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
+    "revolute_chain_with_rotor_4": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, False),
+    "revolute_pair_chain_with_rotor_2": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, False),
+    "revolute_pair_chain_with_rotor_4": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, False),
+}
+
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+CXXFLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-variable", "-Wno-sign-compare"]
+NVCCFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+             "-Xcompiler", "-fPIC", "-I", CSRC, "-ccbin", CXX,
+             "-DGRBDA_DEFAULT_URDF_DIR=\"%s\"" % URDF_DIR]
+
+HOST_SOURCES = ["host/robots.cpp", "host/robot_factory.cpp", "host/urdf.cpp"]
+
+
+def _run(cmd, **kw):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, **kw)
+    if r.returncode != 0:
+        raise RuntimeError("command failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return r.stdout
+
+
+def _digest(paths, extra=""):
+    h = hashlib.sha256(extra.encode())
+    for p in paths:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:20]
+
+
+def _headers():
+    out = []
+    for root, _, files in os.walk(CSRC):
+        if root.startswith(GEN):
+            continue
+        for f in files:
+            if f.endswith((".h", ".cuh")):
+                out.append(os.path.join(root, f))
+    out.append(os.path.join(HERE, "..", "include", "grbda_cuda.h"))
+    return sorted(out)
+
+
+def _compile_cached(src, obj_dir, compiler_cmd, dep_digest, log):
+    """Compile src -> object named by content hash; returns object path."""
+    key = _digest([src], dep_digest + " ".join(compiler_cmd))
+    obj = os.path.join(obj_dir, os.path.basename(src) + "." + key + ".o")
+    if not os.path.exists(obj):
+        log("  compile %s" % os.path.relpath(src, HERE))
+        _run(compiler_cmd + ["-c", src, "-o", obj])
+    return obj
+
+
+def build(verbose=True, jobs=None, models=None):
+    log = (lambda s: print(s, flush=True)) if verbose else (lambda s: None)
+    os.makedirs(GEN, exist_ok=True)
+    os.makedirs(BUILD, exist_ok=True)
+    models = models or MODELS
+    jobs = jobs or max(1, (os.cpu_count() or 2))
+    hdr_digest = _digest(_headers())
+
+    # 1. host objects + modelc
+    host_objs = [_compile_cached(os.path.join(CSRC, s), BUILD, [CXX] + CXXFLAGS, hdr_digest, log)
+                 for s in HOST_SOURCES]
+    modelc_obj = _compile_cached(os.path.join(CSRC, "tools/modelc.cpp"), BUILD, [CXX] + CXXFLAGS, hdr_digest, log)
+    modelc = os.path.join(BUILD, "grbda_modelc")
+    _run([CXX, "-o", modelc, modelc_obj] + host_objs)
+
+    # 2. generate
+    gen_sources = []
+    for name, (algos, variants, f32) in models.items():
+        cmd = [modelc, "--model", name, "--urdf-dir", URDF_DIR, "--out", GEN, "--algos", algos,
+               "--variants", variants]
+        if not f32:
+            cmd.append("--no-f32")
+        log("  " + _run(cmd).strip())
+        ident = "".join(c if c.isalnum() else "_" for c in name)
+        for a in algos.split(","):
+            p = os.path.join(GEN, "%s_%s.cu" % (ident, a))
+            if os.path.exists(p):
+                gen_sources.append(p)
+
+    # 3. nvcc (parallel)
+    cuda_sources = gen_sources + [os.path.join(CSRC, "runtime/capi.cu")]
+    with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
+        futs = [ex.submit(_compile_cached, s, BUILD, [NVCC] + NVCCFLAGS, hdr_digest, log) for s in cuda_sources]
+        cuda_objs = [f.result() for f in futs]
+    reg_obj = _compile_cached(os.path.join(CSRC, "runtime/registry.cpp"), BUILD,
+                              [NVCC] + NVCCFLAGS + ["-x", "cu"], hdr_digest, log)
+
+    # 4. link
+    _run([NVCC, "-shared", "-o", LIB, "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", CXX]
+         + cuda_objs + [reg_obj] + host_objs + ["-lcudart"])
+    log("  linked %s" % os.path.relpath(LIB, os.path.join(HERE, "..")))
+    return LIB
+
+
+if __name__ == "__main__":
+    build()

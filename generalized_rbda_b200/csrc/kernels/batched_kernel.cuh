@@ -1,0 +1,203 @@
+// Hand-written kernel shell around the per-model generated algorithm bodies (sm_100a).
+//
+// Mapping: ONE STATE PER THREAD. The generated body is straight-line FP64 (or FP32) code whose
+// control flow is identical for every thread of the grid: topology, cluster-joint types and the
+// loop-closure structure were resolved when the model was compiled, so there is no divergence.
+// The 6x6 / 6n x 6n spatial algebra lives in registers; values that stay live across the
+// backward / forward sweeps of ABA are kept in an explicit per-thread scratch (local memory,
+// interleaved by the hardware so that a warp's access to one slot is two 128-byte lines).
+//
+// Data movement: states are stored contiguously per state (x[b * n + i], the layout of the
+// reference's setState vectors), so a warp's states form ONE contiguous span of 32 * n values.
+// The CTA's tile of every input array is streamed from HBM with coalesced 128-bit loads into
+// shared memory (stage_in), the threads then read their own state from shared memory with an odd
+// stride (bank-conflict free), and results go back the same way (stage_out).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <type_traits>
+
+namespace grbda_kernels
+{
+    struct LaunchArgs
+    {
+        const void *in[3];
+        void *out[3];
+        int64_t batch;
+        cudaStream_t stream;
+    };
+
+    __device__ __forceinline__ void grbda_sincos(double x, double *s, double *c) { sincos(x, s, c); }
+    __device__ __forceinline__ void grbda_sincos(float x, float *s, float *c) { sincosf(x, s, c); }
+
+    // Row stride (in elements) of a staged tile: odd, so that thread t reading element i of its
+    // own state (address t * stride + i) hits 32 distinct banks for 4-byte and 16 distinct bank
+    // pairs per half warp for 8-byte elements.
+    __host__ __device__ constexpr int oddStride(int n) { return n | 1; }
+
+    // Cooperative, coalesced copy of the CTA's [rows x N] tile (global, dense) into shared memory
+    // rows of stride oddStride(N). 128-bit loads when the tile base is 16-byte aligned.
+    template <typename real, int N, int BLOCK>
+    __device__ __forceinline__ void stage_in(const real *__restrict__ g, real *__restrict__ s, int rows)
+    {
+        constexpr int S = oddStride(N);
+        constexpr int VEC = 16 / sizeof(real);
+        const int total = rows * N;
+        if ((reinterpret_cast<uintptr_t>(g) & 15) == 0)
+        {
+            using vec_t = typename std::conditional<sizeof(real) == 8, double2, float4>::type;
+            const vec_t *gv = reinterpret_cast<const vec_t *>(g);
+            const int nvec = total / VEC;
+#pragma unroll 4
+            for (int k = threadIdx.x; k < nvec; k += BLOCK)
+            {
+                const vec_t v = __ldcs(gv + k); // streaming: every byte is read exactly once
+                const real *e = reinterpret_cast<const real *>(&v);
+                const int base = k * VEC;
+#pragma unroll
+                for (int j = 0; j < VEC; j++)
+                {
+                    const int idx = base + j;
+                    s[(idx / N) * S + (idx % N)] = e[j];
+                }
+            }
+            for (int idx = nvec * VEC + threadIdx.x; idx < total; idx += BLOCK)
+                s[(idx / N) * S + (idx % N)] = g[idx];
+        }
+        else
+        {
+            for (int idx = threadIdx.x; idx < total; idx += BLOCK)
+                s[(idx / N) * S + (idx % N)] = g[idx];
+        }
+    }
+
+    // Inverse of stage_in for results.
+    template <typename real, int N, int BLOCK>
+    __device__ __forceinline__ void stage_out(real *__restrict__ g, const real *__restrict__ s, int rows)
+    {
+        constexpr int S = oddStride(N);
+        constexpr int VEC = 16 / sizeof(real);
+        const int total = rows * N;
+        if ((reinterpret_cast<uintptr_t>(g) & 15) == 0)
+        {
+            using vec_t = typename std::conditional<sizeof(real) == 8, double2, float4>::type;
+            vec_t *gv = reinterpret_cast<vec_t *>(g);
+            const int nvec = total / VEC;
+#pragma unroll 4
+            for (int k = threadIdx.x; k < nvec; k += BLOCK)
+            {
+                vec_t v;
+                real *e = reinterpret_cast<real *>(&v);
+                const int base = k * VEC;
+#pragma unroll
+                for (int j = 0; j < VEC; j++)
+                {
+                    const int idx = base + j;
+                    e[j] = s[(idx / N) * S + (idx % N)];
+                }
+                __stcs(gv + k, v);
+            }
+            for (int idx = nvec * VEC + threadIdx.x; idx < total; idx += BLOCK)
+                g[idx] = s[(idx / N) * S + (idx % N)];
+        }
+        else
+        {
+            for (int idx = threadIdx.x; idx < total; idx += BLOCK)
+                g[idx] = s[(idx / N) * S + (idx % N)];
+        }
+    }
+
+    // Shared-memory budget of one CTA: all input tiles plus the tile of output array 0 when it is
+    // small (dynamics: nv values). Large outputs (FK, H) are streamed chunk-wise by the body itself
+    // through OUTk(), see below.
+    template <typename Body, typename real, int BLOCK>
+    struct TileLayout
+    {
+        static constexpr int S0 = Body::N_IN0 ? oddStride(Body::N_IN0) : 0;
+        static constexpr int S1 = Body::N_IN1 ? oddStride(Body::N_IN1) : 0;
+        static constexpr int S2 = Body::N_IN2 ? oddStride(Body::N_IN2) : 0;
+        static constexpr bool STAGE_OUT0 = Body::N_OUT0 <= 64;
+        static constexpr int SO = STAGE_OUT0 ? oddStride(Body::N_OUT0) : 0;
+        static constexpr int OFF1 = S0 * BLOCK;
+        static constexpr int OFF2 = OFF1 + S1 * BLOCK;
+        static constexpr int OFFO = OFF2 + S2 * BLOCK;
+        static constexpr int ELEMS = OFFO + SO * BLOCK;
+        static constexpr size_t BYTES = (size_t)ELEMS * sizeof(real);
+    };
+
+    // One state per thread. Body::run(in0, in1, in2, out0, out1, out2) is generated code.
+    // STAGED = true : inN address the thread's own row of the staged shared-memory tiles and out0
+    //                 the thread's row of the staged output tile (small outputs);
+    // STAGED = false: inN / outN address global memory directly (x + state * n).
+    template <typename real, typename Body, int BLOCK, int MIN_BLOCKS, bool STAGED>
+    __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
+        grbda_batched_kernel(const real *__restrict__ in0, const real *__restrict__ in1,
+                             const real *__restrict__ in2, real *__restrict__ out0,
+                             real *__restrict__ out1, real *__restrict__ out2, int64_t batch)
+    {
+        using L = TileLayout<Body, real, BLOCK>;
+        const int64_t first = (int64_t)blockIdx.x * BLOCK;
+        const int64_t remaining = batch - first;
+        const int rows = remaining < BLOCK ? (int)remaining : BLOCK;
+        const int t = threadIdx.x;
+        const int64_t state = first + t;
+
+        if constexpr (STAGED)
+        {
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            real *smem = reinterpret_cast<real *>(smem_raw);
+            if (Body::N_IN0)
+                stage_in<real, Body::N_IN0 ? Body::N_IN0 : 1, BLOCK>(in0 + first * Body::N_IN0, smem, rows);
+            if (Body::N_IN1)
+                stage_in<real, Body::N_IN1 ? Body::N_IN1 : 1, BLOCK>(in1 + first * Body::N_IN1,
+                                                                    smem + L::OFF1, rows);
+            if (Body::N_IN2)
+                stage_in<real, Body::N_IN2 ? Body::N_IN2 : 1, BLOCK>(in2 + first * Body::N_IN2,
+                                                                    smem + L::OFF2, rows);
+            __syncthreads();
+            if (t < rows)
+            {
+                real *o0 = L::STAGE_OUT0 ? smem + L::OFFO + t * L::SO : out0 + state * Body::N_OUT0;
+                real *o1 = Body::N_OUT1 ? out1 + state * Body::N_OUT1 : nullptr;
+                real *o2 = Body::N_OUT2 ? out2 + state * Body::N_OUT2 : nullptr;
+                Body::template run<real>(smem + t * L::S0, smem + L::OFF1 + t * L::S1,
+                                         smem + L::OFF2 + t * L::S2, o0, o1, o2);
+            }
+            if (L::STAGE_OUT0)
+            {
+                __syncthreads();
+                stage_out<real, Body::N_OUT0 ? Body::N_OUT0 : 1, BLOCK>(out0 + first * Body::N_OUT0,
+                                                                       smem + L::OFFO, rows);
+            }
+        }
+        else
+        {
+            if (t < rows)
+                Body::template run<real>(in0 + state * Body::N_IN0, in1 + state * Body::N_IN1,
+                                         in2 + state * Body::N_IN2, out0 + state * Body::N_OUT0,
+                                         out1 + state * Body::N_OUT1, out2 + state * Body::N_OUT2);
+        }
+    }
+
+    template <typename real, typename Body, int BLOCK, int MIN_BLOCKS, bool STAGED>
+    cudaError_t launchBatched(const LaunchArgs &a)
+    {
+        using L = TileLayout<Body, real, BLOCK>;
+        auto kernel = grbda_batched_kernel<real, Body, BLOCK, MIN_BLOCKS, STAGED>;
+        const size_t smem = STAGED ? L::BYTES : 0;
+        if (smem > 48 * 1024)
+        {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess)
+                return e;
+        }
+        if (a.batch <= 0)
+            return cudaSuccess;
+        const int64_t grid = (a.batch + BLOCK - 1) / BLOCK;
+        kernel<<<(unsigned)grid, BLOCK, smem, a.stream>>>(
+            (const real *)a.in[0], (const real *)a.in[1], (const real *)a.in[2], (real *)a.out[0],
+            (real *)a.out[1], (real *)a.out[2], a.batch);
+        return cudaGetLastError();
+    }
+
+} // namespace grbda_kernels

@@ -1,0 +1,492 @@
+// Implementation of the C ABI declared in include/grbda_cuda.h.
+// Host logic only: model construction / validation, kernel lookup, launches, pinned-memory
+// pipelining for host buffers. All per-state arithmetic happens in the generated sm_100a kernels;
+// there is deliberately no CPU evaluation path.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include "../../../include/grbda_cuda.h"
+#include "../compiler/compile.h"
+#include "../host/robots.h"
+#include "../host/schedule.h"
+#include "registry.h"
+#include "support_kernels.cuh"
+
+using namespace grbda;
+using grbda_runtime::ModelKernels;
+
+struct grbda_model
+{
+    ClusterTreeModel model;
+    uint64_t hash = 0;
+    int device = -1;
+    const ModelKernels *kernels = nullptr;
+    // host-buffer pipeline (grbda_cuda_dynamics_host_f64)
+    std::mutex host_mutex;
+    static constexpr int NSTREAM = 3;
+    cudaStream_t streams[NSTREAM] = {nullptr, nullptr, nullptr};
+    double *dev_buf[NSTREAM] = {nullptr, nullptr, nullptr};
+    int64_t dev_capacity = 0; // states per stream buffer
+};
+
+namespace
+{
+    thread_local std::string g_error;
+    std::atomic<int64_t> g_launches{0};
+
+    grbda_status fail(grbda_status code, const std::string &msg)
+    {
+        g_error = msg;
+        return code;
+    }
+    grbda_status cudaFail(cudaError_t e, const char *what)
+    {
+        return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? GRBDA_ERR_NO_DEVICE : GRBDA_ERR_CUDA,
+                    std::string(what) + ": " + cudaGetErrorString(e));
+    }
+
+    int kernelVariant()
+    {
+        const char *v = std::getenv("GRBDA_KERNEL_VARIANT");
+        const int k = v ? std::atoi(v) : 0;
+        return k >= 0 && k < grbda_runtime::KERNEL_VARIANTS ? k : 0;
+    }
+
+    std::string urdfDirectory()
+    {
+        if (const char *d = std::getenv("GRBDA_URDF_DIR"))
+            return d;
+#ifdef GRBDA_DEFAULT_URDF_DIR
+        return GRBDA_DEFAULT_URDF_DIR;
+#else
+        return "robot-models";
+#endif
+    }
+
+    grbda_status finishCreate(ClusterTreeModel &&m, int device, grbda_model **out)
+    {
+        grbda_model *h = new grbda_model();
+        h->model = std::move(m);
+        h->hash = modelHash(h->model);
+        h->device = device;
+        h->kernels = grbda_runtime::findModelKernels(h->hash);
+        if (device >= 0)
+        {
+            int count = 0;
+            cudaError_t e = cudaGetDeviceCount(&count);
+            if (e != cudaSuccess || device >= count)
+            {
+                delete h;
+                return e != cudaSuccess ? cudaFail(e, "cudaGetDeviceCount")
+                                        : fail(GRBDA_ERR_NO_DEVICE, "device index out of range");
+            }
+            if (!h->kernels)
+            {
+                char buf[256];
+                std::snprintf(buf, sizeof(buf),
+                              "no sm_100a kernels were compiled for this model (hash %016llx); add it to "
+                              "generalized_rbda_b200/build.py and rebuild",
+                              (unsigned long long)h->hash);
+                delete h;
+                return fail(GRBDA_ERR_NOT_COMPILED, buf);
+            }
+        }
+        *out = h;
+        return GRBDA_OK;
+    }
+
+    template <typename F>
+    grbda_status guarded(F f)
+    {
+        try
+        {
+            return f();
+        }
+        catch (const std::exception &e)
+        {
+            return fail(GRBDA_ERR_INVALID_MODEL, e.what());
+        }
+    }
+
+    grbda_status launchAlgo(const grbda_model *m, int algo, bool f32, const void *in0, const void *in1,
+                            const void *in2, void *out0, void *out1, void *out2, int64_t batch, void *stream)
+    {
+        if (!m)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "null model");
+        if (m->device < 0 || !m->kernels)
+            return fail(GRBDA_ERR_NO_DEVICE, "model was created without a CUDA device (host-only handle)");
+        if (batch < 0)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "negative batch");
+        const grbda_runtime::AlgoKernels &ak = m->kernels->algo[algo];
+        int v = kernelVariant();
+        grbda_runtime::LaunchFn fn = f32 ? ak.f32[v] : ak.f64[v];
+        if (!fn)
+            fn = f32 ? ak.f32[0] : ak.f64[0];
+        if (!fn)
+            return fail(GRBDA_ERR_NOT_COMPILED, std::string("kernel '") + compiler::algoName(algo) +
+                                                    (f32 ? "' (f32)" : "' (f64)") +
+                                                    " was not compiled for this model");
+        if (batch == 0)
+            return GRBDA_OK;
+        const void *ins[3] = {in0, in1, in2};
+        void *outs[3] = {out0, out1, out2};
+        for (int i = 0; i < 3; i++)
+        {
+            if (ak.n_in[i] && !ins[i])
+                return fail(GRBDA_ERR_INVALID_ARGUMENT, "null input pointer");
+            if (ak.n_out[i] && !outs[i])
+                return fail(GRBDA_ERR_INVALID_ARGUMENT, "null output pointer");
+        }
+        grbda_kernels::LaunchArgs a;
+        for (int i = 0; i < 3; i++)
+        {
+            a.in[i] = ins[i];
+            a.out[i] = outs[i];
+        }
+        a.batch = batch;
+        a.stream = (cudaStream_t)stream;
+        cudaError_t e = fn(a);
+        if (e != cudaSuccess)
+            return cudaFail(e, "kernel launch");
+        g_launches++;
+        return GRBDA_OK;
+    }
+} // namespace
+
+extern "C"
+{
+    const char *grbda_cuda_last_error_string(void) { return g_error.c_str(); }
+    const char *grbda_cuda_version(void) { return "grbda_cuda 0.1 (sm_100a)"; }
+
+    grbda_status grbda_cuda_model_create(const grbda_schedule *schedule, int device, grbda_model **out)
+    {
+        if (!schedule || !out)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "null argument");
+        return guarded([&] { return finishCreate(fromSchedule(*schedule), device, out); });
+    }
+    grbda_status grbda_cuda_model_create_from_urdf(const char *urdf_path, int device, grbda_model **out)
+    {
+        if (!urdf_path || !out)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "null argument");
+        return guarded([&] { return finishCreate(ClusterTreeModel(std::string(urdf_path)), device, out); });
+    }
+    grbda_status grbda_cuda_model_create_from_robot(const char *name, int device, grbda_model **out)
+    {
+        if (!name || !out)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "null argument");
+        return guarded([&] { return finishCreate(buildRobotByName(name, urdfDirectory()), device, out); });
+    }
+    grbda_status grbda_cuda_model_destroy(grbda_model *m)
+    {
+        if (!m)
+            return GRBDA_OK;
+        for (int i = 0; i < grbda_model::NSTREAM; i++)
+        {
+            if (m->dev_buf[i])
+                cudaFree(m->dev_buf[i]);
+            if (m->streams[i])
+                cudaStreamDestroy(m->streams[i]);
+        }
+        delete m;
+        return GRBDA_OK;
+    }
+
+    int grbda_cuda_num_positions(const grbda_model *m) { return m ? m->model.getNumPositions() : -1; }
+    int grbda_cuda_num_degrees_of_freedom(const grbda_model *m) { return m ? m->model.getNumDegreesOfFreedom() : -1; }
+    int grbda_cuda_num_bodies(const grbda_model *m) { return m ? m->model.getNumBodies() : -1; }
+    int grbda_cuda_num_clusters(const grbda_model *m) { return m ? m->model.getNumClusters() : -1; }
+    uint64_t grbda_cuda_model_hash(const grbda_model *m) { return m ? m->hash : 0; }
+
+    grbda_status grbda_cuda_cluster_info(const grbda_model *m, int cluster, int32_t *info8, char *type_name64)
+    {
+        if (!m || cluster < 0 || cluster >= m->model.getNumClusters() || !info8)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad cluster index");
+        const ClusterTreeNode &c = m->model.clusters()[cluster];
+        info8[0] = c.parent_index_;
+        info8[1] = c.joint_.num_bodies;
+        info8[2] = c.num_positions_;
+        info8[3] = c.num_velocities_;
+        info8[4] = c.position_index_;
+        info8[5] = c.velocity_index_;
+        info8[6] = (int32_t)c.joint_.type;
+        info8[7] = c.first_body_;
+        if (type_name64)
+            std::snprintf(type_name64, 64, "%s", c.joint_.joint_type_name.c_str());
+        return GRBDA_OK;
+    }
+    grbda_status grbda_cuda_body_info(const grbda_model *m, int body, char *name64, int32_t *info4,
+                                      double *E9, double *r3, double *I36)
+    {
+        if (!m || body < 0 || body >= m->model.getNumBodies())
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad body index");
+        const Body &b = m->model.bodies()[body];
+        const int ci = m->model.getIndexOfClusterContainingBody(body);
+        if (name64)
+            std::snprintf(name64, 64, "%s", b.name_.c_str());
+        if (info4)
+        {
+            info4[0] = b.parent_index_;
+            info4[1] = ci;
+            info4[2] = b.sub_index_within_cluster_;
+            info4[3] = (int32_t)m->model.clusters()[ci].joint_.axes[b.sub_index_within_cluster_];
+        }
+        if (E9)
+            std::memcpy(E9, b.Xtree_.E.data(), 72);
+        if (r3)
+            std::memcpy(r3, b.Xtree_.r.data(), 24);
+        if (I36)
+            std::memcpy(I36, b.inertia_.getMatrix().data(), 288);
+        return GRBDA_OK;
+    }
+    grbda_status grbda_cuda_cluster_G(const grbda_model *m, int cluster, double *G)
+    {
+        if (!m || cluster < 0 || cluster >= m->model.getNumClusters() || !G)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad cluster index");
+        const ClusterDesc &d = m->model.clusters()[cluster].joint_;
+        if (d.type != ClusterType::Explicit)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "cluster has no constant G");
+        std::memcpy(G, d.G.data(), d.G.size() * 8);
+        return GRBDA_OK;
+    }
+    grbda_status grbda_cuda_dump_program(const grbda_model *m, int algo, const char *path, int64_t *counts8)
+    {
+        if (!m || algo < 0 || algo >= compiler::ALGO_COUNT)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        return guarded([&]
+                       {
+            const compiler::CompiledAlgo c = compiler::compileAlgo(m->model, algo, false);
+            if (path)
+                compiler::writeTape(c, path);
+            if (counts8)
+            {
+                const compiler::ProgramStats &s = c.stats;
+                const int64_t v[8] = {s.n_nodes, s.n_add, s.n_mul, s.n_div, s.n_sqrt, s.n_sin, s.n_cos, s.n_fusable};
+                std::memcpy(counts8, v, sizeof(v));
+            }
+            return (grbda_status)GRBDA_OK; });
+    }
+
+    // ---- device-pointer hot path -------------------------------------------------------------------
+    grbda_status grbda_cuda_inverse_dynamics_f64(const grbda_model *m, const double *q, const double *yd,
+                                                 const double *ydd, double *tau, int64_t batch, void *stream)
+    {
+        return launchAlgo(m, compiler::ALGO_ID, false, q, yd, ydd, tau, nullptr, nullptr, batch, stream);
+    }
+    grbda_status grbda_cuda_inverse_dynamics_f32(const grbda_model *m, const float *q, const float *yd,
+                                                 const float *ydd, float *tau, int64_t batch, void *stream)
+    {
+        return launchAlgo(m, compiler::ALGO_ID, true, q, yd, ydd, tau, nullptr, nullptr, batch, stream);
+    }
+    grbda_status grbda_cuda_forward_dynamics_f64(const grbda_model *m, const double *q, const double *yd,
+                                                 const double *tau, double *ydd, int64_t batch, void *stream)
+    {
+        return launchAlgo(m, compiler::ALGO_FD, false, q, yd, tau, ydd, nullptr, nullptr, batch, stream);
+    }
+    grbda_status grbda_cuda_forward_dynamics_f32(const grbda_model *m, const float *q, const float *yd,
+                                                 const float *tau, float *ydd, int64_t batch, void *stream)
+    {
+        return launchAlgo(m, compiler::ALGO_FD, true, q, yd, tau, ydd, nullptr, nullptr, batch, stream);
+    }
+    grbda_status grbda_cuda_mass_matrix_f64(const grbda_model *m, const double *q, double *H, int64_t batch,
+                                            void *stream)
+    {
+        return launchAlgo(m, compiler::ALGO_H, false, q, nullptr, nullptr, H, nullptr, nullptr, batch, stream);
+    }
+    grbda_status grbda_cuda_mass_matrix_f32(const grbda_model *m, const float *q, float *H, int64_t batch,
+                                            void *stream)
+    {
+        return launchAlgo(m, compiler::ALGO_H, true, q, nullptr, nullptr, H, nullptr, nullptr, batch, stream);
+    }
+    grbda_status grbda_cuda_forward_kinematics_f64(const grbda_model *m, const double *q, const double *yd,
+                                                   double *p, double *R, double *v, int64_t batch, void *stream)
+    {
+        return launchAlgo(m, compiler::ALGO_FK, false, q, yd, nullptr, p, R, v, batch, stream);
+    }
+    grbda_status grbda_cuda_forward_kinematics_f32(const grbda_model *m, const float *q, const float *yd,
+                                                   float *p, float *R, float *v, int64_t batch, void *stream)
+    {
+        return launchAlgo(m, compiler::ALGO_FK, true, q, yd, nullptr, p, R, v, batch, stream);
+    }
+
+    // ---- host-pointer path: chunks pipelined over three streams --------------------------------------
+    grbda_status grbda_cuda_dynamics_host_f64(const grbda_model *cm, int algo, const double *q, const double *yd,
+                                              const double *in3, double *out, int64_t batch)
+    {
+        grbda_model *m = const_cast<grbda_model *>(cm);
+        if (!m || (algo != 0 && algo != 1) || !q || !yd || !in3 || !out)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        if (m->device < 0 || !m->kernels)
+            return fail(GRBDA_ERR_NO_DEVICE, "model was created without a CUDA device (host-only handle)");
+        std::lock_guard<std::mutex> lock(m->host_mutex);
+        cudaError_t e = cudaSetDevice(m->device);
+        if (e != cudaSuccess)
+            return cudaFail(e, "cudaSetDevice");
+        const int nq = m->model.getNumPositions(), nv = m->model.getNumDegreesOfFreedom();
+        const int64_t per_state = nq + 3 * (int64_t)nv; // doubles
+        const int64_t chunk = 1 << 16;
+        if (m->dev_capacity < chunk)
+        {
+            for (int i = 0; i < grbda_model::NSTREAM; i++)
+            {
+                if (!m->streams[i] && (e = cudaStreamCreateWithFlags(&m->streams[i], cudaStreamNonBlocking)) != cudaSuccess)
+                    return cudaFail(e, "cudaStreamCreate");
+                if (m->dev_buf[i])
+                    cudaFree(m->dev_buf[i]);
+                if ((e = cudaMalloc(&m->dev_buf[i], chunk * per_state * sizeof(double))) != cudaSuccess)
+                    return cudaFail(e, "cudaMalloc");
+            }
+            m->dev_capacity = chunk;
+        }
+        int k = 0;
+        for (int64_t b0 = 0; b0 < batch; b0 += chunk, k++)
+        {
+            const int64_t nb = std::min(chunk, batch - b0);
+            const int s = k % grbda_model::NSTREAM;
+            cudaStream_t st = m->streams[s];
+            double *dq = m->dev_buf[s], *dyd = dq + chunk * nq, *din = dyd + chunk * nv, *dout = din + chunk * nv;
+            if ((e = cudaMemcpyAsync(dq, q + b0 * nq, nb * nq * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(dyd, yd + b0 * nv, nb * nv * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(din, in3 + b0 * nv, nb * nv * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+                return cudaFail(e, "cudaMemcpyAsync H2D");
+            grbda_status rs = launchAlgo(m, algo == 0 ? compiler::ALGO_ID : compiler::ALGO_FD, false, dq, dyd, din,
+                                         dout, nullptr, nullptr, nb, st);
+            if (rs != GRBDA_OK)
+                return rs;
+            if ((e = cudaMemcpyAsync(out + b0 * nv, dout, nb * nv * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+                return cudaFail(e, "cudaMemcpyAsync D2H");
+        }
+        for (int i = 0; i < grbda_model::NSTREAM; i++)
+            if ((e = cudaStreamSynchronize(m->streams[i])) != cudaSuccess)
+                return cudaFail(e, "cudaStreamSynchronize");
+        return GRBDA_OK;
+    }
+
+    // ---- states, checks, measurement -----------------------------------------------------------------
+    grbda_status grbda_cuda_generate_states(const grbda_model *m, uint64_t seed, int64_t first_index,
+                                            int64_t count, double *q, double *yd, double *aux, int32_t *flags,
+                                            void *stream)
+    {
+        if (!m || !q || !yd || !aux || count < 0)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        if (m->device < 0 || !m->kernels)
+            return fail(GRBDA_ERR_NO_DEVICE, "model was created without a CUDA device (host-only handle)");
+        if (!m->kernels->generate)
+            return fail(GRBDA_ERR_NOT_COMPILED, "state generator was not compiled for this model");
+        grbda_runtime::GenArgs a{seed, first_index, count, q, yd, aux, flags, (cudaStream_t)stream};
+        cudaError_t e = m->kernels->generate(a);
+        if (e != cudaSuccess)
+            return cudaFail(e, "generate launch");
+        g_launches++;
+        return GRBDA_OK;
+    }
+
+    grbda_status grbda_cuda_constraint_violation_f64(const grbda_model *m, const double *q, double *max_abs_phi,
+                                                     int64_t batch, void *stream)
+    {
+        if (!m || !q || !max_abs_phi)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        if (m->device < 0 || !m->kernels)
+            return fail(GRBDA_ERR_NO_DEVICE, "model was created without a CUDA device (host-only handle)");
+        cudaStream_t st = (cudaStream_t)stream;
+        const grbda_runtime::AlgoKernels &ak = m->kernels->algo[compiler::ALGO_PHI];
+        if (!ak.f64[0])
+        {
+            // no implicit cluster: violation is zero by definition
+            cudaError_t e = cudaMemsetAsync(max_abs_phi, 0, batch * 8, st);
+            return e == cudaSuccess ? GRBDA_OK : cudaFail(e, "cudaMemsetAsync");
+        }
+        double *phi = nullptr, *Kd = nullptr;
+        cudaError_t e = cudaMallocAsync(&phi, (size_t)batch * ak.n_out[0] * 8, st);
+        if (e != cudaSuccess)
+            return cudaFail(e, "cudaMallocAsync");
+        e = cudaMallocAsync(&Kd, (size_t)batch * ak.n_out[1] * 8, st);
+        if (e != cudaSuccess)
+            return cudaFail(e, "cudaMallocAsync");
+        grbda_status rs = launchAlgo(m, compiler::ALGO_PHI, false, q, nullptr, nullptr, phi, Kd, nullptr, batch, stream);
+        if (rs == GRBDA_OK && batch > 0)
+        {
+            grbda_kernels::rowMaxAbsKernel<<<(unsigned)((batch + 127) / 128), 128, 0, st>>>(phi, ak.n_out[0], batch,
+                                                                                           max_abs_phi);
+            e = cudaGetLastError();
+            if (e != cudaSuccess)
+                rs = cudaFail(e, "rowMaxAbsKernel");
+            g_launches++;
+        }
+        cudaFreeAsync(phi, st);
+        cudaFreeAsync(Kd, st);
+        return rs;
+    }
+
+    grbda_status grbda_cuda_checksum_f64(const double *x, int64_t n, double *out2, void *stream)
+    {
+        if (!x || !out2 || n < 0)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        cudaStream_t st = (cudaStream_t)stream;
+        double *d = nullptr;
+        cudaError_t e = cudaMallocAsync(&d, 16, st);
+        if (e != cudaSuccess)
+            return cudaFail(e, "cudaMallocAsync");
+        cudaMemsetAsync(d, 0, 16, st);
+        if (n > 0)
+        {
+            const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+            grbda_kernels::checksumKernel<<<grid, 256, 0, st>>>(x, n, d);
+            g_launches++;
+        }
+        e = cudaMemcpyAsync(out2, d, 16, cudaMemcpyDeviceToHost, st);
+        cudaFreeAsync(d, st);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(st);
+        return e == cudaSuccess ? GRBDA_OK : cudaFail(e, "checksum");
+    }
+
+    grbda_status grbda_cuda_measure_fma_peak(int device, int fp32, double seconds, double *flops_per_s)
+    {
+        if (!flops_per_s)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "null output");
+        cudaError_t e = cudaSetDevice(device);
+        if (e != cudaSuccess)
+            return cudaFail(e, "cudaSetDevice");
+        cudaDeviceProp prop;
+        cudaGetDeviceProperties(&prop, device);
+        const int grid = prop.multiProcessorCount * 8, block = 256, iters = 4096;
+        void *out = nullptr;
+        cudaMalloc(&out, 64);
+        cudaEvent_t t0, t1;
+        cudaEventCreate(&t0);
+        cudaEventCreate(&t1);
+        double best = 0.0, elapsed = 0.0;
+        for (int rep = 0; rep < 200 && (rep < 5 || elapsed < seconds); rep++)
+        {
+            cudaEventRecord(t0);
+            if (fp32)
+                grbda_kernels::fmaPeakKernel<float><<<grid, block>>>((float *)out, iters, 1.0000001f, 1e-7f);
+            else
+                grbda_kernels::fmaPeakKernel<double><<<grid, block>>>((double *)out, iters, 1.0000001, 1e-7);
+            cudaEventRecord(t1);
+            e = cudaEventSynchronize(t1);
+            if (e != cudaSuccess)
+                break;
+            g_launches++;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, t0, t1);
+            elapsed += ms * 1e-3;
+            const double flops = 2.0 * 64.0 * iters * (double)grid * block;
+            if (rep >= 2)
+                best = std::max(best, flops / (ms * 1e-3));
+        }
+        cudaEventDestroy(t0);
+        cudaEventDestroy(t1);
+        cudaFree(out);
+        if (e != cudaSuccess)
+            return cudaFail(e, "fma peak");
+        *flops_per_s = best;
+        return GRBDA_OK;
+    }
+
+    int64_t grbda_cuda_launch_count(void) { return g_launches.load(); }
+}

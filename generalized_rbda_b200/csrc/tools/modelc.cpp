@@ -1,0 +1,295 @@
+// grbda_modelc — the device-side model compiler as a build-time tool.
+//   grbda_modelc --model NAME --urdf-dir DIR --out DIR [--algos id,fd,fk,h,phi,gen]
+//                [--variants "BLOCK,MINBLOCKS,STAGED;..."] [--no-f32]
+// writes one CUDA translation unit per algorithm (DIR/NAME_<algo>.cu) whose kernels are the
+// straight-line per-state programs of that model, plus DIR/NAME_gen.cu (state generation) and
+// DIR/NAME.json (sizes, hash, operation counts).
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include "../compiler/compile.h"
+#include "../host/robots.h"
+#include "../host/schedule.h"
+
+using namespace grbda;
+using namespace grbda::compiler;
+
+namespace
+{
+    struct Variant
+    {
+        int block, min_blocks, staged;
+    };
+
+    std::vector<std::string> split(const std::string &s, char sep)
+    {
+        std::vector<std::string> out;
+        std::stringstream ss(s);
+        std::string item;
+        while (std::getline(ss, item, sep))
+            if (!item.empty())
+                out.push_back(item);
+        return out;
+    }
+
+    std::string ident(const std::string &name)
+    {
+        std::string s = name;
+        for (char &c : s)
+            if (!isalnum((unsigned char)c))
+                c = '_';
+        return s;
+    }
+
+    void emitBodyStruct(std::ostream &os, const std::string &struct_name, const CompiledAlgo &c)
+    {
+        os << "struct " << struct_name << "\n{\n";
+        os << "    static constexpr int N_IN0 = " << c.n_in[0] << ", N_IN1 = " << c.n_in[1]
+           << ", N_IN2 = " << c.n_in[2] << ";\n";
+        os << "    static constexpr int N_OUT0 = " << c.n_out[0] << ", N_OUT1 = " << c.n_out[1]
+           << ", N_OUT2 = " << c.n_out[2] << ";\n";
+        os << "    template <typename real>\n";
+        os << "    static __device__ __forceinline__ void run(const real *__restrict__ in0, const real "
+              "*__restrict__ in1,\n"
+              "        const real *__restrict__ in2, real *__restrict__ out0, real *__restrict__ out1, "
+              "real *__restrict__ out2)\n    {\n";
+        os << "#define KC(x) ((real)(x))\n#define IN0(i) in0[i]\n#define IN1(i) in1[i]\n#define IN2(i) in2[i]\n"
+              "#define OUT0(i, x) out0[i] = (x)\n#define OUT1(i, x) out1[i] = (x)\n#define OUT2(i, x) out2[i] = (x)\n";
+        os << c.body;
+        os << "#undef KC\n#undef IN0\n#undef IN1\n#undef IN2\n#undef OUT0\n#undef OUT1\n#undef OUT2\n";
+        os << "    }\n};\n";
+    }
+
+    void writeIfChanged(const std::string &path, const std::string &text)
+    {
+        {
+            std::ifstream f(path);
+            if (f)
+            {
+                std::stringstream ss;
+                ss << f.rdbuf();
+                if (ss.str() == text)
+                    return;
+            }
+        }
+        std::ofstream f(path);
+        if (!f)
+            throw std::runtime_error("cannot write " + path);
+        f << text;
+    }
+} // namespace
+
+int main(int argc, char **argv)
+{
+    std::string model_name, urdf_dir = ".", out_dir = ".", algos = "id,fd,fk,h,phi,gen";
+    std::string variants_s = "128,2,1";
+    bool f32 = true;
+    for (int i = 1; i < argc; i++)
+    {
+        const std::string a = argv[i];
+        auto next = [&]() -> std::string
+        {
+            if (i + 1 >= argc)
+            {
+                std::fprintf(stderr, "missing value for %s\n", a.c_str());
+                std::exit(2);
+            }
+            return argv[++i];
+        };
+        if (a == "--model")
+            model_name = next();
+        else if (a == "--urdf-dir")
+            urdf_dir = next();
+        else if (a == "--out")
+            out_dir = next();
+        else if (a == "--algos")
+            algos = next();
+        else if (a == "--variants")
+            variants_s = next();
+        else if (a == "--no-f32")
+            f32 = false;
+        else
+        {
+            std::fprintf(stderr, "unknown argument %s\n", a.c_str());
+            return 2;
+        }
+    }
+    try
+    {
+        std::vector<Variant> variants;
+        for (auto &v : split(variants_s, ';'))
+        {
+            auto p = split(v, ',');
+            if (p.size() != 3)
+                throw std::runtime_error("bad --variants entry '" + v + "'");
+            variants.push_back({std::atoi(p[0].c_str()), std::atoi(p[1].c_str()), std::atoi(p[2].c_str())});
+        }
+        if (variants.empty() || variants.size() > 4)
+            throw std::runtime_error("between 1 and 4 variants are supported");
+
+        const ClusterTreeModel model = buildRobotByName(model_name, urdf_dir);
+        const uint64_t hash = modelHash(model);
+        const std::string id = ident(model_name);
+        const int nq = model.getNumPositions(), nv = model.getNumDegreesOfFreedom();
+        const int nb = model.getNumBodies(), nc = model.getNumClusters();
+
+        std::ostringstream json;
+        json << "{\"model\": \"" << model_name << "\", \"hash\": \"" << std::hex << hash << std::dec
+             << "\", \"nq\": " << nq << ", \"nv\": " << nv << ", \"nb\": " << nb << ", \"nc\": " << nc
+             << ", \"algos\": {";
+        bool first_algo = true;
+
+        const std::string header_common =
+            "// GENERATED by grbda_modelc from model '" + model_name +
+            "' — do not edit. Straight-line per-state program, one state per thread.\n"
+            "#include \"kernels/batched_kernel.cuh\"\n#include \"kernels/stategen.cuh\"\n"
+            "#include \"runtime/registry.h\"\n\nnamespace\n{\nusing namespace grbda_kernels;\n\n";
+
+        for (const std::string &algo : split(algos, ','))
+        {
+            if (algo == "gen")
+                continue;
+            int a = -1;
+            for (int k = 0; k < ALGO_COUNT; k++)
+                if (algo == algoName(k))
+                    a = k;
+            if (a < 0)
+                throw std::runtime_error("unknown algorithm '" + algo + "'");
+            const CompiledAlgo c = compileAlgo(model, a, true);
+            if (a == ALGO_PHI && c.n_out[0] == 0)
+                continue; // no implicit clusters
+            std::ostringstream os;
+            os << header_common;
+            emitBodyStruct(os, "Body", c);
+            os << "} // namespace\n\n";
+            os << "static const grbda_runtime::AlgoKernels k_algo = {\n    {";
+            for (int v = 0; v < 4; v++)
+            {
+                if (v < (int)variants.size())
+                    os << "&launchBatched<double, Body, " << variants[v].block << ", " << variants[v].min_blocks
+                       << ", " << (variants[v].staged ? "true" : "false") << ">";
+                else
+                    os << "nullptr";
+                os << (v < 3 ? ", " : "");
+            }
+            os << "},\n    {";
+            for (int v = 0; v < 4; v++)
+            {
+                if (f32 && v < (int)variants.size())
+                    os << "&launchBatched<float, Body, " << variants[v].block << ", " << variants[v].min_blocks
+                       << ", " << (variants[v].staged ? "true" : "false") << ">";
+                else
+                    os << "nullptr";
+                os << (v < 3 ? ", " : "");
+            }
+            os << "},\n    {" << c.n_in[0] << ", " << c.n_in[1] << ", " << c.n_in[2] << "}, {" << c.n_out[0] << ", "
+               << c.n_out[1] << ", " << c.n_out[2] << "},\n    {" << c.stats.n_nodes << ", " << c.stats.n_add
+               << ", " << c.stats.n_mul << ", " << c.stats.n_div << ", " << c.stats.n_sqrt << ", "
+               << c.stats.n_sin << ", " << c.stats.n_cos << ", " << c.stats.n_fusable << "}};\n";
+            os << "static grbda_runtime::AlgoRegistrar r_algo(0x" << std::hex << hash << std::dec << "ull, \""
+               << model_name << "\", " << nq << ", " << nv << ", " << nb << ", " << nc << ", " << a
+               << ", &k_algo);\n";
+            writeIfChanged(out_dir + "/" + id + "_" + algo + ".cu", os.str());
+
+            json << (first_algo ? "" : ", ") << "\"" << algo << "\": {\"nodes\": " << c.stats.n_nodes
+                 << ", \"add\": " << c.stats.n_add << ", \"mul\": " << c.stats.n_mul
+                 << ", \"div\": " << c.stats.n_div << ", \"sqrt\": " << c.stats.n_sqrt
+                 << ", \"sin\": " << c.stats.n_sin << ", \"cos\": " << c.stats.n_cos
+                 << ", \"fusable\": " << c.stats.n_fusable << ", \"flops\": " << c.stats.flops() << "}";
+            first_algo = false;
+        }
+        json << "}}\n";
+
+        // ---- state generation -------------------------------------------------------------------
+        if (algos.find("gen") != std::string::npos)
+        {
+            std::ostringstream os;
+            os << header_common;
+            // one (phi, Kd) evaluator per implicit cluster
+            for (const ClusterTreeNode &c : model.clusters())
+            {
+                if (c.joint_.type != ClusterType::Implicit)
+                    continue;
+                const ClusterDesc &d = c.joint_;
+                sym::Graph graph;
+                sym::GraphScope scope(graph);
+                ModelCompiler mc(model);
+                std::vector<sym::Sym> q(d.num_bodies), phi, K, Kd;
+                for (int i = 0; i < d.num_bodies; i++)
+                    q[i] = sym::Sym::input(0, i);
+                mc.implicitJacobian(d, q, nullptr, phi, K, nullptr);
+                std::vector<int> ind, dep;
+                for (int i = 0; i < d.num_bodies; i++)
+                    (d.independent[i] ? ind : dep).push_back(i);
+                for (int i = 0; i < d.num_constraints; i++)
+                    for (int j : dep)
+                        Kd.push_back(K[i * d.num_bodies + j]);
+                Program p;
+                p.outputs = {phi, Kd};
+                Emitter em(graph, p);
+                os << "struct Cluster" << c.index_ << "\n{\n    static constexpr int N = " << d.num_bodies
+                   << ", NC = " << d.num_constraints << ";\n";
+                os << "    static __device__ __forceinline__ int ind(int i) { const int t[] = {";
+                for (size_t i = 0; i < ind.size(); i++)
+                    os << ind[i] << (i + 1 < ind.size() ? ", " : "");
+                os << "}; return t[i]; }\n";
+                os << "    static __device__ __forceinline__ int dep(int i) { const int t[] = {";
+                for (size_t i = 0; i < dep.size(); i++)
+                    os << dep[i] << (i + 1 < dep.size() ? ", " : "");
+                os << "}; return t[i]; }\n";
+                os << "    static __device__ __noinline__ void eval(const double *q, double *phi, double *Kd)\n    {\n"
+                      "        typedef double real;\n"
+                      "#define KC(x) ((real)(x))\n#define IN0(i) q[i]\n#define OUT0(i, x) phi[i] = (x)\n"
+                      "#define OUT1(i, x) Kd[i] = (x)\n";
+                os << em.cudaBody();
+                os << "#undef KC\n#undef IN0\n#undef OUT0\n#undef OUT1\n    }\n};\n\n";
+            }
+            os << "struct Gen\n{\n    static constexpr int NQ = " << nq << ", NV = " << nv << ";\n";
+            os << "    static __device__ bool run(Philox &rng, double *q, double *yd, double *aux)\n    {\n"
+                  "        bool ok = true;\n";
+            for (const ClusterTreeNode &c : model.clusters())
+            {
+                const ClusterDesc &d = c.joint_;
+                const int pi = c.position_index_;
+                if (d.type == ClusterType::FreeQuaternion || d.type == ClusterType::FreeRollPitchYaw)
+                {
+                    os << "        for (int i = 0; i < 3; i++) q[" << pi << " + i] = rng.uniform();\n";
+                    os << "        { double rpy[3]; for (int i = 0; i < 3; i++) rpy[i] = rng.uniform();\n";
+                    if (d.type == ClusterType::FreeQuaternion)
+                        os << "          rpyToQuat(rpy, q + " << pi + 3 << "); }\n";
+                    else
+                        os << "          for (int i = 0; i < 3; i++) q[" << pi + 3 << " + i] = rpy[i]; }\n";
+                }
+                else if (d.type == ClusterType::Explicit)
+                    os << "        for (int i = 0; i < " << d.num_positions << "; i++) q[" << pi
+                       << " + i] = rng.uniform();\n";
+                else
+                    os << "        ok = randomImplicitPosition<Cluster" << c.index_ << ">(rng, q + " << pi
+                       << ") && ok;\n";
+            }
+            os << "        for (int i = 0; i < NV; i++) yd[i] = rng.uniform();\n"
+                  "        for (int i = 0; i < NV; i++) aux[i] = rng.uniform();\n        return ok;\n    }\n};\n";
+            os << "} // namespace\n\n";
+            os << "static cudaError_t launchGenerate(const grbda_runtime::GenArgs &a)\n{\n"
+                  "    if (a.count <= 0) return cudaSuccess;\n"
+                  "    const int block = 128;\n"
+                  "    grbda_generate_kernel<Gen><<<(unsigned)((a.count + block - 1) / block), block, 0, a.stream>>>(\n"
+                  "        a.seed, a.first_index, a.count, a.q, a.yd, a.aux, a.flags);\n"
+                  "    return cudaGetLastError();\n}\n";
+            os << "static grbda_runtime::GenRegistrar r_gen(0x" << std::hex << hash << std::dec << "ull, \""
+               << model_name << "\", " << nq << ", " << nv << ", " << nb << ", " << nc << ", &launchGenerate);\n";
+            writeIfChanged(out_dir + "/" + id + "_gen.cu", os.str());
+        }
+        writeIfChanged(out_dir + "/" + id + ".json", json.str());
+        std::printf("%s: hash %016llx nq %d nv %d nb %d nc %d\n", model_name.c_str(), (unsigned long long)hash,
+                    nq, nv, nb, nc);
+    }
+    catch (const std::exception &e)
+    {
+        std::fprintf(stderr, "grbda_modelc: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

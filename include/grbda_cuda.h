@@ -1,0 +1,196 @@
+/* grbda_cuda — C ABI of the B200-native batched ClusterTreeModel dynamics path.
+ *
+ * The reference (ROAM-Lab-ND/generalized_rbda) has no FFI: its boundary is the C++ class
+ * grbda::ClusterTreeModel. Every entry point below names the reference interface it replaces
+ * (paths relative to the reference repository). A maintainer binds the reference to this library
+ * by walking an existing ClusterTreeModel into a grbda_schedule_t (INTEGRATION.md shows the code)
+ * and calling the batched functions instead of looping over setState()/inverseDynamics().
+ *
+ * Conventions
+ *   - every function returns a grbda_status (0 = ok); no exception crosses the boundary; the
+ *     message of the last error of the calling thread is grbda_cuda_last_error_string()
+ *     (the reference throws std::runtime_error, e.g. src/Dynamics/ClusterJoints/ClusterJoint.cpp:41-48);
+ *   - batched arrays hold one state per column, contiguous per state: element i of state b of an
+ *     array with n entries per state is x[b * n + i];
+ *   - q uses the layout of ClusterTreeModel::setState (src/Dynamics/ClusterTreeModel.cpp:256-308):
+ *     concatenation over clusters of num_positions_ entries — [p(3); quat w,x,y,z] for a free
+ *     base, independent angles for explicit clusters, ALL spanning angles for clusters with an
+ *     implicit loop constraint (they must satisfy phi(q) = 0, GenericJoint.cpp:246-249);
+ *     yd / ydd / tau are the independent velocities / accelerations / generalized forces;
+ *   - `_f64` / `_f32` entry points take DEVICE pointers and are asynchronous on `stream`
+ *     (a cudaStream_t passed as void*, NULL = default stream); `_host` entry points take HOST
+ *     pointers, stage through pinned memory and return when the results are in the host buffers;
+ *   - there is no CPU implementation behind this API: without a CUDA device (or without compiled
+ *     kernels for the model) calls fail with GRBDA_ERR_NO_DEVICE / GRBDA_ERR_NOT_COMPILED.
+ */
+#ifndef GRBDA_CUDA_H
+#define GRBDA_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int grbda_status;
+enum
+{
+    GRBDA_OK = 0,
+    GRBDA_ERR_INVALID_ARGUMENT = 1,
+    GRBDA_ERR_INVALID_MODEL = 2,  /* model description violates a ClusterTreeModel rule          */
+    GRBDA_ERR_NOT_COMPILED = 3,   /* no sm_100a kernels were built for this model                */
+    GRBDA_ERR_NO_DEVICE = 4,
+    GRBDA_ERR_CUDA = 5,
+    GRBDA_ERR_IO = 6,
+    GRBDA_ERR_INTERNAL = 7
+};
+
+/* cluster_type values (what the reference's ClusterJoints classes reduce to for the kernels) */
+enum
+{
+    GRBDA_CLUSTER_FREE_QUATERNION = 0, /* ClusterJoints::Free<.., ori_representation::Quaternion>  */
+    GRBDA_CLUSTER_FREE_RPY = 1,        /* ClusterJoints::Free<.., ori_representation::RollPitchYaw> */
+    GRBDA_CLUSTER_EXPLICIT = 2,        /* Revolute, RevoluteWithRotor, RevolutePair(WithRotor),
+                                          RevoluteTripleWithRotor, Generic + LoopConstraint::Static */
+    GRBDA_CLUSTER_IMPLICIT = 3         /* Generic + LoopConstraint::GenericImplicit / FourBar       */
+};
+
+/* One op of the straight-line program of an implicit constraint phi(q_spanning).
+ * op: 0 const(val) 1 input(b = spanning coordinate) 2 add 3 sub 4 mul 5 div 6 neg 7 sin 8 cos;
+ * a, b index earlier ops of the same cluster's program. Replaces the casadi::SX lambda handed to
+ * LoopConstraint::GenericImplicit (include/grbda/Dynamics/ClusterJoints/GenericJoint.h). */
+typedef struct grbda_phi_op
+{
+    int32_t op, a, b;
+    double val;
+} grbda_phi_op;
+
+/* Flattened structure-of-arrays topology schedule of one ClusterTreeModel.
+ * Replaces: Body (include/grbda/Dynamics/Body.h:12-43), ClusterTreeNode / TreeNode
+ * (Nodes/ClusterTreeNode.h:12-55, Nodes/TreeNode.h:16-75) and the per-type ClusterJoints data.
+ * Bodies are listed in registration order (= body index); the bodies of a cluster are contiguous.
+ * All arrays are caller-owned and copied by grbda_cuda_model_create. */
+typedef struct grbda_schedule
+{
+    int32_t num_bodies;
+    int32_t num_clusters;
+    double gravity[3];                  /* TreeModel::setGravity, TreeModel.h:56                  */
+
+    /* per body */
+    const int32_t *body_parent;         /* Body::parent_index_, -1 = ground                       */
+    const int32_t *body_joint_axis;     /* 0/1/2 = ori::CoordinateAxis X/Y/Z (ignored for free)   */
+    const double *body_xtree_E;         /* 9 per body, row-major rotation of Body::Xtree_         */
+    const double *body_xtree_r;         /* 3 per body, translation of Body::Xtree_                */
+    const double *body_inertia;         /* 36 per body, row-major SpatialInertia::getMatrix()     */
+    const uint8_t *body_independent;    /* implicit clusters: 1 = independent spanning coordinate */
+
+    /* per cluster */
+    const int32_t *cluster_type;        /* GRBDA_CLUSTER_*                                        */
+    const int32_t *cluster_num_bodies;
+    const int32_t *cluster_num_independent; /* ClusterJoints::Base::numVelocities()               */
+    const int32_t *cluster_G_offset;    /* explicit: offset into G_values of the row-major
+                                           (num_bodies x num_independent) LoopConstraint G        */
+    const double *G_values;
+    const int32_t *cluster_phi_offset;  /* implicit: first op of the cluster's phi program        */
+    const int32_t *cluster_phi_count;   /* implicit: number of ops                                */
+    const int32_t *cluster_phi_out_offset; /* implicit: offset into phi_outputs                   */
+    const int32_t *cluster_num_constraints;
+    const grbda_phi_op *phi_ops;
+    const int32_t *phi_outputs;         /* op index (within the cluster program) of each phi row  */
+} grbda_schedule;
+
+typedef struct grbda_model grbda_model; /* opaque; immutable after creation; one per device       */
+
+const char *grbda_cuda_last_error_string(void);
+const char *grbda_cuda_version(void);
+
+/* ---- model creation ------------------------------------------------------------------------ */
+/* From a schedule. Replaces the registerBody / appendRegisteredBodiesAsCluster construction
+ * sequence, src/Dynamics/ClusterTreeModel.cpp:9-67. device < 0: host-only handle (introspection). */
+grbda_status grbda_cuda_model_create(const grbda_schedule *schedule, int device, grbda_model **out);
+/* From a URDF+ file. Replaces ClusterTreeModel(const std::string &urdf_filename),
+ * include/grbda/Dynamics/ClusterTreeModel.h:33-46 + src/Dynamics/ClusterTreeParsing.cpp. */
+grbda_status grbda_cuda_model_create_from_urdf(const char *urdf_path, int device, grbda_model **out);
+/* From one of the reference's robot classes (include/grbda/Robots): "tello", "tello_with_arms",
+ * "mini_cheetah", "mit_humanoid", "revolute_chain_with_rotor_<N>",
+ * "revolute_pair_chain_with_rotor_<N>", or a URDF name from robot-models ("four_bar", ...). */
+grbda_status grbda_cuda_model_create_from_robot(const char *name, int device, grbda_model **out);
+grbda_status grbda_cuda_model_destroy(grbda_model *model);
+
+/* ---- introspection (TreeModel.h:25-28, ClusterTreeModel.h:97,151-153) ---------------------- */
+int grbda_cuda_num_positions(const grbda_model *m);          /* getNumPositions()                 */
+int grbda_cuda_num_degrees_of_freedom(const grbda_model *m); /* getNumDegreesOfFreedom()          */
+int grbda_cuda_num_bodies(const grbda_model *m);             /* getNumBodies()                    */
+int grbda_cuda_num_clusters(const grbda_model *m);           /* clusters().size()                 */
+uint64_t grbda_cuda_model_hash(const grbda_model *m);
+/* cluster: info[8] = {parent, num_bodies, num_positions, num_velocities, position_index,
+ * velocity_index, cluster_type, first_body}; type_name64: ClusterJoints class name. */
+grbda_status grbda_cuda_cluster_info(const grbda_model *m, int cluster, int32_t *info8, char *type_name64);
+/* body: info[4] = {parent, cluster, sub_index_within_cluster, joint_axis} */
+grbda_status grbda_cuda_body_info(const grbda_model *m, int body, char *name64, int32_t *info4,
+                                  double *xtree_E9, double *xtree_r3, double *inertia36);
+/* explicit cluster: G (num_bodies x num_independent, row-major) */
+grbda_status grbda_cuda_cluster_G(const grbda_model *m, int cluster, double *G);
+/* Emitted program of one algorithm (0 ID, 1 FD, 2 FK, 3 H, 4 phi/Kd) written as a binary tape to
+ * `path` (format: csrc/compiler/compile.h); counts[8] = {nodes, add, mul, div, sqrt, sin, cos,
+ * fusable mul+add pairs} of the straight-line program each thread executes. */
+grbda_status grbda_cuda_dump_program(const grbda_model *m, int algo, const char *path, int64_t *counts8);
+
+/* ---- batched hot path, device pointers ----------------------------------------------------- */
+/* tau = ID(q, yd, ydd). Replaces setState + ClusterTreeModel::inverseDynamics(ydd),
+ * src/Dynamics/ClusterTreeDynamics.cpp:79-83 -> TreeModel.cpp:174-212. */
+grbda_status grbda_cuda_inverse_dynamics_f64(const grbda_model *m, const double *q, const double *yd,
+                                             const double *ydd, double *tau, int64_t batch, void *stream);
+grbda_status grbda_cuda_inverse_dynamics_f32(const grbda_model *m, const float *q, const float *yd,
+                                             const float *ydd, float *tau, int64_t batch, void *stream);
+/* ydd = FD(q, yd, tau). Replaces setState + ClusterTreeModel::forwardDynamics(tau),
+ * src/Dynamics/ClusterTreeDynamics.cpp:85-191. */
+grbda_status grbda_cuda_forward_dynamics_f64(const grbda_model *m, const double *q, const double *yd,
+                                             const double *tau, double *ydd, int64_t batch, void *stream);
+grbda_status grbda_cuda_forward_dynamics_f32(const grbda_model *m, const float *q, const float *yd,
+                                             const float *tau, float *ydd, int64_t batch, void *stream);
+/* H (nv x nv per state, symmetric). Replaces setState + getMassMatrix(),
+ * src/Dynamics/ClusterTreeModel.cpp:98-103 -> TreeModel.cpp:116-160. */
+grbda_status grbda_cuda_mass_matrix_f64(const grbda_model *m, const double *q, double *H, int64_t batch,
+                                        void *stream);
+grbda_status grbda_cuda_mass_matrix_f32(const grbda_model *m, const float *q, float *H, int64_t batch,
+                                        void *stream);
+/* Per state and body: p[3] world position of the body origin (getPosition), R[9] row-major
+ * body-to-world rotation (getOrientation), v[6] = [world angular velocity; world linear velocity of
+ * the origin] (getAngularVelocity, getLinearVelocity). Replaces setState + forwardKinematics() +
+ * getters, TreeModel.cpp:7-32, ClusterTreeModel.cpp:319-373. */
+grbda_status grbda_cuda_forward_kinematics_f64(const grbda_model *m, const double *q, const double *yd,
+                                               double *p, double *R, double *v, int64_t batch, void *stream);
+grbda_status grbda_cuda_forward_kinematics_f32(const grbda_model *m, const float *q, const float *yd,
+                                               float *p, float *R, float *v, int64_t batch, void *stream);
+
+/* ---- batched hot path, host pointers (H2D, kernel, D2H pipelined over pinned staging) -------- */
+/* algo: 0 ID (in3 = ydd, out = tau), 1 FD (in3 = tau, out = ydd) */
+grbda_status grbda_cuda_dynamics_host_f64(const grbda_model *m, int algo, const double *q, const double *yd,
+                                          const double *in3, double *out, int64_t batch);
+
+/* ---- synthetic states, checks, measurement --------------------------------------------------- */
+/* Random valid states for global state indices [first_index, first_index + count): counter based
+ * (Philox4x32-10), so a shard is reproducible whatever the GPU count. Ranges follow
+ * ClusterJoints::Base::randomJointState (ClusterJoint.cpp:74-81), Free (FreeJoint.cpp:49-60) and
+ * Generic (GenericJoint.cpp:290-385: Newton solve of phi for the dependent coordinates).
+ * aux receives nv uniform [-1,1) values (ydd or tau). flags (optional, int32 per state) is set to
+ * 1 for states whose implicit clusters could not be solved. */
+grbda_status grbda_cuda_generate_states(const grbda_model *m, uint64_t seed, int64_t first_index,
+                                        int64_t count, double *q, double *yd, double *aux,
+                                        int32_t *flags, void *stream);
+/* max |phi| over the implicit clusters of each state (isValidSpanningPosition, LoopConstraint.cpp:15-20) */
+grbda_status grbda_cuda_constraint_violation_f64(const grbda_model *m, const double *q, double *max_abs_phi,
+                                                 int64_t batch, void *stream);
+/* out[0] = sum x_i, out[1] = sum |x_i| in double (device pointer x, host pointer out; synchronises) */
+grbda_status grbda_cuda_checksum_f64(const double *x, int64_t n, double *out2, void *stream);
+/* Achieved FP64 FMA throughput (FLOP/s, FMA = 2) and FP32 of the device with a dependent-free
+ * FMA loop over all SMs; the roofline denominator for ID / FD. */
+grbda_status grbda_cuda_measure_fma_peak(int device, int fp32, double seconds, double *flops_per_s);
+/* Kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t grbda_cuda_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRBDA_CUDA_H */

@@ -1,0 +1,133 @@
+"""CPU tests of the product's host logic (no GPU): model construction, schedule round trip, the
+device-side model compiler (its emitted programs are replayed by tests/tape.py and compared with
+the oracle), and the C-ABI surface."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tape import load_tape, run_tape
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# product robot name -> oracle robot name
+ROBOTS = {"tello": "tello", "tello_with_arms": "tello_with_arms",
+          "revolute_chain_with_rotor_2": "revolute_chain_with_rotor_2",
+          "revolute_chain_with_rotor_4": "revolute_chain_with_rotor_4",
+          "revolute_pair_chain_with_rotor_2": "revolute_pair_chain_with_rotor_2",
+          "revolute_pair_chain_with_rotor_4": "revolute_pair_chain_with_rotor_4"}
+TOL = 1e-10  # north_star: <= 1e-10 relative in FP64
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(1e-300, np.abs(b).max())
+
+
+def test_c_abi_exports_every_declared_symbol(grbda):
+    header = open(os.path.join(ROOT, "include", "grbda_cuda.h")).read()
+    declared = set(re.findall(r"\b(grbda_cuda_[A-Za-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = C.CDLL(grbda.library_path())
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), "libgrbda_cuda.so does not export " + sym
+    assert declared == set(grbda.EXPORTED_SYMBOLS)
+
+
+def test_no_cpu_fallback_without_device(grbda):
+    """Host-only handles refuse compute calls; unknown models refuse to be created on a device."""
+    m = grbda.ClusterTreeModel.from_robot("tello", device=None)
+    st = grbda.lib().grbda_cuda_inverse_dynamics_f64(m._h, None, None, None, None, 1, None)
+    assert st == 4  # GRBDA_ERR_NO_DEVICE
+    with pytest.raises(grbda.GrbdaError):
+        grbda.ClusterTreeModel.from_robot("no_such_robot", device=None)
+
+
+@pytest.mark.parametrize("robot", sorted(ROBOTS))
+def test_topology_matches_oracle(grbda, oracle, robot):
+    m = grbda.ClusterTreeModel.from_robot(robot, device=None)
+    o = oracle.OracleModel(ROBOTS[robot])
+    assert (m.nq, m.nv, m.nb, m.nc) == (o.nq, o.nv, o.nb, o.nc)
+    for a, b in zip(m.clusters(), o.clusters()):
+        for k in ("parent", "num_bodies", "num_positions", "num_velocities", "position_index", "velocity_index"):
+            assert a[k] == b[k]
+        assert (a["type"] == 3) == bool(b["implicit"])
+    for a, b in zip(m.bodies(), o.bodies()):
+        assert a["parent"] == b["parent"] and a["cluster"] == b["cluster"] and a["sub_index"] == b["sub_index"]
+        assert np.abs(a["E"] - b["E"]).max() < 1e-15 and np.abs(a["r"] - b["r"]).max() < 1e-15
+        assert np.abs(a["inertia"] - b["inertia"]).max() < 1e-15
+
+
+@pytest.mark.parametrize("robot", sorted(ROBOTS))
+def test_emitted_programs_match_oracle(grbda, oracle, robot, tmp_path):
+    """The straight-line programs the kernels execute, replayed in numpy, against the oracle."""
+    m = grbda.ClusterTreeModel.from_robot(robot, device=None)
+    o = oracle.OracleModel(ROBOTS[robot])
+    q, yd, aux = o.generate_states(48, seed=7)
+    tapes = {}
+    for algo, name in enumerate(grbda.ALGO_NAMES):
+        path = str(tmp_path / (name + ".tape"))
+        counts = m.dump_program(algo, path)
+        tapes[name] = load_tape(path)
+        assert counts["nodes"] == len(tapes[name]["op"])
+    ins = [q, yd, aux]
+    assert rel(run_tape(tapes["id"], ins)[0], o.inverse_dynamics(q, yd, aux)) < TOL
+    assert rel(run_tape(tapes["fd"], ins)[0], o.forward_dynamics(q, yd, aux)) < TOL
+    assert rel(run_tape(tapes["h"], ins)[0].reshape(-1, o.nv, o.nv), o.mass_matrix(q)) < TOL
+    p, R, v = o.forward_kinematics(q, yd)
+    fk = run_tape(tapes["fk"], ins)
+    assert rel(fk[0].reshape(p.shape), p) < TOL and rel(fk[1].reshape(R.shape), R) < TOL
+    assert rel(fk[2].reshape(v.shape), v) < TOL
+    phi = run_tape(tapes["phi"], ins)[0]
+    if phi.shape[1]:
+        assert np.abs(phi).max() < 1e-8  # generated states satisfy the loop constraints
+
+
+def test_schedule_round_trip(grbda):
+    """model -> grbda_schedule -> grbda_cuda_model_create reproduces the same model (same hash)."""
+    import struct
+    m = grbda.ClusterTreeModel.from_robot("tello", device=None)
+    clusters, bodies = m.clusters(), m.bodies()
+
+    class PhiOp(C.Structure):
+        _fields_ = [("op", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("val", C.c_double)]
+
+    class Schedule(C.Structure):
+        _fields_ = [("num_bodies", C.c_int32), ("num_clusters", C.c_int32), ("gravity", C.c_double * 3),
+                    ("body_parent", C.c_void_p), ("body_joint_axis", C.c_void_p), ("body_xtree_E", C.c_void_p),
+                    ("body_xtree_r", C.c_void_p), ("body_inertia", C.c_void_p), ("body_independent", C.c_void_p),
+                    ("cluster_type", C.c_void_p), ("cluster_num_bodies", C.c_void_p),
+                    ("cluster_num_independent", C.c_void_p), ("cluster_G_offset", C.c_void_p),
+                    ("G_values", C.c_void_p), ("cluster_phi_offset", C.c_void_p), ("cluster_phi_count", C.c_void_p),
+                    ("cluster_phi_out_offset", C.c_void_p), ("cluster_num_constraints", C.c_void_p),
+                    ("phi_ops", C.c_void_p), ("phi_outputs", C.c_void_p)]
+
+    # explicit clusters only can be rebuilt from the introspection API; use a chain for the full trip
+    m = grbda.ClusterTreeModel.from_robot("revolute_pair_chain_with_rotor_4", device=None)
+    clusters, bodies = m.clusters(), m.bodies()
+    i32 = lambda x: np.ascontiguousarray(x, dtype=np.int32)
+    f64 = lambda x: np.ascontiguousarray(x, dtype=np.float64)
+    arrs = dict(
+        body_parent=i32([b["parent"] for b in bodies]), body_joint_axis=i32([b["axis"] for b in bodies]),
+        body_xtree_E=f64([b["E"] for b in bodies]), body_xtree_r=f64([b["r"] for b in bodies]),
+        body_inertia=f64([b["inertia"] for b in bodies]),
+        body_independent=np.ones(len(bodies), dtype=np.uint8),
+        cluster_type=i32([c["type"] for c in clusters]), cluster_num_bodies=i32([c["num_bodies"] for c in clusters]),
+        cluster_num_independent=i32([c["num_velocities"] for c in clusters]),
+        cluster_G_offset=i32(np.cumsum([0] + [c["G"].size for c in clusters])[:-1]),
+        G_values=f64(np.concatenate([c["G"].ravel() for c in clusters])),
+        cluster_phi_offset=i32([0] * len(clusters)), cluster_phi_count=i32([0] * len(clusters)),
+        cluster_phi_out_offset=i32([0] * len(clusters)), cluster_num_constraints=i32([2] * len(clusters)),
+        phi_ops=np.zeros(1), phi_outputs=i32([0]))
+    s = Schedule()
+    s.num_bodies, s.num_clusters = len(bodies), len(clusters)
+    s.gravity[:] = [9.81, 0.0, 0.0]
+    for k, v in arrs.items():
+        setattr(s, k, v.ctypes.data)
+    m2 = grbda.ClusterTreeModel.from_schedule(C.byref(s), device=None)
+    assert m2.hash == m.hash
+    assert (m2.nq, m2.nv, m2.nb, m2.nc) == (m.nq, m.nv, m.nb, m.nc)
+    # a schedule that breaks a ClusterTreeModel rule is rejected with a status, not a crash
+    arrs["body_parent"][1] = 5
+    with pytest.raises(grbda.GrbdaError):
+        grbda.ClusterTreeModel.from_schedule(C.byref(s), device=None)

@@ -1,0 +1,152 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Every call goes through the C ABI
+(generalized_rbda_b200 -> libgrbda_cuda.so); results are compared with the CPU oracle on the same
+seeded states. Tolerances: <= 1e-10 relative (FP64), <= 1e-4 (FP32 variant) — BASELINE.json north_star."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROBOTS = {"tello": "tello", "tello_with_arms": "tello_with_arms",
+          "revolute_chain_with_rotor_2": "revolute_chain_with_rotor_2",
+          "revolute_chain_with_rotor_4": "revolute_chain_with_rotor_4",
+          "revolute_pair_chain_with_rotor_2": "revolute_pair_chain_with_rotor_2",
+          "revolute_pair_chain_with_rotor_4": "revolute_pair_chain_with_rotor_4"}
+TOL64, TOL32 = 1e-10, 1e-4
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(1e-300, np.abs(b).max())
+
+
+def relrows(a, b):
+    """largest per-state relative error (each state normalised by its own largest entry)"""
+    a, b = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
+    return (np.abs(a - b).max(1) / np.maximum(1e-300, np.abs(b).max(1))).max()
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.mark.parametrize("robot", sorted(ROBOTS))
+def test_state_generator_matches_oracle(grbda, oracle, torch, robot):
+    m = grbda.ClusterTreeModel.from_robot(robot)
+    o = oracle.OracleModel(ROBOTS[robot])
+    q, yd, aux, flags = m.generateStates(777, seed=123, first_index=1000)
+    assert int(flags.sum()) == 0
+    qo, ydo, auxo = o.generate_states(777, seed=123, first_index=1000)
+    assert np.array_equal(yd.cpu().numpy(), ydo) and np.array_equal(aux.cpu().numpy(), auxo)
+    # positions: identical draws; implicit clusters go through Newton on both sides
+    close = np.abs(q.cpu().numpy() - qo).max(1) < 1e-9
+    assert close.mean() > 0.99
+    assert float(m.constraintViolation(q).max()) < 1e-8
+    assert o.validate_states(q.cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("robot", sorted(ROBOTS))
+def test_dynamics_parity_f64(grbda, oracle, torch, robot):
+    m = grbda.ClusterTreeModel.from_robot(robot)
+    o = oracle.OracleModel(ROBOTS[robot])
+    B = 1000  # not a multiple of the CTA size: exercises the ragged last tile
+    q, yd, aux, _ = m.generateStates(B, seed=42)
+    qn, ydn, auxn = q.cpu().numpy(), yd.cpu().numpy(), aux.cpu().numpy()
+    assert relrows(m.inverseDynamics(q, yd, aux).cpu().numpy(), o.inverse_dynamics(qn, ydn, auxn)) < TOL64
+    assert relrows(m.forwardDynamics(q, yd, aux).cpu().numpy(), o.forward_dynamics(qn, ydn, auxn)) < TOL64
+    assert relrows(m.getMassMatrix(q).cpu().numpy(), o.mass_matrix(qn)) < TOL64
+    p, R, v = m.forwardKinematics(q, yd)
+    po, Ro, vo = o.forward_kinematics(qn, ydn)
+    assert rel(p.cpu().numpy(), po) < TOL64 and rel(R.cpu().numpy(), Ro) < TOL64 and rel(v.cpu().numpy(), vo) < TOL64
+    C = m.getBiasForceVector(q, yd).cpu().numpy()
+    assert relrows(C, o.inverse_dynamics(qn, ydn, np.zeros_like(ydn))) < TOL64
+
+
+@pytest.mark.parametrize("robot", ["tello_with_arms", "revolute_chain_with_rotor_2"])
+def test_dynamics_parity_f32(grbda, oracle, torch, robot):
+    """FP32 variant against the FP64 oracle on float-rounded states."""
+    m = grbda.ClusterTreeModel.from_robot(robot)
+    o = oracle.OracleModel(ROBOTS[robot])
+    q, yd, aux, _ = m.generateStates(512, seed=4)
+    q32, yd32, aux32 = q.float(), yd.float(), aux.float()
+    qn, ydn, auxn = (x.double().cpu().numpy() for x in (q32, yd32, aux32))
+    # well conditioned comparison: ID and H (FD amplifies rounding by cond(H))
+    assert relrows(m.inverseDynamics(q32, yd32, aux32).double().cpu().numpy(), o.inverse_dynamics(qn, ydn, auxn)) < TOL32
+    assert relrows(m.getMassMatrix(q32).double().cpu().numpy(), o.mass_matrix(qn)) < TOL32
+    ydd32 = m.forwardDynamics(q32, yd32, aux32).double().cpu().numpy()
+    ydd = o.forward_dynamics(qn, ydn, auxn)
+    # FD: residual form, tau recovered from the FP32 accelerations
+    tau_back = o.inverse_dynamics(qn, ydn, ydd32)
+    assert relrows(tau_back, auxn) < 5e-3
+    assert np.median(np.abs(ydd32 - ydd).max(1) / np.abs(ydd).max(1)) < TOL32 * 50
+
+
+def test_golden_vectors_on_gpu(grbda, torch):
+    """The reference's own generated closed-form dynamics (tests/golden/codegen_kat.json)."""
+    kat = json.load(open(os.path.join(HERE, "golden", "codegen_kat.json")))
+    for case in kat["cases"]:
+        m = grbda.ClusterTreeModel.from_robot(case["robot"])
+        y = torch.tensor([s["y"] for s in case["states"]], dtype=torch.float64, device="cuda")
+        yd = torch.tensor([s["yd"] for s in case["states"]], dtype=torch.float64, device="cuda")
+        tau = torch.tensor([s["tau"] for s in case["states"]], dtype=torch.float64, device="cuda")
+        ydd_ref = np.array([s["ydd_fwd"] for s in case["states"]])
+        tau_ref = np.array([s["tau_inv_of_ydd"] for s in case["states"]])
+        assert relrows(m.forwardDynamics(y, yd, tau).cpu().numpy(), ydd_ref) < TOL64
+        ydd = torch.tensor(ydd_ref, dtype=torch.float64, device="cuda")
+        assert relrows(m.inverseDynamics(y, yd, ydd).cpu().numpy(), tau_ref) < TOL64
+
+
+def test_full_size_round_trip_and_sharding(grbda, torch):
+    """BASELINE size (2^20 Tello states): ID(FD(tau)) = tau; shards reproduce the global batch."""
+    m = grbda.ClusterTreeModel.from_robot("tello_with_arms")
+    B = 1 << 20
+    q, yd, tau, flags = m.generateStates(B)
+    assert int(flags.sum()) == 0
+    ydd = m.forwardDynamics(q, yd, tau)
+    tau2 = m.inverseDynamics(q, yd, ydd)
+    err = ((tau2 - tau).abs().amax(1) / tau.abs().amax(1))
+    assert float(err.max()) < 1e-6 and float(err.median()) < 1e-11
+    H = m.getMassMatrix(q[:4096])
+    C = m.getBiasForceVector(q[:4096], yd[:4096])
+    res = torch.einsum("bij,bj->bi", H, ydd[:4096]) + C - tau[:4096]
+    assert float((res.abs().amax(1) / tau[:4096].abs().amax(1)).median()) < 1e-10
+    # two half shards generated independently == the global batch; checksums add up
+    qa, yda, ta, _ = m.generateStates(B // 2, first_index=0)
+    qb, ydb, tb, _ = m.generateStates(B // 2, first_index=B // 2)
+    assert torch.equal(torch.cat([qa, qb]), q) and torch.equal(torch.cat([ta, tb]), tau)
+    ya = m.forwardDynamics(qa, yda, ta)
+    yb = m.forwardDynamics(qb, ydb, tb)
+    assert torch.equal(torch.cat([ya, yb]), ydd)
+    sa, sb, s = grbda.checksum(ya), grbda.checksum(yb), grbda.checksum(ydd)
+    assert abs(sa[1] + sb[1] - s[1]) <= 1e-9 * s[1]
+
+
+def test_host_buffer_path(grbda, oracle, torch):
+    m = grbda.ClusterTreeModel.from_robot("tello_with_arms")
+    o = oracle.OracleModel("tello_with_arms")
+    B = 70000  # more than one pipeline chunk
+    q, yd, tau, _ = m.generateStates(B, seed=8)
+    qh, ydh, tauh = (x.cpu().pin_memory() for x in (q, yd, tau))
+    out = torch.empty((B, m.nv), dtype=torch.float64).pin_memory()
+    m.dynamics_host(1, qh, ydh, tauh, out)
+    assert torch.equal(out, m.forwardDynamics(q, yd, tau).cpu())
+    sel = slice(0, 256)
+    assert relrows(out[sel].numpy(), o.forward_dynamics(qh[sel].numpy(), ydh[sel].numpy(), tauh[sel].numpy())) < TOL64
+    m.dynamics_host(0, qh, ydh, out.clone(), out)
+    assert relrows(out[sel].numpy(), tauh[sel].numpy()) < 1e-6
+
+
+def test_empty_and_error_paths(grbda, torch):
+    m = grbda.ClusterTreeModel.from_robot("tello")
+    q = torch.zeros((0, m.nq), dtype=torch.float64, device="cuda")
+    yd = torch.zeros((0, m.nv), dtype=torch.float64, device="cuda")
+    assert m.forwardDynamics(q, yd, yd).shape == (0, m.nv)
+    with pytest.raises(ValueError):
+        m.forwardDynamics(torch.zeros((4, m.nq + 1), dtype=torch.float64, device="cuda"), yd, yd)
+    with pytest.raises(grbda.GrbdaError):
+        grbda.ClusterTreeModel.from_robot("tello", device=99)
