@@ -47,6 +47,7 @@ _lib.grbda_cuda_cluster_info.argtypes = [_vp, C.c_int, _vp, _vp]
 _lib.grbda_cuda_body_info.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]
 _lib.grbda_cuda_cluster_G.argtypes = [_vp, C.c_int, _vp]
 _lib.grbda_cuda_dump_program.argtypes = [_vp, C.c_int, C.c_char_p, _vp]
+_lib.grbda_cuda_dump_role_program.argtypes = [_vp, C.c_int, C.c_char_p, _vp]
 for _p in ("f64", "f32"):
     getattr(_lib, "grbda_cuda_inverse_dynamics_" + _p).argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp]
     getattr(_lib, "grbda_cuda_forward_dynamics_" + _p).argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp]
@@ -63,7 +64,7 @@ EXPORTED_SYMBOLS = [
     "grbda_cuda_model_create_from_urdf", "grbda_cuda_model_create_from_robot", "grbda_cuda_model_destroy",
     "grbda_cuda_num_positions", "grbda_cuda_num_degrees_of_freedom", "grbda_cuda_num_bodies",
     "grbda_cuda_num_clusters", "grbda_cuda_model_hash", "grbda_cuda_cluster_info", "grbda_cuda_body_info",
-    "grbda_cuda_cluster_G", "grbda_cuda_dump_program",
+    "grbda_cuda_cluster_G", "grbda_cuda_dump_program", "grbda_cuda_dump_role_program",
     "grbda_cuda_inverse_dynamics_f64", "grbda_cuda_inverse_dynamics_f32",
     "grbda_cuda_forward_dynamics_f64", "grbda_cuda_forward_dynamics_f32",
     "grbda_cuda_mass_matrix_f64", "grbda_cuda_mass_matrix_f32",
@@ -145,7 +146,7 @@ class ClusterTreeModel:
         return cls(h, device)
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:
             _lib.grbda_cuda_model_destroy(self._h)
             self._h = None
 
@@ -207,6 +208,11 @@ class ClusterTreeModel:
         d = dict(zip(keys, [int(x) for x in counts]))
         d["flops"] = d["add"] + d["mul"] + d["div"] + d["sqrt"]
         return d
+
+    def dump_role_program(self, algo, path=None):
+        info = (C.c_int64 * 4)()
+        _check(_lib.grbda_cuda_dump_role_program(self._h, algo, path.encode() if path else None, info))
+        return dict(W=int(info[0]), slots=int(info[1]), max_role_flops=int(info[2]), sum_role_flops=int(info[3]))
 
     # ---- batched hot path (device tensors) ----------------------------------------------------
     def _prep(self, t, n, dtype=None):

@@ -22,9 +22,9 @@ URDF_DIR = os.path.join(HERE, "robot-models")
 LIB = os.path.join(HERE, "libgrbda_cuda.so")
 
 # model name -> (algorithms, launch variants "BLOCK,MIN_BLOCKS,STAGED;...", build f32 variants)
-DEFAULT_VARIANTS = "128,2,1"
+DEFAULT_VARIANTS = "S,128,2"
 MODELS = {
-    "tello_with_arms": ("id,fd,fk,h,phi,gen", "128,2,1;64,4,1;128,2,0;64,2,1", True),
+    "tello_with_arms": ("id,fd,fk,h,phi,gen", "R,128,2;R,128,3;R,128,4;S,128,2", True),
     "tello": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
     "revolute_chain_with_rotor_2": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_4": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, False),

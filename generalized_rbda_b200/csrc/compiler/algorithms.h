@@ -25,6 +25,7 @@
 //     6N x 6N products; rigid 10-parameter inertias are kept as long as possible;
 //   * D^-1 is an unrolled LDL^T (D = S^T IA S is SPD); the reference uses ColPivHouseholderQR.
 #pragma once
+#include <functional>
 #include <map>
 #include "../host/model.h"
 #include "spatial_sym.h"
@@ -311,13 +312,44 @@ namespace grbda
             // ---------------------------------------------------------------------------------
             // kinematics of every body (forward pass)
             // ---------------------------------------------------------------------------------
+            // children lists and the depth-first cluster order. The emitted program follows the
+            // order in which expressions are created, so every sweep below visits the tree depth
+            // first (finish one limb before starting the next): the values that must stay live across
+            // the downward and upward sweep of a limb are then few enough to stay in registers.
+            void buildTraversal()
+            {
+                const int Nc = m_.getNumClusters();
+                children_.assign(Nc, std::vector<int>());
+                roots_.clear();
+                for (const ClusterTreeNode &c : m_.clusters())
+                    (c.parent_index_ >= 0 ? children_[c.parent_index_] : roots_).push_back(c.index_);
+            }
+
+            void beginKinematics()
+            {
+                bk_.assign(m_.getNumBodies(), BodyKin());
+                ck_.assign(m_.getNumClusters(), ClusterKin());
+                buildTraversal();
+            }
+
+            // all clusters, depth first
             void kinematics(bool with_velocity, bool with_subspace)
             {
-                const int Nb = m_.getNumBodies();
-                bk_.assign(Nb, BodyKin());
-                ck_.clear();
-                for (const ClusterTreeNode &c : m_.clusters())
+                beginKinematics();
+                std::function<void(int)> visit = [&](int ci) {
+                    kinematicsCluster(ci, with_velocity, with_subspace);
+                    for (int ch : children_[ci])
+                        visit(ch);
+                };
+                for (int r : roots_)
+                    visit(r);
+            }
+
+            // kinematics of the bodies of one cluster (its parent cluster must have been processed)
+            void kinematicsCluster(int ci, bool with_velocity, bool with_subspace)
+            {
                 {
+                    const ClusterTreeNode &c = m_.clusters()[ci];
                     const ClusterDesc &d = c.joint_;
                     const int n = d.num_velocities;
                     if (d.type == ClusterType::FreeQuaternion || d.type == ClusterType::FreeRollPitchYaw)
@@ -351,8 +383,7 @@ namespace grbda
                             for (int k = 0; k < 6; k++)
                                 b.S[k][k] = Sym(1.0);
                         }
-                        ck_.push_back(ClusterKin());
-                        continue;
+                        return;
                     }
 
                     ClusterKin ck = clusterConstraint(c, with_velocity);
@@ -400,7 +431,7 @@ namespace grbda
                             }
                         }
                     }
-                    ck_.push_back(ck);
+                    ck_[ci] = ck;
                 }
             }
 
@@ -442,12 +473,14 @@ namespace grbda
             // ---------------------------------------------------------------------------------
             std::vector<Sym> inverseDynamics()
             {
-                kinematics(true, false);
+                beginKinematics();
                 const int Nb = m_.getNumBodies(), nv = m_.getNumDegreesOfFreedom();
                 std::vector<SV> a(Nb), f(Nb);
-                std::vector<RigidInertia> I(Nb);
-                for (const ClusterTreeNode &c : m_.clusters())
-                {
+                std::vector<Sym> tau(nv, Sym(0.0));
+
+                auto downward = [&](int ci) {
+                    kinematicsCluster(ci, true, false);
+                    const ClusterTreeNode &c = m_.clusters()[ci];
                     const ClusterDesc &d = c.joint_;
                     const int n = d.num_velocities;
                     std::vector<Sym> ydd(n);
@@ -481,18 +514,17 @@ namespace grbda
                             ai = ai + motionCross(b.v, sq);
                         }
                         a[bi] = ai;
-                        I[bi] = RigidInertia::fromMatrix(body.inertia_.getMatrix());
-                        f[bi] = I[bi].apply(ai) + forceCross(b.v, I[bi].apply(b.v));
+                        const RigidInertia I = RigidInertia::fromMatrix(body.inertia_.getMatrix());
+                        f[bi] = I.apply(ai) + forceCross(b.v, I.apply(b.v));
                     }
-                }
-                std::vector<Sym> tau(nv, Sym(0.0));
-                for (int ci = m_.getNumClusters() - 1; ci >= 0; ci--)
-                {
+                };
+                auto upward = [&](int ci) {
                     const ClusterTreeNode &c = m_.clusters()[ci];
                     const ClusterDesc &d = c.joint_;
                     const int n = d.num_velocities;
                     const bool is_free = d.type == ClusterType::FreeQuaternion ||
                                          d.type == ClusterType::FreeRollPitchYaw;
+                    std::map<int, SV> to_parent;
                     for (int i = d.num_bodies - 1; i >= 0; i--)
                     {
                         const int bi = c.first_body_ + i;
@@ -508,9 +540,28 @@ namespace grbda
                                 tau[c.velocity_index_ + k] = tau[c.velocity_index_ + k] + ck.G[i * n + k] * tau_s;
                         }
                         if (p >= 0)
-                            f[p] = f[p] + bk_[bi].Xl.applyForceTranspose(f[bi]);
+                        {
+                            const SV fp = bk_[bi].Xl.applyForceTranspose(f[bi]);
+                            if (m_.getIndexOfClusterContainingBody(p) == ci)
+                                f[p] = f[p] + fp; // in-cluster parent
+                            else if (to_parent.count(p))
+                                to_parent[p] = to_parent[p] + fp;
+                            else
+                                to_parent[p] = fp;
+                        }
                     }
-                }
+                    // one sum per parent body: the limb hands a single 6-vector to the trunk
+                    for (auto &kv : to_parent)
+                        f[kv.first] = f[kv.first] + kv.second;
+                };
+                std::function<void(int)> visit = [&](int ci) {
+                    downward(ci);
+                    for (int ch : children_[ci])
+                        visit(ch);
+                    upward(ci);
+                };
+                for (int r : roots_)
+                    visit(r);
                 return tau;
             }
 
@@ -615,7 +666,7 @@ namespace grbda
             // ---------------------------------------------------------------------------------
             std::vector<Sym> forwardDynamics()
             {
-                kinematics(true, true);
+                beginKinematics();
                 const int Nb = m_.getNumBodies(), nv = m_.getNumDegreesOfFreedom(), Nc = m_.getNumClusters();
 
                 // articulated inertia: rigid accumulator + general symmetric accumulator on the
@@ -625,15 +676,16 @@ namespace grbda
                 std::vector<char> has_gen(Nb, 0);
                 std::map<std::pair<int, int>, M6> offdiag;
                 std::vector<SV> pA(Nb);
-                for (int i = 0; i < Nb; i++)
-                {
-                    rigid[i] = RigidInertia::fromMatrix(m_.bodies()[i].inertia_.getMatrix());
-                    // pA = v x* (I v)   (ClusterTreeDynamics.cpp:95-98)
-                    pA[i] = forceCross(bk_[i].v, rigid[i].apply(bk_[i].v));
-                }
-                auto IAdiag = [&](int i) {
-                    SymInertia I = SymInertia::fromRigid(rigid[i]);
-                    return has_gen[i] ? I + gen[i] : I;
+                // downward sweep of one cluster: kinematics, rigid inertias, pA = v x* (I v)
+                // (ClusterTreeDynamics.cpp:95-98)
+                auto downward = [&](int ci) {
+                    kinematicsCluster(ci, true, true);
+                    const ClusterTreeNode &c = m_.clusters()[ci];
+                    for (int i = c.first_body_; i < c.first_body_ + c.joint_.num_bodies; i++)
+                    {
+                        rigid[i] = RigidInertia::fromMatrix(m_.bodies()[i].inertia_.getMatrix());
+                        pA[i] = forceCross(bk_[i].v, rigid[i].apply(bk_[i].v));
+                    }
                 };
                 auto applyIA = [&](int i, const SV &x) {
                     SV y = rigid[i].apply(x);
@@ -650,8 +702,8 @@ namespace grbda
                 };
                 std::vector<ClusterABA> aba(Nc);
 
-                for (int ci = Nc - 1; ci >= 0; ci--)
-                {
+                // upward sweep of one cluster (ClusterTreeDynamics.cpp:108-129,157-191)
+                auto upward = [&](int ci) {
                     const ClusterTreeNode &c = m_.clusters()[ci];
                     const int N = c.joint_.num_bodies, n = c.joint_.num_velocities, b0 = c.first_body_;
                     ClusterABA &A = aba[ci];
@@ -698,7 +750,7 @@ namespace grbda
                     A.ldl.factor(D, n);
 
                     if (c.parent_index_ < 0)
-                        continue;
+                        return;
 
                     // z = D^-1 (u - U^T c)
                     std::vector<Sym> t = A.u;
@@ -707,6 +759,17 @@ namespace grbda
                             t[k] = t[k] - dot(A.U[i][k], cb[i]);
                     const std::vector<Sym> z = A.ldl.solve(t);
                     // pa_i = pA_i + sum_j IA_ij c_j + U_i z ; parent pA += X_i^T pa_i
+                    // Everything this cluster hands to an ancestor body is summed first (one symmetric
+                    // 6x6 + one 6-vector per ancestor), so a limb crosses the trunk cut with 27 values.
+                    std::map<int, SV> pA_to;
+                    std::map<int, SymInertia> IA_to;
+                    auto addInertiaTo = [&](int anc, const SymInertia &I) {
+                        auto it = IA_to.find(anc);
+                        if (it == IA_to.end())
+                            IA_to[anc] = I;
+                        else
+                            it->second = it->second + I;
+                    };
                     for (int i = 0; i < N; i++)
                     {
                         SV pa = pA[b0 + i] + applyIA(b0 + i, cb[i]);
@@ -722,7 +785,11 @@ namespace grbda
                         for (int k = 0; k < n; k++)
                             pa = pa + z[k] * A.U[i][k];
                         const int anc = bk_[b0 + i].anc;
-                        pA[anc] = pA[anc] + bk_[b0 + i].Xup.applyForceTranspose(pa);
+                        const SV pa_p = bk_[b0 + i].Xup.applyForceTranspose(pa);
+                        if (pA_to.count(anc))
+                            pA_to[anc] = pA_to[anc] + pa_p;
+                        else
+                            pA_to[anc] = pa_p;
                     }
                     // parent IA += X^T IA X - W D^-1 W^T,   W_a = sum_{i -> a} X_i^T U_i
                     std::map<int, std::vector<SV>> W;
@@ -734,14 +801,10 @@ namespace grbda
                             Wa.assign(n, SV());
                         for (int k = 0; k < n; k++)
                             Wa[k] = Wa[k] + bk_[b0 + i].Xup.applyForceTranspose(A.U[i][k]);
-                        // diagonal blocks
-                        rigid[anc] = rigid[anc] + rigid[b0 + i].toParent(bk_[b0 + i].Xup);
+                        // diagonal blocks: rigid part transformed in 10-parameter form
+                        addInertiaTo(anc, SymInertia::fromRigid(rigid[b0 + i].toParent(bk_[b0 + i].Xup)));
                         if (has_gen[b0 + i])
-                        {
-                            const SymInertia G = gen[b0 + i].toParent(bk_[b0 + i].Xup);
-                            gen[anc] = has_gen[anc] ? gen[anc] + G : G;
-                            has_gen[anc] = 1;
-                        }
+                            addInertiaTo(anc, gen[b0 + i].toParent(bk_[b0 + i].Xup));
                     }
                     // off-diagonal blocks of this cluster
                     for (auto &kv : offdiag)
@@ -787,16 +850,39 @@ namespace grbda
                                         M(s, r) = -e;
                                 }
                             if (a == b)
-                                addSymmetric(a, M, gen, has_gen);
+                                addInertiaTo(a, symFromM6(M));
                             else
                                 addBlock(a, b, M, gen, has_gen, offdiag);
                         }
-                }
+                    for (auto &kv : IA_to)
+                    {
+                        gen[kv.first] = has_gen[kv.first] ? gen[kv.first] + kv.second : kv.second;
+                        has_gen[kv.first] = 1;
+                    }
+                    for (auto &kv : pA_to)
+                        pA[kv.first] = pA[kv.first] + kv.second;
+                };
+                std::function<void(int)> visit = [&](int ci) {
+                    downward(ci);
+                    for (int ch : children_[ci])
+                        visit(ch);
+                    upward(ci);
+                };
+                for (int r : roots_)
+                    visit(r);
 
-                // forward pass: accelerations (ClusterTreeDynamics.cpp:132-152)
+                // forward pass: accelerations (ClusterTreeDynamics.cpp:132-152), depth first as well
                 std::vector<Sym> ydd_out(nv);
                 std::vector<SV> a(Nb);
-                for (int ci = 0; ci < Nc; ci++)
+                std::vector<int> order;
+                std::function<void(int)> collect = [&](int ci) {
+                    order.push_back(ci);
+                    for (int ch : children_[ci])
+                        collect(ch);
+                };
+                for (int r : roots_)
+                    collect(r);
+                for (int ci : order)
                 {
                     const ClusterTreeNode &c = m_.clusters()[ci];
                     const int N = c.joint_.num_bodies, n = c.joint_.num_velocities, b0 = c.first_body_;
@@ -886,6 +972,8 @@ namespace grbda
             const ClusterTreeModel &m_;
             std::vector<BodyKin> bk_;
             std::vector<ClusterKin> ck_;
+            std::vector<std::vector<int>> children_;
+            std::vector<int> roots_;
         };
 
     } // namespace compiler

@@ -3,6 +3,7 @@
 #include <fstream>
 #include "algorithms.h"
 #include "emit.h"
+#include "partition.h"
 
 namespace grbda
 {
@@ -33,10 +34,9 @@ namespace grbda
             Tape tape;
         };
 
-        inline CompiledAlgo compileAlgo(const ClusterTreeModel &model, int algo, bool want_body = true)
+        // Build the symbolic program of one algorithm in the CURRENT graph scope.
+        inline Program buildProgram(const ClusterTreeModel &model, int algo)
         {
-            sym::Graph graph;
-            sym::GraphScope scope(graph);
             ModelCompiler mc(model);
             Program p;
             p.name = algoName(algo);
@@ -90,6 +90,14 @@ namespace grbda
             default:
                 throw std::runtime_error("compileAlgo: unknown algorithm");
             }
+            return p;
+        }
+
+        inline CompiledAlgo compileAlgo(const ClusterTreeModel &model, int algo, bool want_body = true)
+        {
+            sym::Graph graph;
+            sym::GraphScope scope(graph);
+            const Program p = buildProgram(model, algo);
             CompiledAlgo out;
             out.name = p.name;
             for (int i = 0; i < 3; i++)
@@ -102,6 +110,135 @@ namespace grbda
             if (want_body)
                 out.body = em.cudaBody();
             return out;
+        }
+
+        // ---- limb-parallel (one warp per limb) version of the same program ---------------------------
+        struct CompiledRoles
+        {
+            std::string name;
+            int W = 1, num_slots = 0;
+            bool has_barrier = false;
+            int n_in[3] = {0, 0, 0};
+            int n_out[3] = {0, 0, 0};
+            std::vector<std::string> bodies;  // per role
+            std::vector<ProgramStats> stats;  // per role
+            // for the CPU-side self test (tests/tape.py): the whole graph + the role instruction lists
+            sym::Graph graph;
+            RolePrograms programs;
+            std::vector<std::vector<RolePartitioner::Out>> role_outputs;
+        };
+
+        inline CompiledRoles compileAlgoRoles(const ClusterTreeModel &model, int algo, bool want_body = true)
+        {
+            CompiledRoles out;
+            const RolePlan plan = planRoles(model);
+            sym::GraphScope scope(out.graph);
+            const Program p = buildProgram(model, algo);
+            out.name = p.name;
+            out.W = algo == ALGO_PHI ? 1 : plan.W;
+            for (int i = 0; i < 3; i++)
+                out.n_in[i] = p.n_in[i];
+            for (size_t i = 0; i < p.outputs.size(); i++)
+                out.n_out[i] = (int)p.outputs[i].size();
+            const int nv = model.getNumDegreesOfFreedom();
+
+            // cluster of a position / velocity / body index
+            std::vector<int> pos_cluster(model.getNumPositions()), vel_cluster(nv), body_cluster(model.getNumBodies());
+            std::vector<int> weight(std::max(1, plan.W), 0);
+            for (const ClusterTreeNode &c : model.clusters())
+            {
+                for (int i = 0; i < c.num_positions_; i++)
+                    pos_cluster[c.position_index_ + i] = c.index_;
+                for (int i = 0; i < c.num_velocities_; i++)
+                    vel_cluster[c.velocity_index_ + i] = c.index_;
+                for (int i = 0; i < c.joint_.num_bodies; i++)
+                    body_cluster[c.first_body_ + i] = c.index_;
+                if (plan.cluster_role[c.index_] >= 0)
+                    weight[plan.cluster_role[c.index_]] += c.joint_.num_bodies * (c.joint_.type == ClusterType::Implicit ? 3 : 1);
+            }
+            // trunk outputs go to the lightest limb
+            const int trunk_role = (int)(std::min_element(weight.begin(), weight.end()) - weight.begin());
+            auto roleOfCluster = [&](int c) { return out.W > 1 ? plan.cluster_role[c] : 0; };
+            auto input_role = [&](int array, int element) {
+                return roleOfCluster(array == IN_Q ? pos_cluster[element] : vel_cluster[element]);
+            };
+            auto output_role = [&](int array, int element) {
+                int r = -1;
+                switch (algo)
+                {
+                case ALGO_ID:
+                case ALGO_FD: r = roleOfCluster(vel_cluster[element]); break;
+                case ALGO_FK:
+                    r = roleOfCluster(body_cluster[element / (array == 0 ? 3 : (array == 1 ? 9 : 6))]);
+                    break;
+                case ALGO_H:
+                {
+                    const int ra = roleOfCluster(vel_cluster[element / nv]), rb = roleOfCluster(vel_cluster[element % nv]);
+                    r = ra >= 0 ? ra : rb;
+                    break;
+                }
+                default: r = 0;
+                }
+                return r >= 0 ? r : trunk_role;
+            };
+            RolePartitioner part(out.graph, p, out.W, input_role, output_role);
+            out.programs = part.build();
+            out.num_slots = out.programs.num_slots;
+            out.has_barrier = out.programs.has_barrier;
+            out.role_outputs = part.roleOutputs();
+            RoleEmitter em(out.graph, part, out.programs);
+            for (int r = 0; r < out.W; r++)
+            {
+                out.stats.push_back(em.roleStats(r));
+                if (want_body)
+                    out.bodies.push_back(em.roleBody(r));
+            }
+            return out;
+        }
+
+        // Role tape (tests/tape.py run_role_tape): int32 header {magic 0x47524245, n_nodes, W, num_slots,
+        // n_in0, n_in1, n_in2, n_out0, n_out1, n_out2}; node table op,a,b,c,e (int32) + val (float64);
+        // per role: int32 n_ops, then (kind, id, slot) int32 triples; int32 n_outputs, then
+        // (id, array, element) int32 triples.
+        inline void writeRoleTape(const CompiledRoles &c, const std::string &path)
+        {
+            std::ofstream f(path, std::ios::binary);
+            if (!f)
+                throw std::runtime_error("cannot write " + path);
+            const int32_t n = (int32_t)c.graph.nodes.size();
+            const int32_t hdr[10] = {0x47524245, n, c.W, c.num_slots, c.n_in[0], c.n_in[1], c.n_in[2],
+                                     c.n_out[0], c.n_out[1], c.n_out[2]};
+            f.write((const char *)hdr, sizeof(hdr));
+            std::vector<int32_t> col(n);
+            auto dump = [&](auto get) {
+                for (int32_t i = 0; i < n; i++)
+                    col[i] = get(c.graph.nodes[i]);
+                f.write((const char *)col.data(), (size_t)n * 4);
+            };
+            dump([](const sym::Node &x) { return (int32_t)x.op; });
+            dump([](const sym::Node &x) { return x.a; });
+            dump([](const sym::Node &x) { return x.b; });
+            dump([](const sym::Node &x) { return x.c; });
+            dump([](const sym::Node &x) { return x.e; });
+            for (int32_t i = 0; i < n; i++)
+                f.write((const char *)&c.graph.nodes[i].val, 8);
+            for (int r = 0; r < c.W; r++)
+            {
+                const int32_t no = (int32_t)c.programs.ops[r].size();
+                f.write((const char *)&no, 4);
+                for (const RoleOp &op : c.programs.ops[r])
+                {
+                    const int32_t t[3] = {op.kind, op.id, op.slot};
+                    f.write((const char *)t, 12);
+                }
+                const int32_t nout = (int32_t)c.role_outputs[r].size();
+                f.write((const char *)&nout, 4);
+                for (auto &o : c.role_outputs[r])
+                {
+                    const int32_t t[3] = {o.id, o.array, o.element};
+                    f.write((const char *)t, 12);
+                }
+            }
         }
 
         // Binary tape: int32 header {magic, n_ops, n_arrays, n_in0, n_in1, n_in2}, then op,a,b,c,e

@@ -200,4 +200,99 @@ namespace grbda_kernels
         return cudaGetLastError();
     }
 
+    // ---------------------------------------------------------------------------------------------
+    // Limb-parallel shell: ONE STATE PER LANE, ONE LIMB PER WARP (compiler/partition.h).
+    // A CTA of W warps evaluates 32 states; warp w runs the straight-line program of limb
+    // (w + blockIdx.x) % W (rotated so that heavy and light limbs spread over the four schedulers of
+    // an SM), publishes what the trunk needs from its limb in shared memory (COMM_ST), meets the
+    // other warps at ONE named barrier and continues with the values of the other limbs (COMM_LD).
+    //   Body::W, Body::NUM_SLOTS, Body::N_INk / N_OUTk
+    //   Body::run<real>(role, in0, in1, in2, out0, out1, out2, comm)
+    // ---------------------------------------------------------------------------------------------
+    template <typename Body, typename real>
+    struct RoleLayout
+    {
+        static constexpr int TILE = 32;
+        static constexpr int S0 = Body::N_IN0 ? oddStride(Body::N_IN0) : 0;
+        static constexpr int S1 = Body::N_IN1 ? oddStride(Body::N_IN1) : 0;
+        static constexpr int S2 = Body::N_IN2 ? oddStride(Body::N_IN2) : 0;
+        static constexpr bool STAGE_OUT0 = Body::N_OUT0 <= 64;
+        static constexpr int SO = STAGE_OUT0 ? oddStride(Body::N_OUT0) : 0;
+        static constexpr int OFF1 = S0 * TILE;
+        static constexpr int OFF2 = OFF1 + S1 * TILE;
+        static constexpr int OFFO = OFF2 + S2 * TILE;
+        static constexpr int OFFC = OFFO + SO * TILE;
+        static constexpr int ELEMS = OFFC + Body::NUM_SLOTS * TILE;
+        static constexpr size_t BYTES = (size_t)ELEMS * sizeof(real);
+    };
+
+    template <int NTHREADS>
+    __device__ __forceinline__ void roleBarrier()
+    {
+        // named barrier 1: every warp of the CTA arrives exactly once, from its own role program
+        asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
+    }
+
+    template <typename real, typename Body, int MIN_BLOCKS>
+    __global__ void __launch_bounds__(Body::W * 32, MIN_BLOCKS)
+        grbda_role_kernel(const real *__restrict__ in0, const real *__restrict__ in1,
+                          const real *__restrict__ in2, real *__restrict__ out0, real *__restrict__ out1,
+                          real *__restrict__ out2, int64_t batch)
+    {
+        using L = RoleLayout<Body, real>;
+        constexpr int BLOCK = Body::W * 32;
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        real *smem = reinterpret_cast<real *>(smem_raw);
+
+        const int64_t first = (int64_t)blockIdx.x * L::TILE;
+        const int64_t remaining = batch - first;
+        const int rows = remaining < L::TILE ? (int)remaining : L::TILE;
+
+        if (Body::N_IN0)
+            stage_in<real, Body::N_IN0 ? Body::N_IN0 : 1, BLOCK>(in0 + first * Body::N_IN0, smem, rows);
+        if (Body::N_IN1)
+            stage_in<real, Body::N_IN1 ? Body::N_IN1 : 1, BLOCK>(in1 + first * Body::N_IN1, smem + L::OFF1, rows);
+        if (Body::N_IN2)
+            stage_in<real, Body::N_IN2 ? Body::N_IN2 : 1, BLOCK>(in2 + first * Body::N_IN2, smem + L::OFF2, rows);
+        __syncthreads();
+
+        const int warp = threadIdx.x >> 5;
+        const int role = (warp + (int)(blockIdx.x % Body::W)) % Body::W;
+        // lanes past the end of the batch recompute the last valid state (identical values, so the
+        // duplicate stores are benign) and thereby still take part in the barrier
+        const int lane = min((int)(threadIdx.x & 31), rows - 1);
+        const int64_t state = first + lane;
+        real *o0 = L::STAGE_OUT0 ? smem + L::OFFO + lane * L::SO : out0 + state * Body::N_OUT0;
+        real *o1 = Body::N_OUT1 ? out1 + state * Body::N_OUT1 : nullptr;
+        real *o2 = Body::N_OUT2 ? out2 + state * Body::N_OUT2 : nullptr;
+        Body::template run<real>(role, smem + lane * L::S0, smem + L::OFF1 + lane * L::S1,
+                                 smem + L::OFF2 + lane * L::S2, o0, o1, o2, smem + L::OFFC + lane);
+        if (L::STAGE_OUT0)
+        {
+            __syncthreads();
+            stage_out<real, Body::N_OUT0 ? Body::N_OUT0 : 1, BLOCK>(out0 + first * Body::N_OUT0,
+                                                                   smem + L::OFFO, rows);
+        }
+    }
+
+    template <typename real, typename Body, int MIN_BLOCKS>
+    cudaError_t launchRoles(const LaunchArgs &a)
+    {
+        using L = RoleLayout<Body, real>;
+        auto kernel = grbda_role_kernel<real, Body, MIN_BLOCKS>;
+        if (L::BYTES > 48 * 1024)
+        {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES);
+            if (e != cudaSuccess)
+                return e;
+        }
+        if (a.batch <= 0)
+            return cudaSuccess;
+        const int64_t grid = (a.batch + L::TILE - 1) / L::TILE;
+        kernel<<<(unsigned)grid, Body::W * 32, L::BYTES, a.stream>>>(
+            (const real *)a.in[0], (const real *)a.in[1], (const real *)a.in[2], (real *)a.out[0],
+            (real *)a.out[1], (real *)a.out[2], a.batch);
+        return cudaGetLastError();
+    }
+
 } // namespace grbda_kernels

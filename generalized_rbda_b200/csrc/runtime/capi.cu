@@ -270,6 +270,28 @@ extern "C"
             return (grbda_status)GRBDA_OK; });
     }
 
+    grbda_status grbda_cuda_dump_role_program(const grbda_model *m, int algo, const char *path, int64_t *info4)
+    {
+        if (!m || algo < 0 || algo >= compiler::ALGO_COUNT)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        return guarded([&]
+                       {
+            const compiler::CompiledRoles c = compiler::compileAlgoRoles(m->model, algo, false);
+            if (path)
+                compiler::writeRoleTape(c, path);
+            if (info4)
+            {
+                int64_t mx = 0, sum = 0;
+                for (auto &s : c.stats)
+                {
+                    mx = std::max<int64_t>(mx, s.flops());
+                    sum += s.flops();
+                }
+                info4[0] = c.W, info4[1] = c.num_slots, info4[2] = mx, info4[3] = sum;
+            }
+            return (grbda_status)GRBDA_OK; });
+    }
+
     // ---- device-pointer hot path -------------------------------------------------------------------
     grbda_status grbda_cuda_inverse_dynamics_f64(const grbda_model *m, const double *q, const double *yd,
                                                  const double *ydd, double *tau, int64_t batch, void *stream)

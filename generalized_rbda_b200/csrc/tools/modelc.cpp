@@ -20,7 +20,8 @@ namespace
 {
     struct Variant
     {
-        int block, min_blocks, staged;
+        char kind; // 'S' one state per thread, staged I/O; 'D' direct global I/O; 'R' one limb per warp
+        int block, min_blocks;
     };
 
     std::vector<std::string> split(const std::string &s, char sep)
@@ -62,6 +63,35 @@ namespace
         os << "    }\n};\n";
     }
 
+    void emitRoleStruct(std::ostream &os, const std::string &struct_name, const CompiledRoles &c)
+    {
+        os << "struct " << struct_name << "\n{\n";
+        os << "    static constexpr int W = " << c.W << ", NUM_SLOTS = " << c.num_slots << ";\n";
+        os << "    static constexpr int N_IN0 = " << c.n_in[0] << ", N_IN1 = " << c.n_in[1]
+           << ", N_IN2 = " << c.n_in[2] << ";\n";
+        os << "    static constexpr int N_OUT0 = " << c.n_out[0] << ", N_OUT1 = " << c.n_out[1]
+           << ", N_OUT2 = " << c.n_out[2] << ";\n";
+        os << "    template <typename real>\n";
+        os << "    static __device__ __forceinline__ void run(const int role, const real *__restrict__ in0,\n"
+              "        const real *__restrict__ in1, const real *__restrict__ in2, real *__restrict__ out0,\n"
+              "        real *__restrict__ out1, real *__restrict__ out2, real *__restrict__ comm)\n    {\n";
+        os << "#define KC(x) ((real)(x))\n#define IN0(i) in0[i]\n#define IN1(i) in1[i]\n#define IN2(i) in2[i]\n"
+              "#define OUT0(i, x) out0[i] = (x)\n#define OUT1(i, x) out1[i] = (x)\n#define OUT2(i, x) out2[i] = (x)\n"
+              "#define COMM_ST(s, x) comm[(s) * 32] = (x)\n#define COMM_LD(s) comm[(s) * 32]\n"
+              "#define ROLE_BARRIER() roleBarrier<W * 32>()\n";
+        os << "        switch (role)\n        {\n";
+        for (int r = 0; r < c.W; r++)
+        {
+            os << "        case " << r << ":\n        {\n";
+            os << c.bodies[r];
+            os << "        }\n        break;\n";
+        }
+        os << "        default: break;\n        }\n";
+        os << "#undef KC\n#undef IN0\n#undef IN1\n#undef IN2\n#undef OUT0\n#undef OUT1\n#undef OUT2\n"
+              "#undef COMM_ST\n#undef COMM_LD\n#undef ROLE_BARRIER\n";
+        os << "    }\n};\n";
+    }
+
     void writeIfChanged(const std::string &path, const std::string &text)
     {
         {
@@ -84,7 +114,7 @@ namespace
 int main(int argc, char **argv)
 {
     std::string model_name, urdf_dir = ".", out_dir = ".", algos = "id,fd,fk,h,phi,gen";
-    std::string variants_s = "128,2,1";
+    std::string variants_s = "S,128,2";
     bool f32 = true;
     for (int i = 1; i < argc; i++)
     {
@@ -122,9 +152,9 @@ int main(int argc, char **argv)
         for (auto &v : split(variants_s, ';'))
         {
             auto p = split(v, ',');
-            if (p.size() != 3)
-                throw std::runtime_error("bad --variants entry '" + v + "'");
-            variants.push_back({std::atoi(p[0].c_str()), std::atoi(p[1].c_str()), std::atoi(p[2].c_str())});
+            if (p.size() != 3 || p[0].size() != 1 || std::string("SDR").find(p[0][0]) == std::string::npos)
+                throw std::runtime_error("bad --variants entry '" + v + "' (expected KIND,BLOCK,MINBLOCKS)");
+            variants.push_back({p[0][0], std::atoi(p[1].c_str()), std::atoi(p[2].c_str())});
         }
         if (variants.empty() || variants.size() > 4)
             throw std::runtime_error("between 1 and 4 variants are supported");
@@ -160,30 +190,37 @@ int main(int argc, char **argv)
             const CompiledAlgo c = compileAlgo(model, a, true);
             if (a == ALGO_PHI && c.n_out[0] == 0)
                 continue; // no implicit clusters
+            bool want_roles = false, want_single = false;
+            for (auto &v : variants)
+                (v.kind == 'R' ? want_roles : want_single) = true;
+            CompiledRoles roles;
+            if (want_roles && a != ALGO_PHI)
+                roles = compileAlgoRoles(model, a, true);
+            const bool have_roles = want_roles && a != ALGO_PHI && roles.W > 1;
             std::ostringstream os;
             os << header_common;
-            emitBodyStruct(os, "Body", c);
+            if (want_single || !have_roles)
+                emitBodyStruct(os, "Body", c);
+            if (have_roles)
+                emitRoleStruct(os, "RoleBody", roles);
             os << "} // namespace\n\n";
+            auto launcher = [&](const Variant &v, const char *real) {
+                std::ostringstream l;
+                if (v.kind == 'R' && have_roles)
+                    l << "&launchRoles<" << real << ", RoleBody, " << v.min_blocks << ">";
+                else
+                    l << "&launchBatched<" << real << ", Body, " << (v.kind == 'R' ? 128 : v.block) << ", "
+                      << (v.kind == 'R' ? 2 : v.min_blocks) << ", " << (v.kind == 'D' ? "false" : "true") << ">";
+                return l.str();
+            };
             os << "static const grbda_runtime::AlgoKernels k_algo = {\n    {";
             for (int v = 0; v < 4; v++)
-            {
-                if (v < (int)variants.size())
-                    os << "&launchBatched<double, Body, " << variants[v].block << ", " << variants[v].min_blocks
-                       << ", " << (variants[v].staged ? "true" : "false") << ">";
-                else
-                    os << "nullptr";
-                os << (v < 3 ? ", " : "");
-            }
+                os << (v < (int)variants.size() ? launcher(variants[v], "double") : std::string("nullptr"))
+                   << (v < 3 ? ", " : "");
             os << "},\n    {";
             for (int v = 0; v < 4; v++)
-            {
-                if (f32 && v < (int)variants.size())
-                    os << "&launchBatched<float, Body, " << variants[v].block << ", " << variants[v].min_blocks
-                       << ", " << (variants[v].staged ? "true" : "false") << ">";
-                else
-                    os << "nullptr";
-                os << (v < 3 ? ", " : "");
-            }
+                os << (f32 && v < (int)variants.size() ? launcher(variants[v], "float") : std::string("nullptr"))
+                   << (v < 3 ? ", " : "");
             os << "},\n    {" << c.n_in[0] << ", " << c.n_in[1] << ", " << c.n_in[2] << "}, {" << c.n_out[0] << ", "
                << c.n_out[1] << ", " << c.n_out[2] << "},\n    {" << c.stats.n_nodes << ", " << c.stats.n_add
                << ", " << c.stats.n_mul << ", " << c.stats.n_div << ", " << c.stats.n_sqrt << ", "

@@ -136,6 +136,11 @@ grbda_status grbda_cuda_cluster_G(const grbda_model *m, int cluster, double *G);
  * fusable mul+add pairs} of the straight-line program each thread executes. */
 grbda_status grbda_cuda_dump_program(const grbda_model *m, int algo, const char *path, int64_t *counts8);
 
+/* The limb-parallel (one warp per limb, compiler/partition.h) form of the same program, written as a
+ * role tape; info4 = {W (warps per state), communication slots, max per-role flops, sum of per-role
+ * flops}. W = 1 when the model has no trunk with at least two limbs. */
+grbda_status grbda_cuda_dump_role_program(const grbda_model *m, int algo, const char *path, int64_t *info4);
+
 /* ---- batched hot path, device pointers ----------------------------------------------------- */
 /* tau = ID(q, yd, ydd). Replaces setState + ClusterTreeModel::inverseDynamics(ydd),
  * src/Dynamics/ClusterTreeDynamics.cpp:79-83 -> TreeModel.cpp:174-212. */

@@ -8,7 +8,7 @@ import re
 import numpy as np
 import pytest
 
-from tape import load_tape, run_tape
+from tape import load_role_tape, load_tape, run_role_tape, run_tape
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # product robot name -> oracle robot name
@@ -81,6 +81,33 @@ def test_emitted_programs_match_oracle(grbda, oracle, robot, tmp_path):
     phi = run_tape(tapes["phi"], ins)[0]
     if phi.shape[1]:
         assert np.abs(phi).max() < 1e-8  # generated states satisfy the loop constraints
+
+
+@pytest.mark.parametrize("robot", ["tello", "tello_with_arms"])
+def test_limb_parallel_programs_match_oracle(grbda, oracle, robot, tmp_path):
+    """One warp per limb: each role may only use values it computed or received through a
+    communication slot (the interpreter enforces it), one barrier, same results as the oracle."""
+    m = grbda.ClusterTreeModel.from_robot(robot, device=None)
+    o = oracle.OracleModel(ROBOTS[robot])
+    q, yd, aux = o.generate_states(32, seed=21)
+    ins = [q, yd, aux]
+    res = {}
+    for algo, name in enumerate(grbda.ALGO_NAMES[:4]):
+        path = str(tmp_path / (name + ".rtape"))
+        info = m.dump_role_program(algo, path)
+        assert info["W"] == {"tello": 2, "tello_with_arms": 4}[robot]
+        res[name] = (run_role_tape(load_role_tape(path), ins), info)
+    assert res["fd"][1]["slots"] == res["fd"][1]["W"] * 27  # articulated inertia (21) + bias force (6) per limb
+    assert res["fk"][1]["slots"] == 0       # kinematics needs no exchange
+    assert rel(res["id"][0][0], o.inverse_dynamics(q, yd, aux)) < TOL
+    assert rel(res["fd"][0][0], o.forward_dynamics(q, yd, aux)) < TOL
+    assert rel(res["h"][0][0].reshape(-1, o.nv, o.nv), o.mass_matrix(q)) < TOL
+    p, R, v = o.forward_kinematics(q, yd)
+    fk = res["fk"][0]
+    assert rel(fk[0].reshape(p.shape), p) < TOL and rel(fk[1].reshape(R.shape), R) < TOL
+    assert rel(fk[2].reshape(v.shape), v) < TOL
+    # a chain has no trunk with several limbs: the partition degenerates to one role
+    assert grbda.ClusterTreeModel.from_robot("revolute_chain_with_rotor_4", device=None).dump_role_program(1)["W"] == 1
 
 
 def test_schedule_round_trip(grbda):

@@ -80,10 +80,12 @@ def test_dynamics_parity_f32(grbda, oracle, torch, robot):
     assert relrows(m.getMassMatrix(q32).double().cpu().numpy(), o.mass_matrix(qn)) < TOL32
     ydd32 = m.forwardDynamics(q32, yd32, aux32).double().cpu().numpy()
     ydd = o.forward_dynamics(qn, ydn, auxn)
-    # FD: residual form, tau recovered from the FP32 accelerations
+    # FD amplifies input rounding by cond(H) (rotor inertias ~1e-5 next to link inertias ~1e-2), so
+    # the FP32 accelerations are judged on the typical state and through the residual tau = ID(ydd)
     tau_back = o.inverse_dynamics(qn, ydn, ydd32)
-    assert relrows(tau_back, auxn) < 5e-3
-    assert np.median(np.abs(ydd32 - ydd).max(1) / np.abs(ydd).max(1)) < TOL32 * 50
+    res = np.abs(tau_back - auxn).max(1) / np.abs(auxn).max(1)
+    assert np.median(res) < 1e-3
+    assert np.median(np.abs(ydd32 - ydd).max(1) / np.abs(ydd).max(1)) < 1e-3
 
 
 def test_golden_vectors_on_gpu(grbda, torch):
