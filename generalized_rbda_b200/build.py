@@ -23,8 +23,9 @@ LIB = os.path.join(HERE, "libgrbda_cuda.so")
 
 # model name -> (algorithms, launch variants "BLOCK,MIN_BLOCKS,STAGED;...", build f32 variants)
 DEFAULT_VARIANTS = "S,128,2"
+SYNC_EVERY = int(os.environ.get("GRBDA_SYNC_EVERY", "256"))
 MODELS = {
-    "tello_with_arms": ("id,fd,fk,h,phi,gen", "R,128,2;R,128,3;R,128,4;S,128,2", True),
+    "tello_with_arms": ("id,fd,fk,h,phi,gen", "S,128,2;S,256,1;D,256,1;S,64,4", True),
     "tello": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
     "revolute_chain_with_rotor_2": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_4": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, False),
@@ -98,7 +99,7 @@ def build(verbose=True, jobs=None, models=None):
     gen_sources = []
     for name, (algos, variants, f32) in models.items():
         cmd = [modelc, "--model", name, "--urdf-dir", URDF_DIR, "--out", GEN, "--algos", algos,
-               "--variants", variants]
+               "--variants", variants, "--sync-every", str(SYNC_EVERY)]
         if not f32:
             cmd.append("--no-f32")
         log("  " + _run(cmd).strip())
@@ -119,6 +120,12 @@ def build(verbose=True, jobs=None, models=None):
     # 4. link
     _run([NVCC, "-shared", "-o", LIB, "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", CXX]
          + cuda_objs + [reg_obj] + host_objs + ["-lcudart"])
+    # drop stale cached objects so that _build does not grow without bound
+    keep = set(cuda_objs + [reg_obj, modelc_obj, modelc] + host_objs)
+    for f in os.listdir(BUILD):
+        p = os.path.join(BUILD, f)
+        if p not in keep and f.endswith(".o"):
+            os.remove(p)
     log("  linked %s" % os.path.relpath(LIB, os.path.join(HERE, "..")))
     return LIB
 

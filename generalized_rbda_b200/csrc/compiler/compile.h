@@ -93,7 +93,8 @@ namespace grbda
             return p;
         }
 
-        inline CompiledAlgo compileAlgo(const ClusterTreeModel &model, int algo, bool want_body = true)
+        inline CompiledAlgo compileAlgo(const ClusterTreeModel &model, int algo, bool want_body = true,
+                                        int sync_every = 0, ConstTable *consts = nullptr)
         {
             sym::Graph graph;
             sym::GraphScope scope(graph);
@@ -104,11 +105,11 @@ namespace grbda
                 out.n_in[i] = p.n_in[i];
             for (size_t i = 0; i < p.outputs.size(); i++)
                 out.n_out[i] = (int)p.outputs[i].size();
-            Emitter em(graph, p);
+            Emitter em(graph, p, consts);
             out.stats = em.stats();
             out.tape = em.tape();
             if (want_body)
-                out.body = em.cudaBody();
+                out.body = em.cudaBody(sync_every);
             return out;
         }
 
@@ -128,7 +129,8 @@ namespace grbda
             std::vector<std::vector<RolePartitioner::Out>> role_outputs;
         };
 
-        inline CompiledRoles compileAlgoRoles(const ClusterTreeModel &model, int algo, bool want_body = true)
+        inline CompiledRoles compileAlgoRoles(const ClusterTreeModel &model, int algo, bool want_body = true,
+                                              ConstTable *consts = nullptr)
         {
             CompiledRoles out;
             const RolePlan plan = planRoles(model);
@@ -186,7 +188,7 @@ namespace grbda
             out.num_slots = out.programs.num_slots;
             out.has_barrier = out.programs.has_barrier;
             out.role_outputs = part.roleOutputs();
-            RoleEmitter em(out.graph, part, out.programs);
+            RoleEmitter em(out.graph, part, out.programs, consts);
             for (int r = 0; r < out.W; r++)
             {
                 out.stats.push_back(em.roleStats(r));

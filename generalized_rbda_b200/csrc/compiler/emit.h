@@ -6,6 +6,7 @@
 #pragma once
 #include <cstdio>
 #include <sstream>
+#include <algorithm>
 #include <string>
 #include "sym.h"
 
@@ -28,6 +29,71 @@ namespace grbda
             std::vector<std::vector<int32_t>> outputs; // per output array: tape index per element
         };
 
+        // Model constants that do not fit an instruction immediate (a double whose low 32 bits are
+        // non-zero costs two UMOV instructions when written as a literal) are collected in a
+        // __constant__ table of the translation unit; FP64 instructions then read them as constant-bank
+        // operands for free. KT(i) in the emitted text indexes this table.
+        struct ConstTable
+        {
+            std::vector<double> values;
+            std::unordered_map<uint64_t, int> index;
+            static bool fitsImmediate(double v)
+            {
+                uint64_t bits;
+                std::memcpy(&bits, &v, 8);
+                return (bits & 0xffffffffull) == 0;
+            }
+            std::string ref(double v)
+            {
+                char buf[64];
+                if (fitsImmediate(v))
+                {
+                    std::snprintf(buf, sizeof(buf), "KC(%.17g)", v);
+                    return buf;
+                }
+                uint64_t bits;
+                std::memcpy(&bits, &v, 8);
+                auto it = index.find(bits);
+                int k;
+                if (it == index.end())
+                {
+                    k = (int)values.size();
+                    values.push_back(v);
+                    index[bits] = k;
+                }
+                else
+                    k = it->second;
+                std::snprintf(buf, sizeof(buf), "KT(%d)", k);
+                return buf;
+            }
+            std::string definition(const std::string &name) const
+            {
+                std::ostringstream os;
+                os.precision(17);
+                const size_t n = std::max<size_t>(1, values.size());
+                os << "static __constant__ double " << name << "_f64[" << n << "] = {";
+                for (size_t i = 0; i < n; i++)
+                    os << (i ? ", " : "") << (i < values.size() ? values[i] : 0.0);
+                os << "};\nstatic __constant__ float " << name << "_f32[" << n << "] = {";
+                for (size_t i = 0; i < n; i++)
+                {
+                    char buf[48];
+                    std::snprintf(buf, sizeof(buf), "%.9g", (double)(float)(i < values.size() ? values[i] : 0.0));
+                    std::string t = buf;
+                    if (t.find_first_of(".en") == std::string::npos)
+                        t += ".0";
+                    os << (i ? ", " : "") << t << "f";
+                }
+                os << "};\n";
+                os << "template <typename real> __device__ __forceinline__ real " << name << "(int i);\n";
+                os << "template <> __device__ __forceinline__ double " << name << "<double>(int i) { return " << name
+                   << "_f64[i]; }\n";
+                os << "template <> __device__ __forceinline__ float " << name << "<float>(int i) { return " << name
+                   << "_f32[i]; }\n";
+                return os.str();
+            }
+        };
+
         struct Program
         {
             std::string name;
@@ -38,7 +104,11 @@ namespace grbda
         class Emitter
         {
         public:
-            Emitter(const sym::Graph &g, const Program &p) : g_(g), p_(p) { analyse(); }
+            Emitter(const sym::Graph &g, const Program &p, ConstTable *consts = nullptr)
+                : g_(g), p_(p), consts_(consts)
+            {
+                analyse();
+            }
 
             const ProgramStats &stats() const { return stats_; }
 
@@ -71,9 +141,14 @@ namespace grbda
 
             // Body text. Inputs are read through IN0(i)/IN1(i)/IN2(i), results written through
             // OUT0(i, x)/OUT1/OUT2; `real` is the arithmetic type; KC(x) makes a literal of type real.
-            std::string cudaBody() const
+            // sync_every > 0: emit GRBDA_ALIGN() after every `sync_every` statements. All warps of a CTA
+            // run the same straight-line code; keeping them within a few hundred instructions of each
+            // other lets them share instruction-cache lines (the kernels are instruction-fetch bound
+            // otherwise: ncu 'no_instruction' is the top stall of the unaligned version).
+            std::string cudaBody(int sync_every = 0) const
             {
                 std::ostringstream os;
+                int since_sync = 0;
                 std::vector<char> done(g_.nodes.size(), 0);
                 // node id -> list of (array, element) it must be stored to
                 std::vector<std::vector<std::pair<int, int>>> stores(g_.nodes.size());
@@ -138,7 +213,7 @@ namespace grbda
                             done[other] = 1;
                         }
                         else
-                            os << "const real t" << i << " = " << (n.op == sym::OP_SIN ? "sin(" : "cos(")
+                            os << "const real t" << i << " = " << (n.op == sym::OP_SIN ? "grbda_sin(" : "grbda_cos(")
                                << ref(n.a) << ");\n";
                         break;
                     }
@@ -147,6 +222,11 @@ namespace grbda
                     }
                     done[i] = 1;
                     emitStores(i);
+                    if (sync_every > 0 && ++since_sync >= sync_every)
+                    {
+                        os << "GRBDA_ALIGN();\n";
+                        since_sync = 0;
+                    }
                 }
                 return os.str();
             }
@@ -157,6 +237,8 @@ namespace grbda
                 const sym::Node &n = g_.nodes[id];
                 if (n.op == sym::OP_CONST)
                 {
+                    if (consts_)
+                        return consts_->ref(n.val);
                     char buf[64];
                     std::snprintf(buf, sizeof(buf), "KC(%.17g)", n.val);
                     return buf;
@@ -244,6 +326,7 @@ namespace grbda
 
             const sym::Graph &g_;
             const Program &p_;
+            ConstTable *consts_;
             std::vector<char> live_;
             std::vector<int> uses_;
             std::vector<int32_t> partner_;

@@ -281,8 +281,9 @@ namespace grbda
         class RoleEmitter
         {
         public:
-            RoleEmitter(const sym::Graph &g, const RolePartitioner &part, const RolePrograms &rp)
-                : g_(g), part_(part), rp_(rp) {}
+            RoleEmitter(const sym::Graph &g, const RolePartitioner &part, const RolePrograms &rp,
+                        ConstTable *consts = nullptr)
+                : g_(g), part_(part), rp_(rp), consts_(consts) {}
 
             ProgramStats roleStats(int r) const
             {
@@ -406,7 +407,7 @@ namespace grbda
                             defined[it->second] = 1;
                         }
                         else
-                            os << "const real t" << i << " = " << (n.op == sym::OP_SIN ? "sin(" : "cos(") << ref(n.a)
+                            os << "const real t" << i << " = " << (n.op == sym::OP_SIN ? "grbda_sin(" : "grbda_cos(") << ref(n.a)
                                << ");\n";
                         break;
                     }
@@ -429,6 +430,8 @@ namespace grbda
                     return "t" + std::to_string(id);
                 if (n.op == sym::OP_CONST)
                 {
+                    if (consts_)
+                        return consts_->ref(n.val);
                     char buf[64];
                     std::snprintf(buf, sizeof(buf), "KC(%.17g)", n.val);
                     return buf;
@@ -440,6 +443,7 @@ namespace grbda
             const sym::Graph &g_;
             const RolePartitioner &part_;
             const RolePrograms &rp_;
+            ConstTable *consts_;
         };
 
     } // namespace compiler

@@ -56,10 +56,11 @@ namespace
               "*__restrict__ in1,\n"
               "        const real *__restrict__ in2, real *__restrict__ out0, real *__restrict__ out1, "
               "real *__restrict__ out2)\n    {\n";
-        os << "#define KC(x) ((real)(x))\n#define IN0(i) in0[i]\n#define IN1(i) in1[i]\n#define IN2(i) in2[i]\n"
-              "#define OUT0(i, x) out0[i] = (x)\n#define OUT1(i, x) out1[i] = (x)\n#define OUT2(i, x) out2[i] = (x)\n";
+        os << "#define KC(x) ((real)(x))\n#define KT(i) kc_table<real>(i)\n#define IN0(i) in0[i]\n#define IN1(i) in1[i]\n#define IN2(i) in2[i]\n"
+              "#define OUT0(i, x) out0[i] = (x)\n#define OUT1(i, x) out1[i] = (x)\n#define OUT2(i, x) out2[i] = (x)\n"
+              "#define GRBDA_ALIGN() __syncthreads()\n";
         os << c.body;
-        os << "#undef KC\n#undef IN0\n#undef IN1\n#undef IN2\n#undef OUT0\n#undef OUT1\n#undef OUT2\n";
+        os << "#undef KC\n#undef KT\n#undef IN0\n#undef IN1\n#undef IN2\n#undef OUT0\n#undef OUT1\n#undef OUT2\n#undef GRBDA_ALIGN\n";
         os << "    }\n};\n";
     }
 
@@ -75,7 +76,7 @@ namespace
         os << "    static __device__ __forceinline__ void run(const int role, const real *__restrict__ in0,\n"
               "        const real *__restrict__ in1, const real *__restrict__ in2, real *__restrict__ out0,\n"
               "        real *__restrict__ out1, real *__restrict__ out2, real *__restrict__ comm)\n    {\n";
-        os << "#define KC(x) ((real)(x))\n#define IN0(i) in0[i]\n#define IN1(i) in1[i]\n#define IN2(i) in2[i]\n"
+        os << "#define KC(x) ((real)(x))\n#define KT(i) kc_table<real>(i)\n#define IN0(i) in0[i]\n#define IN1(i) in1[i]\n#define IN2(i) in2[i]\n"
               "#define OUT0(i, x) out0[i] = (x)\n#define OUT1(i, x) out1[i] = (x)\n#define OUT2(i, x) out2[i] = (x)\n"
               "#define COMM_ST(s, x) comm[(s) * 32] = (x)\n#define COMM_LD(s) comm[(s) * 32]\n"
               "#define ROLE_BARRIER() roleBarrier<W * 32>()\n";
@@ -87,7 +88,7 @@ namespace
             os << "        }\n        break;\n";
         }
         os << "        default: break;\n        }\n";
-        os << "#undef KC\n#undef IN0\n#undef IN1\n#undef IN2\n#undef OUT0\n#undef OUT1\n#undef OUT2\n"
+        os << "#undef KC\n#undef KT\n#undef IN0\n#undef IN1\n#undef IN2\n#undef OUT0\n#undef OUT1\n#undef OUT2\n"
               "#undef COMM_ST\n#undef COMM_LD\n#undef ROLE_BARRIER\n";
         os << "    }\n};\n";
     }
@@ -116,6 +117,7 @@ int main(int argc, char **argv)
     std::string model_name, urdf_dir = ".", out_dir = ".", algos = "id,fd,fk,h,phi,gen";
     std::string variants_s = "S,128,2";
     bool f32 = true;
+    int sync_every = 0;
     for (int i = 1; i < argc; i++)
     {
         const std::string a = argv[i];
@@ -140,6 +142,8 @@ int main(int argc, char **argv)
             variants_s = next();
         else if (a == "--no-f32")
             f32 = false;
+        else if (a == "--sync-every")
+            sync_every = std::atoi(next().c_str());
         else
         {
             std::fprintf(stderr, "unknown argument %s\n", a.c_str());
@@ -187,7 +191,8 @@ int main(int argc, char **argv)
                     a = k;
             if (a < 0)
                 throw std::runtime_error("unknown algorithm '" + algo + "'");
-            const CompiledAlgo c = compileAlgo(model, a, true);
+            ConstTable consts;
+            const CompiledAlgo c = compileAlgo(model, a, true, sync_every, &consts);
             if (a == ALGO_PHI && c.n_out[0] == 0)
                 continue; // no implicit clusters
             bool want_roles = false, want_single = false;
@@ -195,10 +200,11 @@ int main(int argc, char **argv)
                 (v.kind == 'R' ? want_roles : want_single) = true;
             CompiledRoles roles;
             if (want_roles && a != ALGO_PHI)
-                roles = compileAlgoRoles(model, a, true);
+                roles = compileAlgoRoles(model, a, true, &consts);
             const bool have_roles = want_roles && a != ALGO_PHI && roles.W > 1;
             std::ostringstream os;
             os << header_common;
+            os << consts.definition("kc_table");
             if (want_single || !have_roles)
                 emitBodyStruct(os, "Body", c);
             if (have_roles)
@@ -281,7 +287,7 @@ int main(int argc, char **argv)
                       "#define KC(x) ((real)(x))\n#define IN0(i) q[i]\n#define OUT0(i, x) phi[i] = (x)\n"
                       "#define OUT1(i, x) Kd[i] = (x)\n";
                 os << em.cudaBody();
-                os << "#undef KC\n#undef IN0\n#undef OUT0\n#undef OUT1\n    }\n};\n\n";
+                os << "#undef KC\n#undef KT\n#undef IN0\n#undef OUT0\n#undef OUT1\n    }\n};\n\n";
             }
             os << "struct Gen\n{\n    static constexpr int NQ = " << nq << ", NV = " << nv << ";\n";
             os << "    static __device__ bool run(Philox &rng, double *q, double *yd, double *aux)\n    {\n"
