@@ -46,6 +46,8 @@ _lib.grbda_cuda_model_destroy.argtypes = [_vp]
 _lib.grbda_cuda_cluster_info.argtypes = [_vp, C.c_int, _vp, _vp]
 _lib.grbda_cuda_body_info.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]
 _lib.grbda_cuda_cluster_G.argtypes = [_vp, C.c_int, _vp]
+_lib.grbda_cuda_model_gravity.argtypes = [_vp, _vp]
+_lib.grbda_cuda_cluster_phi.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp]
 _lib.grbda_cuda_dump_program.argtypes = [_vp, C.c_int, C.c_char_p, _vp]
 _lib.grbda_cuda_dump_role_program.argtypes = [_vp, C.c_int, C.c_char_p, _vp]
 for _p in ("f64", "f32"):
@@ -64,7 +66,7 @@ EXPORTED_SYMBOLS = [
     "grbda_cuda_model_create_from_urdf", "grbda_cuda_model_create_from_robot", "grbda_cuda_model_destroy",
     "grbda_cuda_num_positions", "grbda_cuda_num_degrees_of_freedom", "grbda_cuda_num_bodies",
     "grbda_cuda_num_clusters", "grbda_cuda_model_hash", "grbda_cuda_cluster_info", "grbda_cuda_body_info",
-    "grbda_cuda_cluster_G", "grbda_cuda_dump_program", "grbda_cuda_dump_role_program",
+    "grbda_cuda_cluster_G", "grbda_cuda_model_gravity", "grbda_cuda_cluster_phi", "grbda_cuda_dump_program", "grbda_cuda_dump_role_program",
     "grbda_cuda_inverse_dynamics_f64", "grbda_cuda_inverse_dynamics_f32",
     "grbda_cuda_forward_dynamics_f64", "grbda_cuda_forward_dynamics_f32",
     "grbda_cuda_mass_matrix_f64", "grbda_cuda_mass_matrix_f32",
@@ -74,6 +76,9 @@ EXPORTED_SYMBOLS = [
 ]
 
 DEFAULT_SEED = 0x6772626461  # "grbda"
+# layout of grbda_phi_op (int32 op, a, b; 4 bytes padding; float64 val)
+PHI_OP_DTYPE = np.dtype({"names": ["op", "a", "b", "val"], "formats": [np.int32, np.int32, np.int32, np.float64],
+                         "offsets": [0, 4, 8, 16], "itemsize": 24})
 
 
 class GrbdaError(RuntimeError):
@@ -186,6 +191,15 @@ class ClusterTreeModel:
                 G = np.zeros((d["num_bodies"], d["num_velocities"]))
                 _check(_lib.grbda_cuda_cluster_G(self._h, c, G.ctypes.data_as(_vp)))
                 d["G"] = G
+            elif d["type"] == 3:
+                sizes = (C.c_int32 * 2)()
+                _check(_lib.grbda_cuda_cluster_phi(self._h, c, None, None, None, sizes))
+                ops = np.zeros(sizes[0], dtype=PHI_OP_DTYPE)
+                outs = np.zeros(sizes[1], dtype=np.int32)
+                ind = np.zeros(d["num_bodies"], dtype=np.uint8)
+                _check(_lib.grbda_cuda_cluster_phi(self._h, c, ops.ctypes.data_as(_vp), outs.ctypes.data_as(_vp),
+                                                   ind.ctypes.data_as(_vp), sizes))
+                d["phi_ops"], d["phi_outputs"], d["independent"] = ops, outs, ind.astype(bool)
             out.append(d)
         return out
 
@@ -200,6 +214,11 @@ class ClusterTreeModel:
             out.append(dict(name=name.value.decode(), parent=info[0], cluster=info[1], sub_index=info[2],
                             axis=info[3], E=E, r=r, inertia=I))
         return out
+
+    def getGravity(self):
+        g = np.zeros(3)
+        _check(_lib.grbda_cuda_model_gravity(self._h, g.ctypes.data_as(_vp)))
+        return g
 
     def dump_program(self, algo, path=None):
         counts = (C.c_int64 * 8)()

@@ -25,8 +25,12 @@ LIB = os.path.join(HERE, "libgrbda_cuda.so")
 DEFAULT_VARIANTS = "S,128,2"
 SYNC_EVERY = int(os.environ.get("GRBDA_SYNC_EVERY", "256"))
 MODELS = {
-    "tello_with_arms": ("id,fd,fk,h,phi,gen", "S,128,2;S,256,1;D,256,1;S,64,4", True),
+    "tello_with_arms": ("id,fd,fk,h,phi,gen", "S,128,2;D,128,2", True),
     "tello": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
+    "mini_cheetah": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
+    "mit_humanoid": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
+    "four_bar": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, True),
+    "revolute_rotor_chain": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, False),
     "revolute_chain_with_rotor_2": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_4": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, False),
     "revolute_pair_chain_with_rotor_2": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, False),

@@ -252,6 +252,35 @@ extern "C"
         std::memcpy(G, d.G.data(), d.G.size() * 8);
         return GRBDA_OK;
     }
+    grbda_status grbda_cuda_model_gravity(const grbda_model *m, double *gravity3)
+    {
+        if (!m || !gravity3)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        for (int i = 0; i < 3; i++)
+            gravity3[i] = m->model.getGravity()[i];
+        return GRBDA_OK;
+    }
+    grbda_status grbda_cuda_cluster_phi(const grbda_model *m, int cluster, grbda_phi_op *ops, int32_t *outputs,
+                                        uint8_t *independent, int32_t *sizes2)
+    {
+        if (!m || cluster < 0 || cluster >= m->model.getNumClusters() || !sizes2)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad cluster index");
+        const ClusterDesc &d = m->model.clusters()[cluster].joint_;
+        if (d.type != ClusterType::Implicit)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "cluster has no implicit constraint");
+        sizes2[0] = (int32_t)d.phi.ops.size();
+        sizes2[1] = (int32_t)d.phi.outputs.size();
+        if (ops)
+            for (size_t i = 0; i < d.phi.ops.size(); i++)
+                ops[i] = grbda_phi_op{d.phi.ops[i].op, d.phi.ops[i].a, d.phi.ops[i].b, d.phi.ops[i].val};
+        if (outputs)
+            for (size_t i = 0; i < d.phi.outputs.size(); i++)
+                outputs[i] = d.phi.outputs[i];
+        if (independent)
+            for (size_t i = 0; i < d.independent.size(); i++)
+                independent[i] = d.independent[i];
+        return GRBDA_OK;
+    }
     grbda_status grbda_cuda_dump_program(const grbda_model *m, int algo, const char *path, int64_t *counts8)
     {
         if (!m || algo < 0 || algo >= compiler::ALGO_COUNT)

@@ -129,6 +129,11 @@ grbda_status grbda_cuda_cluster_info(const grbda_model *m, int cluster, int32_t 
 /* body: info[4] = {parent, cluster, sub_index_within_cluster, joint_axis} */
 grbda_status grbda_cuda_body_info(const grbda_model *m, int body, char *name64, int32_t *info4,
                                   double *xtree_E9, double *xtree_r3, double *inertia36);
+grbda_status grbda_cuda_model_gravity(const grbda_model *m, double *gravity3);
+/* implicit cluster: its phi program and independence flags. Pass ops = NULL to query the sizes:
+ * sizes2 = {number of ops, number of phi rows}. */
+grbda_status grbda_cuda_cluster_phi(const grbda_model *m, int cluster, grbda_phi_op *ops, int32_t *outputs,
+                                    uint8_t *independent, int32_t *sizes2);
 /* explicit cluster: G (num_bodies x num_independent, row-major) */
 grbda_status grbda_cuda_cluster_G(const grbda_model *m, int cluster, double *G);
 /* Emitted program of one algorithm (0 ID, 1 FD, 2 FK, 3 H, 4 phi/Kd) written as a binary tape to

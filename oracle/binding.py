@@ -200,6 +200,18 @@ class OracleBuilder:
         lib().oracle_builder_append_generic_loops(self._h, name.encode(), (C.c_int * len(axes))(*axes),
                                                   (C.c_int * len(axes))(*[int(x) for x in independent]))
 
+    def append_generic_phi(self, name, axes, independent, ops, outputs):
+        """ops: structured array with fields op, a, b, val (generalized_rbda_b200.PHI_OP_DTYPE)"""
+        ci = lambda x: np.ascontiguousarray(x, dtype=np.int32)
+        op, a, b = ci(ops["op"]), ci(ops["a"]), ci(ops["b"])
+        val = np.ascontiguousarray(ops["val"], dtype=np.float64)
+        out = ci(outputs)
+        ip = C.POINTER(C.c_int)
+        lib().oracle_builder_append_generic_phi(self._h, name.encode(), (C.c_int * len(axes))(*axes),
+                                                (C.c_int * len(axes))(*[int(x) for x in independent]),
+                                                op.ctypes.data_as(ip), a.ctypes.data_as(ip), b.ctypes.data_as(ip),
+                                                _P(val), len(op), out.ctypes.data_as(ip), len(out))
+
     def finish(self, generic=False):
         _check(lib().oracle_builder_finish(self._h, int(generic)))
         h, self._h = self._h, None

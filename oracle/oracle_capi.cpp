@@ -43,6 +43,9 @@ namespace
         std::vector<int> loop_rows; // rows (0..2) of each loop that are kept, flattened (loop, axis)
         double gear[2] = {0, 0};
         std::vector<double> belt1, belt2;
+        // kind 8: phi given as a straight-line op list (op, a, b, val), see include/grbda_cuda.h
+        std::vector<int> phi_op, phi_a, phi_b, phi_out;
+        std::vector<double> phi_val;
     };
     struct ModelSpec
     {
@@ -189,6 +192,49 @@ namespace
                                 if (rows[3 * l + j])
                                     out.push_back(rp[j] - rs[j]);
                         }
+                        return out;
+                    };
+                    joint = std::make_shared<GenericCluster<T>>(
+                        bodies, joints, std::make_shared<GenericImplicitConstraint<T>>(ind, phi));
+                    break;
+                }
+                case 8:
+                {
+                    JointVec<T> joints;
+                    for (int i = 0; i < N; i++)
+                        joints.push_back(std::make_shared<SingleRevolute<T>>((Axis)c.axes[i]));
+                    std::vector<bool> ind;
+                    for (int v : c.independent)
+                        ind.push_back(v != 0);
+                    using S = Taylor2<T>;
+                    const ClusterCmd cc = c;
+                    auto phi = [cc](const std::vector<S> &q)
+                    {
+                        std::vector<S> v;
+                        for (size_t i = 0; i < cc.phi_op.size(); i++)
+                        {
+                            const int a = cc.phi_a[i], b = cc.phi_b[i];
+                            switch (cc.phi_op[i])
+                            {
+                            case 0: v.push_back(S(cc.phi_val[i])); break;
+                            case 1: v.push_back(q[b]); break;
+                            case 2: v.push_back(v[a] + v[b]); break;
+                            case 3: v.push_back(v[a] - v[b]); break;
+                            case 4: v.push_back(v[a] * v[b]); break;
+                            case 5:
+                                if (cc.phi_op[b] != 0)
+                                    throw std::runtime_error("oracle: phi division by a non-constant");
+                                v.push_back(v[a] / cc.phi_val[b]);
+                                break;
+                            case 6: v.push_back(-v[a]); break;
+                            case 7: v.push_back(sin(v[a])); break;
+                            case 8: v.push_back(cos(v[a])); break;
+                            default: throw std::runtime_error("oracle: unsupported phi op");
+                            }
+                        }
+                        std::vector<S> out;
+                        for (int o : cc.phi_out)
+                            out.push_back(v[o]);
                         return out;
                     };
                     joint = std::make_shared<GenericCluster<T>>(
@@ -423,6 +469,26 @@ extern "C"
         c.kind = 5;
         c.axes.assign(axes, axes + N);
         c.independent.assign(independent, independent + N);
+        h->spec.clusters.push_back(c);
+        h->spec.pending = ClusterCmd();
+    }
+    // phi as an op list: op/a/b (int, n_ops), val (double, n_ops), outputs (int, n_out)
+    void oracle_builder_append_generic_phi(void *hv, const char *name, const int *axes, const int *independent,
+                                           const int *op, const int *a, const int *b, const double *val,
+                                           int n_ops, const int *outputs, int n_out)
+    {
+        Handle *h = (Handle *)hv;
+        ClusterCmd &c = h->spec.pending;
+        const int N = (int)c.bodies.size();
+        c.name = name;
+        c.kind = 8;
+        c.axes.assign(axes, axes + N);
+        c.independent.assign(independent, independent + N);
+        c.phi_op.assign(op, op + n_ops);
+        c.phi_a.assign(a, a + n_ops);
+        c.phi_b.assign(b, b + n_ops);
+        c.phi_val.assign(val, val + n_ops);
+        c.phi_out.assign(outputs, outputs + n_out);
         h->spec.clusters.push_back(c);
         h->spec.pending = ClusterCmd();
     }

@@ -110,6 +110,83 @@ def test_limb_parallel_programs_match_oracle(grbda, oracle, robot, tmp_path):
     assert grbda.ClusterTreeModel.from_robot("revolute_chain_with_rotor_4", device=None).dump_role_program(1)["W"] == 1
 
 
+# URDF+ models: product (URDF front end) against the oracle's hand-coded builders — the reference's
+# UnitTests/testClusterTreeModel.cpp:100-230 (URDFvsManual) restated across the two implementations
+@pytest.mark.parametrize("robot", ["mini_cheetah", "mit_humanoid"])
+def test_urdf_model_equals_manual_builder(grbda, oracle, robot, tmp_path):
+    m = grbda.ClusterTreeModel.from_robot(robot, device=None)
+    o = oracle.OracleModel(robot)
+    assert (m.nq, m.nv, m.nb, m.nc) == (o.nq, o.nv, o.nb, o.nc)
+    assert [b["name"] for b in m.bodies()] == [b["name"] for b in o.bodies()]
+    for a, b in zip(m.bodies(), o.bodies()):
+        assert a["parent"] == b["parent"] and a["cluster"] == b["cluster"] and a["sub_index"] == b["sub_index"]
+        assert np.abs(a["E"] - b["E"]).max() < 1e-15 and np.abs(a["r"] - b["r"]).max() < 1e-15
+        assert np.abs(a["inertia"] - b["inertia"]).max() < 1e-12
+    q, yd, aux = o.generate_states(32, seed=13)
+    ins = [q, yd, aux]
+    tapes = {}
+    for algo, name in enumerate(grbda.ALGO_NAMES[:4]):
+        path = str(tmp_path / name)
+        m.dump_program(algo, path)
+        tapes[name] = load_tape(path)
+    assert rel(run_tape(tapes["id"], ins)[0], o.inverse_dynamics(q, yd, aux)) < TOL
+    assert rel(run_tape(tapes["fd"], ins)[0], o.forward_dynamics(q, yd, aux)) < 1e-9  # reference tol * 10
+    assert rel(run_tape(tapes["h"], ins)[0].reshape(-1, o.nv, o.nv), o.mass_matrix(q)) < TOL
+
+
+@pytest.mark.parametrize("robot", ["four_bar", "revolute_rotor_chain", "mini_cheetah"])
+def test_urdf_models_against_mirrored_oracle(grbda, oracle, robot, tmp_path):
+    """Models that exist only as URDF+ files: the oracle is assembled from the product's topology
+    (tests/mirror.py) and evaluates the dynamics with its own dense cluster algorithms."""
+    from mirror import mirror_to_oracle
+    m = grbda.ClusterTreeModel.from_robot(robot, device=None)
+    o = mirror_to_oracle(m, oracle)
+    assert (m.nq, m.nv, m.nb, m.nc) == (o.nq, o.nv, o.nb, o.nc)
+    q, yd, aux = o.generate_states(32, seed=17)
+    assert o.validate_states(q).all()
+    ins = [q, yd, aux]
+    tapes = {}
+    for algo, name in enumerate(grbda.ALGO_NAMES):
+        path = str(tmp_path / name)
+        m.dump_program(algo, path)
+        tapes[name] = load_tape(path)
+    assert rel(run_tape(tapes["id"], ins)[0], o.inverse_dynamics(q, yd, aux)) < TOL
+    assert rel(run_tape(tapes["fd"], ins)[0], o.forward_dynamics(q, yd, aux)) < TOL
+    assert rel(run_tape(tapes["h"], ins)[0].reshape(-1, o.nv, o.nv), o.mass_matrix(q)) < TOL
+    p, R, v = o.forward_kinematics(q, yd)
+    fk = run_tape(tapes["fk"], ins)
+    assert rel(fk[0].reshape(p.shape), p) < TOL and rel(fk[2].reshape(v.shape), v) < TOL
+    if robot == "four_bar":
+        # geometry of robot-models/four_bar.urdf:60-90 checked directly: the loop joint closes, i.e.
+        # the constraint point reached through link1-link2 equals the one reached through link3
+        assert [c["type"] for c in m.clusters()] == [3] and m.clusters()[0]["independent"].tolist() == [True, False, False]
+        q1, q2, q3 = q[:, 0], q[:, 1], q[:, 2]
+        via_pred = np.stack([0.5 * np.cos(q1) + np.cos(q1 + q2), 0.5 * np.sin(q1) + np.sin(q1 + q2)], 1)
+        via_succ = np.stack([1.0 + 0.5 * np.cos(q3), 0.5 * np.sin(q3)], 1)
+        assert np.abs(via_pred - via_succ).max() < 1e-8
+        assert np.abs(run_tape(tapes["phi"], ins)[0]).max() < 1e-8
+        assert tapes["phi"]["outs"][0].shape[0] == 2  # the z row does not depend on q and is dropped
+
+
+def test_urdf_parser_structure(grbda):
+    """Structure pinned by the reference's UnitTests/testUrdfParser.cpp / testClusterTreeModel.cpp."""
+    m = grbda.ClusterTreeModel.from_robot("mini_cheetah", device=None)
+    names = [b["name"] for b in m.bodies()]
+    # legs in the order of MiniCheetah.cpp:29 {HR, HL, FR, FL}; link before rotor in every cluster
+    assert names[0] == "Floating Base" and [n[:2] for n in names[1::6]] == ["HR", "HL", "FR", "FL"]
+    assert all(c["num_bodies"] == 2 and c["joint_type"] == "Generic" for c in m.clusters()[1:])
+    g = m.clusters()[3]["G"]
+    assert g.shape == (2, 1) and g[0, 0] == 1.0 and abs(g[1, 0] - 9.33) < 1e-12  # knee gear ratio
+    m = grbda.ClusterTreeModel.from_robot("mit_humanoid", device=None)
+    knee = [c for c in m.clusters() if c["num_bodies"] == 4][0]
+    body_names = [b["name"] for b in m.bodies()][knee["first_body"]:knee["first_body"] + 4]
+    # MIT_Humanoid.cpp:172-179: ankle_rotor, knee_link, knee_rotor, ankle_link
+    assert [n.split("_", 1)[1] for n in body_names] == ["ankle_rotor", "knee_link", "knee_rotor", "ankle_link"]
+    assert np.allclose(knee["G"], [[12.0, 12.0], [1.0, 0.0], [12.0, 0.0], [0.0, 1.0]])
+    with pytest.raises(grbda.GrbdaError):
+        grbda.ClusterTreeModel.from_urdf("/nonexistent.urdf", device=None)
+
+
 def test_schedule_round_trip(grbda):
     """model -> grbda_schedule -> grbda_cuda_model_create reproduces the same model (same hash)."""
     import struct
