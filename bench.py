@@ -141,6 +141,7 @@ def main():
     import torch
     import torch.distributed as dist
     import generalized_rbda_b200 as grbda
+    from generalized_rbda_b200.sharding import gather_summary, weak_shard
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -153,7 +154,8 @@ def main():
     m = grbda.ClusterTreeModel.from_robot(args.model, device=local_rank)
     B = args.batch
     # contiguous shard of the global index range, generated on this GPU
-    q, yd, tau, flags = m.generateStates(B, first_index=rank * B)
+    first_index, _ = weak_shard(B, rank)
+    q, yd, tau, flags = m.generateStates(B, first_index=first_index)
     ydd = torch.empty_like(tau)
     tau_back = torch.empty_like(tau)
     assert int(flags.sum()) == 0
@@ -205,9 +207,9 @@ def main():
 
     # parity spot check + checksum gather (the only collective)
     err = float(((tau_back - tau).abs().amax(1) / tau.abs().amax(1)).median())
-    cs = torch.tensor(list(grbda.checksum(ydd)), dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(cs)
+    # the only collective: per-rank checksum / timing summary
+    summary = gather_summary(list(grbda.checksum(ydd)) + [ms], device=dev)
+    cs = summary[:, :2].sum(0)
 
     e2e = None
     if not args.no_e2e:

@@ -10,11 +10,22 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+# product robot -> oracle robot (hand-coded builder restated from the reference) or None = the oracle is
+# assembled from the product's topology (tests/mirror.py; URDF-only models)
 ROBOTS = {"tello": "tello", "tello_with_arms": "tello_with_arms",
+          "mini_cheetah": "mini_cheetah", "mit_humanoid": "mit_humanoid",
+          "four_bar": None, "revolute_rotor_chain": None,
           "revolute_chain_with_rotor_2": "revolute_chain_with_rotor_2",
           "revolute_chain_with_rotor_4": "revolute_chain_with_rotor_4",
           "revolute_pair_chain_with_rotor_2": "revolute_pair_chain_with_rotor_2",
           "revolute_pair_chain_with_rotor_4": "revolute_pair_chain_with_rotor_4"}
+
+
+def oracle_for(oracle, m, robot):
+    if ROBOTS[robot] is not None:
+        return oracle.OracleModel(ROBOTS[robot])
+    from mirror import mirror_to_oracle
+    return mirror_to_oracle(m, oracle)
 TOL64, TOL32 = 1e-10, 1e-4
 
 
@@ -38,7 +49,7 @@ def torch():
 @pytest.mark.parametrize("robot", sorted(ROBOTS))
 def test_state_generator_matches_oracle(grbda, oracle, torch, robot):
     m = grbda.ClusterTreeModel.from_robot(robot)
-    o = oracle.OracleModel(ROBOTS[robot])
+    o = oracle_for(oracle, m, robot)
     q, yd, aux, flags = m.generateStates(777, seed=123, first_index=1000)
     assert int(flags.sum()) == 0
     qo, ydo, auxo = o.generate_states(777, seed=123, first_index=1000)
@@ -53,7 +64,7 @@ def test_state_generator_matches_oracle(grbda, oracle, torch, robot):
 @pytest.mark.parametrize("robot", sorted(ROBOTS))
 def test_dynamics_parity_f64(grbda, oracle, torch, robot):
     m = grbda.ClusterTreeModel.from_robot(robot)
-    o = oracle.OracleModel(ROBOTS[robot])
+    o = oracle_for(oracle, m, robot)
     B = 1000  # not a multiple of the CTA size: exercises the ragged last tile
     q, yd, aux, _ = m.generateStates(B, seed=42)
     qn, ydn, auxn = q.cpu().numpy(), yd.cpu().numpy(), aux.cpu().numpy()
@@ -67,11 +78,11 @@ def test_dynamics_parity_f64(grbda, oracle, torch, robot):
     assert relrows(C, o.inverse_dynamics(qn, ydn, np.zeros_like(ydn))) < TOL64
 
 
-@pytest.mark.parametrize("robot", ["tello_with_arms", "revolute_chain_with_rotor_2"])
+@pytest.mark.parametrize("robot", ["tello_with_arms", "mini_cheetah", "mit_humanoid", "revolute_chain_with_rotor_2"])
 def test_dynamics_parity_f32(grbda, oracle, torch, robot):
     """FP32 variant against the FP64 oracle on float-rounded states."""
     m = grbda.ClusterTreeModel.from_robot(robot)
-    o = oracle.OracleModel(ROBOTS[robot])
+    o = oracle_for(oracle, m, robot)
     q, yd, aux, _ = m.generateStates(512, seed=4)
     q32, yd32, aux32 = q.float(), yd.float(), aux.float()
     qn, ydn, auxn = (x.double().cpu().numpy() for x in (q32, yd32, aux32))
