@@ -56,6 +56,7 @@ for _p in ("f64", "f32"):
     getattr(_lib, "grbda_cuda_mass_matrix_" + _p).argtypes = [_vp, _vp, _vp, _i64, _vp]
     getattr(_lib, "grbda_cuda_forward_kinematics_" + _p).argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
 _lib.grbda_cuda_dynamics_host_f64.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _i64]
+_lib.grbda_cuda_forward_inverse_host_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64]
 _lib.grbda_cuda_generate_states.argtypes = [_vp, C.c_uint64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]
 _lib.grbda_cuda_constraint_violation_f64.argtypes = [_vp, _vp, _vp, _i64, _vp]
 _lib.grbda_cuda_checksum_f64.argtypes = [_vp, _i64, _vp, _vp]
@@ -71,7 +72,7 @@ EXPORTED_SYMBOLS = [
     "grbda_cuda_forward_dynamics_f64", "grbda_cuda_forward_dynamics_f32",
     "grbda_cuda_mass_matrix_f64", "grbda_cuda_mass_matrix_f32",
     "grbda_cuda_forward_kinematics_f64", "grbda_cuda_forward_kinematics_f32",
-    "grbda_cuda_dynamics_host_f64", "grbda_cuda_generate_states", "grbda_cuda_constraint_violation_f64",
+    "grbda_cuda_dynamics_host_f64", "grbda_cuda_forward_inverse_host_f64", "grbda_cuda_generate_states", "grbda_cuda_constraint_violation_f64",
     "grbda_cuda_checksum_f64", "grbda_cuda_measure_fma_peak", "grbda_cuda_launch_count",
 ]
 
@@ -310,6 +311,14 @@ class ClusterTreeModel:
         batch = q.shape[0]
         _check(_lib.grbda_cuda_dynamics_host_f64(self._h, algo, hp(q), hp(yd), hp(in3), hp(out), batch))
         return out
+
+    def forward_inverse_host(self, q, yd, tau, ydd, tau_back):
+        """One benchmark step on HOST arrays: ydd = FD(q, yd, tau), tau_back = ID(q, yd, ydd)."""
+        def hp(a):
+            return _vp(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
+        _check(_lib.grbda_cuda_forward_inverse_host_f64(self._h, hp(q), hp(yd), hp(tau), hp(ydd), hp(tau_back),
+                                                        q.shape[0]))
+        return ydd, tau_back
 
     # ---- synthetic states / checks --------------------------------------------------------------
     def generateStates(self, count, seed=DEFAULT_SEED, first_index=0, device=None):

@@ -21,11 +21,17 @@ BUILD = os.path.join(HERE, "_build")
 URDF_DIR = os.path.join(HERE, "robot-models")
 LIB = os.path.join(HERE, "libgrbda_cuda.so")
 
-# model name -> (algorithms, launch variants "BLOCK,MIN_BLOCKS,STAGED;...", build f32 variants)
-DEFAULT_VARIANTS = "S,128,2"
+# model name -> (algorithms, launch variants, build f32 variants). A variant is KIND,BLOCK,MIN_BLOCKS with
+# KIND = T (TMA bulk-copy staged tiles), S (software-staged tiles), D (direct global access),
+# R (one limb per warp); up to four ';'-separated variants per kernel, the first is the default,
+# GRBDA_KERNEL_VARIANT selects another one at run time (tools/sweep_variants.py).
+# Measured on B200 (profiles/): ID and the kinematics kernels do not spill and are fastest with TMA
+# staging; FD spills ~2.5 KB per thread to local memory and needs the L1 capacity that the TMA tiles
+# would take, so it keeps the smaller software-staged tiles.
+DEFAULT_VARIANTS = "id=T,128,2;S,128,2|fd=S,128,2;T,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2"
 SYNC_EVERY = int(os.environ.get("GRBDA_SYNC_EVERY", "256"))
 MODELS = {
-    "tello_with_arms": ("id,fd,fk,h,phi,gen", "S,128,2;D,128,2", True),
+    "tello_with_arms": ("id,fd,fk,h,phi,gen", "id=T,128,2;S,128,2;D,128,2;T,256,1|fd=S,128,2;T,128,2;S,64,4;T,64,4|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2", True),
     "tello": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
     "mini_cheetah": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
     "mit_humanoid": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),

@@ -250,6 +250,203 @@ namespace grbda_kernels
     }
 
     // ---------------------------------------------------------------------------------------------
+    // TMA-staged shell (variant 'T'): the CTA's input tiles are brought into shared memory by the
+    // bulk-copy engine (cp.async.bulk, SASS UBLKCP) instead of by load/store instructions of the
+    // compute warps: the straight-line bodies are instruction-issue bound, and a software copy of
+    // 81 + 24 values per state costs ~10 % of all issued instructions. One mbarrier tracks the
+    // transaction bytes. Results leave the same way (cp.async.bulk shared -> global).
+    //   * an array whose rows are a multiple of 16 bytes (FP64: even N, FP32: N % 4 == 0) is copied row
+    //     by row, one bulk copy per thread, into rows padded by 16 bytes (keeps the alignment the bulk
+    //     engine needs and breaks the power-of-two stride: at most 2-way bank conflicts);
+    //   * any other array is copied as one dense tile (row stride N; conflict-free for odd N).
+    // Requires 16-byte aligned array base pointers (checked on the host, which otherwise picks the
+    // software-staged shell above).
+    // ---------------------------------------------------------------------------------------------
+    template <typename real>
+    __host__ __device__ constexpr bool tmaRowWise(int n) { return n > 0 && (n * sizeof(real)) % 16 == 0; }
+    template <typename real>
+    __host__ __device__ constexpr int tmaStride(int n) { return tmaRowWise<real>(n) ? n + 16 / (int)sizeof(real) : n; }
+
+    __device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+    __device__ __forceinline__ void mbarInit(uint64_t *bar, uint32_t count)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __device__ __forceinline__ void mbarArriveExpectTx(uint64_t *bar, uint32_t bytes)
+    {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes)
+                     : "memory");
+    }
+    __device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity)
+    {
+        asm volatile("{\n"
+                     ".reg .pred p;\n"
+                     "WAIT_%=:\n"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                     "@p bra DONE_%=;\n"
+                     "bra WAIT_%=;\n"
+                     "DONE_%=:\n"
+                     "}" ::"r"(smemAddr(bar)),
+                     "r"(parity)
+                     : "memory");
+    }
+    __device__ __forceinline__ void bulkGlobalToShared(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+    {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smemAddr(dst)),
+                     "l"(src), "r"(bytes), "r"(smemAddr(bar))
+                     : "memory");
+    }
+    __device__ __forceinline__ void bulkSharedToGlobal(void *dst, const void *src, uint32_t bytes)
+    {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smemAddr(src)),
+                     "r"(bytes)
+                     : "memory");
+    }
+
+    // bytes thread `t` contributes to the tile of one input array, and the copies themselves
+    template <typename real, int N>
+    __device__ __forceinline__ uint32_t tmaTileBytes(int t, int rows)
+    {
+        if (N == 0)
+            return 0;
+        if (!tmaRowWise<real>(N)) // dense tile, issued by thread 0; a tail of < 16 bytes is copied by hand
+            return t == 0 ? (uint32_t)(((size_t)rows * N * sizeof(real)) & ~(size_t)15) : 0u;
+        return t < rows ? (uint32_t)(N * sizeof(real)) : 0u;
+    }
+    template <typename real, int N>
+    __device__ __forceinline__ void tmaTileIssue(const real *__restrict__ g, real *s, int t, int rows, uint64_t *bar)
+    {
+        if (N == 0)
+            return;
+        if (!tmaRowWise<real>(N))
+        {
+            if (t == 0)
+            {
+                const size_t total = (size_t)rows * N * sizeof(real);
+                const size_t bulk = total & ~(size_t)15;
+                if (bulk)
+                    bulkGlobalToShared(s, g, (uint32_t)bulk, bar);
+                for (size_t k = bulk / sizeof(real); k < total / sizeof(real); k++)
+                    s[k] = g[k]; // ordered before the waiters by this thread's mbarrier arrive (release)
+            }
+        }
+        else if (t < rows)
+            bulkGlobalToShared(s + (size_t)t * tmaStride<real>(N), g + (size_t)t * N, (uint32_t)(N * sizeof(real)), bar);
+    }
+
+    template <typename Body, typename real, int BLOCK>
+    struct TmaLayout
+    {
+        static constexpr int S0 = tmaStride<real>(Body::N_IN0), S1 = tmaStride<real>(Body::N_IN1),
+                             S2 = tmaStride<real>(Body::N_IN2);
+        static constexpr bool STAGE_OUT0 = Body::N_OUT0 <= 64;
+        static constexpr int SO = STAGE_OUT0 ? tmaStride<real>(Body::N_OUT0) : 0;
+        // byte offsets; every tile starts on a 16-byte boundary, the first 16 bytes hold the mbarrier
+        static constexpr size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+        static constexpr size_t OFF0 = 16;
+        static constexpr size_t OFF1 = align16(OFF0 + (size_t)S0 * BLOCK * sizeof(real));
+        static constexpr size_t OFF2 = align16(OFF1 + (size_t)S1 * BLOCK * sizeof(real));
+        static constexpr size_t OFFO = align16(OFF2 + (size_t)S2 * BLOCK * sizeof(real));
+        static constexpr size_t BYTES = align16(OFFO + (size_t)SO * BLOCK * sizeof(real));
+    };
+
+    template <typename real, typename Body, int BLOCK, int MIN_BLOCKS>
+    __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
+        grbda_batched_kernel_tma(const real *__restrict__ in0, const real *__restrict__ in1,
+                                 const real *__restrict__ in2, real *__restrict__ out0,
+                                 real *__restrict__ out1, real *__restrict__ out2, int64_t batch)
+    {
+        using L = TmaLayout<Body, real, BLOCK>;
+        extern __shared__ __align__(128) unsigned char smem_raw[];
+        uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+        real *s0 = reinterpret_cast<real *>(smem_raw + L::OFF0);
+        real *s1 = reinterpret_cast<real *>(smem_raw + L::OFF1);
+        real *s2 = reinterpret_cast<real *>(smem_raw + L::OFF2);
+        real *so = reinterpret_cast<real *>(smem_raw + L::OFFO);
+
+        const int64_t first = (int64_t)blockIdx.x * BLOCK;
+        const int64_t remaining = batch - first;
+        const int rows = remaining < BLOCK ? (int)remaining : BLOCK;
+        const int tid = threadIdx.x;
+
+        if (tid == 0)
+            mbarInit(bar, BLOCK);
+        __syncthreads();
+        {
+            const real *g0 = in0 + first * Body::N_IN0, *g1 = in1 + first * Body::N_IN1, *g2 = in2 + first * Body::N_IN2;
+            const uint32_t bytes = tmaTileBytes<real, Body::N_IN0>(tid, rows) + tmaTileBytes<real, Body::N_IN1>(tid, rows) +
+                                   tmaTileBytes<real, Body::N_IN2>(tid, rows);
+            tmaTileIssue<real, Body::N_IN0>(g0, s0, tid, rows, bar);
+            tmaTileIssue<real, Body::N_IN1>(g1, s1, tid, rows, bar);
+            tmaTileIssue<real, Body::N_IN2>(g2, s2, tid, rows, bar);
+            mbarArriveExpectTx(bar, bytes);
+        }
+        mbarWait(bar, 0);
+
+        // every thread runs the body (alignment barriers inside); tail threads redo the last valid state
+        const int t = min(tid, rows - 1);
+        const int64_t state = first + t;
+        real *o0 = L::STAGE_OUT0 ? so + t * L::SO : out0 + state * Body::N_OUT0;
+        real *o1 = Body::N_OUT1 ? out1 + state * Body::N_OUT1 : nullptr;
+        real *o2 = Body::N_OUT2 ? out2 + state * Body::N_OUT2 : nullptr;
+        Body::template run<real>(s0 + t * L::S0, s1 + t * L::S1, s2 + t * L::S2, o0, o1, o2);
+
+        if (L::STAGE_OUT0)
+        {
+            // generic-proxy writes to shared memory -> visible to the bulk-copy (async) proxy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            real *g = out0 + first * Body::N_OUT0;
+            if (!tmaRowWise<real>(Body::N_OUT0))
+            {
+                if (tid == 0)
+                {
+                    const size_t total = (size_t)rows * Body::N_OUT0 * sizeof(real);
+                    const size_t bulk = total & ~(size_t)15;
+                    if (bulk)
+                        bulkSharedToGlobal(g, so, (uint32_t)bulk);
+                    for (size_t k = bulk / sizeof(real); k < total / sizeof(real); k++)
+                        g[k] = so[k];
+                }
+            }
+            else if (tid < rows)
+                bulkSharedToGlobal(g + (size_t)tid * Body::N_OUT0, so + (size_t)tid * L::SO,
+                                   (uint32_t)(Body::N_OUT0 * sizeof(real)));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    }
+
+    template <typename real, typename Body, int BLOCK, int MIN_BLOCKS>
+    cudaError_t launchBatchedTma(const LaunchArgs &a)
+    {
+        // the bulk-copy engine needs 16-byte aligned global addresses
+        uintptr_t bits = 0;
+        for (int i = 0; i < 3; i++)
+            bits |= (uintptr_t)a.in[i];
+        bits |= (uintptr_t)a.out[0];
+        if (bits & 15)
+            return launchBatched<real, Body, BLOCK, MIN_BLOCKS, true>(a);
+        using L = TmaLayout<Body, real, BLOCK>;
+        auto kernel = grbda_batched_kernel_tma<real, Body, BLOCK, MIN_BLOCKS>;
+        if (L::BYTES > 48 * 1024)
+        {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES);
+            if (e != cudaSuccess)
+                return e;
+        }
+        if (a.batch <= 0)
+            return cudaSuccess;
+        const int64_t grid = (a.batch + BLOCK - 1) / BLOCK;
+        kernel<<<(unsigned)grid, BLOCK, L::BYTES, a.stream>>>(
+            (const real *)a.in[0], (const real *)a.in[1], (const real *)a.in[2], (real *)a.out[0],
+            (real *)a.out[1], (real *)a.out[2], a.batch);
+        return cudaGetLastError();
+    }
+
+    // ---------------------------------------------------------------------------------------------
     // Limb-parallel shell: ONE STATE PER LANE, ONE LIMB PER WARP (compiler/partition.h).
     // A CTA of W warps evaluates 32 states; warp w runs the straight-line program of limb
     // (w + blockIdx.x) % W (rotated so that heavy and light limbs spread over the four schedulers of

@@ -364,12 +364,10 @@ extern "C"
     }
 
     // ---- host-pointer path: chunks pipelined over three streams --------------------------------------
-    grbda_status grbda_cuda_dynamics_host_f64(const grbda_model *cm, int algo, const double *q, const double *yd,
-                                              const double *in3, double *out, int64_t batch)
+    // mode 0: ID, 1: FD, 2: FD followed by ID of the result (out2 = tau_back)
+    static grbda_status hostPipeline(grbda_model *m, int mode, const double *q, const double *yd,
+                                     const double *in3, double *out, double *out2, int64_t batch)
     {
-        grbda_model *m = const_cast<grbda_model *>(cm);
-        if (!m || (algo != 0 && algo != 1) || !q || !yd || !in3 || !out)
-            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
         if (m->device < 0 || !m->kernels)
             return fail(GRBDA_ERR_NO_DEVICE, "model was created without a CUDA device (host-only handle)");
         std::lock_guard<std::mutex> lock(m->host_mutex);
@@ -377,7 +375,7 @@ extern "C"
         if (e != cudaSuccess)
             return cudaFail(e, "cudaSetDevice");
         const int nq = m->model.getNumPositions(), nv = m->model.getNumDegreesOfFreedom();
-        const int64_t per_state = nq + 3 * (int64_t)nv; // doubles
+        const int64_t per_state = nq + 4 * (int64_t)nv; // q, yd, in3, out, out2 (doubles)
         const int64_t chunk = 1 << 16;
         if (m->dev_capacity < chunk)
         {
@@ -398,22 +396,49 @@ extern "C"
             const int64_t nb = std::min(chunk, batch - b0);
             const int s = k % grbda_model::NSTREAM;
             cudaStream_t st = m->streams[s];
-            double *dq = m->dev_buf[s], *dyd = dq + chunk * nq, *din = dyd + chunk * nv, *dout = din + chunk * nv;
+            double *dq = m->dev_buf[s], *dyd = dq + chunk * nq, *din = dyd + chunk * nv, *dout = din + chunk * nv,
+                   *dout2 = dout + chunk * nv;
             if ((e = cudaMemcpyAsync(dq, q + b0 * nq, nb * nq * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
                 (e = cudaMemcpyAsync(dyd, yd + b0 * nv, nb * nv * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
                 (e = cudaMemcpyAsync(din, in3 + b0 * nv, nb * nv * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
                 return cudaFail(e, "cudaMemcpyAsync H2D");
-            grbda_status rs = launchAlgo(m, algo == 0 ? compiler::ALGO_ID : compiler::ALGO_FD, false, dq, dyd, din,
+            grbda_status rs = launchAlgo(m, mode == 0 ? compiler::ALGO_ID : compiler::ALGO_FD, false, dq, dyd, din,
                                          dout, nullptr, nullptr, nb, st);
             if (rs != GRBDA_OK)
                 return rs;
             if ((e = cudaMemcpyAsync(out + b0 * nv, dout, nb * nv * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
                 return cudaFail(e, "cudaMemcpyAsync D2H");
+            if (mode == 2)
+            {
+                rs = launchAlgo(m, compiler::ALGO_ID, false, dq, dyd, dout, dout2, nullptr, nullptr, nb, st);
+                if (rs != GRBDA_OK)
+                    return rs;
+                if ((e = cudaMemcpyAsync(out2 + b0 * nv, dout2, nb * nv * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+                    return cudaFail(e, "cudaMemcpyAsync D2H");
+            }
         }
         for (int i = 0; i < grbda_model::NSTREAM; i++)
             if ((e = cudaStreamSynchronize(m->streams[i])) != cudaSuccess)
                 return cudaFail(e, "cudaStreamSynchronize");
         return GRBDA_OK;
+    }
+
+    grbda_status grbda_cuda_dynamics_host_f64(const grbda_model *cm, int algo, const double *q, const double *yd,
+                                              const double *in3, double *out, int64_t batch)
+    {
+        grbda_model *m = const_cast<grbda_model *>(cm);
+        if (!m || (algo != 0 && algo != 1) || !q || !yd || !in3 || !out)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        return hostPipeline(m, algo, q, yd, in3, out, nullptr, batch);
+    }
+    grbda_status grbda_cuda_forward_inverse_host_f64(const grbda_model *cm, const double *q, const double *yd,
+                                                     const double *tau, double *ydd, double *tau_back,
+                                                     int64_t batch)
+    {
+        grbda_model *m = const_cast<grbda_model *>(cm);
+        if (!m || !q || !yd || !tau || !ydd || !tau_back)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        return hostPipeline(m, 2, q, yd, tau, ydd, tau_back, batch);
     }
 
     // ---- states, checks, measurement -----------------------------------------------------------------

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <map>
 #include <sstream>
 #include "../compiler/compile.h"
 #include "../host/robots.h"
@@ -20,7 +21,8 @@ namespace
 {
     struct Variant
     {
-        char kind; // 'S' one state per thread, staged I/O; 'D' direct global I/O; 'R' one limb per warp
+        char kind; // 'S' one state per thread, software-staged I/O; 'T' the same with TMA bulk-copy staging;
+                   // 'D' direct global I/O; 'R' one limb per warp
         int block, min_blocks;
     };
 
@@ -152,16 +154,31 @@ int main(int argc, char **argv)
     }
     try
     {
+        // "--variants spec" or "--variants id=spec|fd=spec|..." (per algorithm)
+        std::map<std::string, std::string> per_algo;
+        if (variants_s.find('=') != std::string::npos)
+        {
+            for (auto &entry : split(variants_s, '|'))
+            {
+                const size_t eq = entry.find('=');
+                per_algo[entry.substr(0, eq)] = entry.substr(eq + 1);
+            }
+            variants_s = per_algo.begin()->second;
+        }
+        auto parseVariants = [&](const std::string &spec) {
         std::vector<Variant> variants;
-        for (auto &v : split(variants_s, ';'))
+        for (auto &v : split(spec, ';'))
         {
             auto p = split(v, ',');
-            if (p.size() != 3 || p[0].size() != 1 || std::string("SDR").find(p[0][0]) == std::string::npos)
+            if (p.size() != 3 || p[0].size() != 1 || std::string("SDRT").find(p[0][0]) == std::string::npos)
                 throw std::runtime_error("bad --variants entry '" + v + "' (expected KIND,BLOCK,MINBLOCKS)");
             variants.push_back({p[0][0], std::atoi(p[1].c_str()), std::atoi(p[2].c_str())});
         }
         if (variants.empty() || variants.size() > 4)
             throw std::runtime_error("between 1 and 4 variants are supported");
+        return variants;
+        };
+        std::vector<Variant> variants = parseVariants(variants_s);
 
         const ClusterTreeModel model = buildRobotByName(model_name, urdf_dir);
         const uint64_t hash = modelHash(model);
@@ -191,6 +208,8 @@ int main(int argc, char **argv)
                     a = k;
             if (a < 0)
                 throw std::runtime_error("unknown algorithm '" + algo + "'");
+            if (per_algo.count(algo))
+                variants = parseVariants(per_algo[algo]);
             ConstTable consts;
             const CompiledAlgo c = compileAlgo(model, a, true, sync_every, &consts);
             if (a == ALGO_PHI && c.n_out[0] == 0)
@@ -214,6 +233,8 @@ int main(int argc, char **argv)
                 std::ostringstream l;
                 if (v.kind == 'R' && have_roles)
                     l << "&launchRoles<" << real << ", RoleBody, " << v.min_blocks << ">";
+                else if (v.kind == 'T')
+                    l << "&launchBatchedTma<" << real << ", Body, " << v.block << ", " << v.min_blocks << ">";
                 else
                     l << "&launchBatched<" << real << ", Body, " << (v.kind == 'R' ? 128 : v.block) << ", "
                       << (v.kind == 'R' ? 2 : v.min_blocks) << ", " << (v.kind == 'D' ? "false" : "true") << ">";

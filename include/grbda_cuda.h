@@ -179,6 +179,12 @@ grbda_status grbda_cuda_forward_kinematics_f32(const grbda_model *m, const float
 grbda_status grbda_cuda_dynamics_host_f64(const grbda_model *m, int algo, const double *q, const double *yd,
                                           const double *in3, double *out, int64_t batch);
 
+/* One benchmark step on host buffers: ydd = FD(q, yd, tau) followed by tau_back = ID(q, yd, ydd); q, yd
+ * and tau cross PCIe once, both results come back. */
+grbda_status grbda_cuda_forward_inverse_host_f64(const grbda_model *m, const double *q, const double *yd,
+                                                 const double *tau, double *ydd, double *tau_back,
+                                                 int64_t batch);
+
 /* ---- synthetic states, checks, measurement --------------------------------------------------- */
 /* Random valid states for global state indices [first_index, first_index + count): counter based
  * (Philox4x32-10), so a shard is reproducible whatever the GPU count. Ranges follow
