@@ -642,7 +642,10 @@ namespace grbda
                                     {sdof[c.first_body_ + i], ck.G[i * d.num_velocities + k]});
                 }
                 std::vector<Sym> H(nv * nv, Sym(0.0));
-                for (int b = 0; b < nv; b++)
+                // columns from last to first: row b of H (entries to its ancestors from this step, to its
+                // descendants from earlier steps) is then complete at step b, so the emitter can hand
+                // finished 16-value chunks of the row-major output to the coalesced store path early
+                for (int b = nv - 1; b >= 0; b--)
                 {
                     // t = H_s G[:, b]
                     std::vector<Sym> t(ns, Sym(0.0));

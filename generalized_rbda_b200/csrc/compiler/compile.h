@@ -94,7 +94,7 @@ namespace grbda
         }
 
         inline CompiledAlgo compileAlgo(const ClusterTreeModel &model, int algo, bool want_body = true,
-                                        int sync_every = 0, ConstTable *consts = nullptr)
+                                        int sync_every = 0, ConstTable *consts = nullptr, int out_chunk = 0)
         {
             sym::Graph graph;
             sym::GraphScope scope(graph);
@@ -109,7 +109,7 @@ namespace grbda
             out.stats = em.stats();
             out.tape = em.tape();
             if (want_body)
-                out.body = em.cudaBody(sync_every);
+                out.body = em.cudaBody(sync_every, out_chunk);
             return out;
         }
 

@@ -145,7 +145,13 @@ namespace grbda
             // run the same straight-line code; keeping them within a few hundred instructions of each
             // other lets them share instruction-cache lines (the kernels are instruction-fetch bound
             // otherwise: ncu 'no_instruction' is the top stall of the unaligned version).
-            std::string cudaBody(int sync_every = 0) const
+            // out_chunk > 0 (kernels with large outputs: FK, H): results are not stored one by one —
+            // a thread's row of such an array is thousands of bytes away from its neighbour's, so
+            // direct stores touch 32 sectors per instruction. Instead the values of one chunk of
+            // `out_chunk` consecutive elements are held until the chunk is complete, written to the
+            // warp's shared-memory staging buffer (STG_PUT) and flushed with coalesced stores
+            // (STG_FLUSHk: 32 states x chunk, 128 contiguous bytes per state).
+            std::string cudaBody(int sync_every = 0, int out_chunk = 0) const
             {
                 std::ostringstream os;
                 int since_sync = 0;
@@ -156,10 +162,80 @@ namespace grbda
                     for (size_t i = 0; i < p_.outputs[arr].size(); i++)
                         stores[p_.outputs[arr][i].id].push_back({(int)arr, (int)i});
 
+                // chunked output staging state
+                const size_t n_arr = p_.outputs.size();
+                std::vector<std::vector<char>> ready(n_arr);
+                std::vector<std::vector<int>> chunk_missing(n_arr);
+                std::vector<char> chunked(n_arr, 0);
+                for (size_t arr = 0; arr < n_arr; arr++)
+                {
+                    const int n = (int)p_.outputs[arr].size();
+                    chunked[arr] = out_chunk > 0 && n > 64;
+                    ready[arr].assign(n, 0);
+                    if (chunked[arr])
+                    {
+                        chunk_missing[arr].assign((n + out_chunk - 1) / out_chunk, 0);
+                        for (int i = 0; i < n; i++)
+                            chunk_missing[arr][i / out_chunk]++;
+                    }
+                }
+                auto flushChunk = [&](int arr, int c) {
+                    const int n = (int)p_.outputs[arr].size();
+                    const int base = c * out_chunk, count = std::min(out_chunk, n - base);
+                    for (int j = 0; j < count; j++)
+                        os << "STG_PUT(" << j << ", " << ref(p_.outputs[arr][base + j].id) << ");\n";
+                    os << "STG_FLUSH" << arr << "(" << base << ", " << count << ");\n";
+                };
+                auto markReady = [&](int arr, int el) {
+                    if (ready[arr][el])
+                        return;
+                    ready[arr][el] = 1;
+                    if (--chunk_missing[arr][el / out_chunk] == 0)
+                        flushChunk(arr, el / out_chunk);
+                };
                 auto emitStores = [&](size_t id) {
                     for (auto &st : stores[id])
-                        os << "OUT" << st.first << "(" << st.second << ", " << ref((int32_t)id) << ");\n";
+                    {
+                        if (chunked[st.first])
+                            markReady(st.first, st.second);
+                        else
+                            os << "OUT" << st.first << "(" << st.second << ", " << ref((int32_t)id) << ");\n";
+                    }
                 };
+                // a negated output is available as soon as its operand is
+                auto readyNow = [&](int32_t id) {
+                    int32_t k = id;
+                    while (g_.nodes[k].op == sym::OP_NEG)
+                        k = g_.nodes[k].a;
+                    return g_.nodes[k].op == sym::OP_CONST || done[k];
+                };
+                // constant outputs (structural zeros of H, ...) are ready from the start
+                for (size_t arr = 0; arr < n_arr; arr++)
+                    if (chunked[arr])
+                        for (size_t i = 0; i < p_.outputs[arr].size(); i++)
+                        {
+                            int32_t k = p_.outputs[arr][i].id;
+                            while (g_.nodes[k].op == sym::OP_NEG)
+                                k = g_.nodes[k].a;
+                            if (g_.nodes[k].op == sym::OP_CONST)
+                                markReady((int)arr, (int)i);
+                        }
+                (void)readyNow;
+                // NEG outputs become ready together with their operand
+                std::vector<std::vector<int32_t>> neg_outputs_of(g_.nodes.size());
+                for (size_t arr = 0; arr < n_arr; arr++)
+                    for (size_t i = 0; i < p_.outputs[arr].size(); i++)
+                    {
+                        const int32_t id = p_.outputs[arr][i].id;
+                        if (g_.nodes[id].op != sym::OP_NEG)
+                            continue;
+                        int32_t k = id;
+                        while (g_.nodes[k].op == sym::OP_NEG)
+                            k = g_.nodes[k].a;
+                        if (g_.nodes[k].op != sym::OP_CONST)
+                            neg_outputs_of[k].push_back(id);
+                    }
+
                 for (size_t i = 0; i < g_.nodes.size(); i++)
                 {
                     if (!live_[i])
@@ -167,12 +243,23 @@ namespace grbda
                     const sym::Node &n = g_.nodes[i];
                     if (n.op == sym::OP_CONST || n.op == sym::OP_NEG)
                     {
-                        emitStores(i);
+                        // direct (non chunked) stores of constants / negations are emitted in place;
+                        // chunked ones are handled through markReady above / below
+                        for (auto &st : stores[i])
+                            if (!chunked[st.first])
+                            {
+                                if (n.op == sym::OP_CONST || readyNow((int32_t)i))
+                                    os << "OUT" << st.first << "(" << st.second << ", " << ref((int32_t)i) << ");\n";
+                                else
+                                    throw std::runtime_error("emit: negation stored before its operand");
+                            }
                         continue;
                     }
                     if (done[i])
                     {
                         emitStores(i);
+                        for (int32_t ng : neg_outputs_of[i])
+                            emitStores(ng);
                         continue;
                     }
                     switch (n.op)
@@ -222,6 +309,8 @@ namespace grbda
                     }
                     done[i] = 1;
                     emitStores(i);
+                    for (int32_t ng : neg_outputs_of[i])
+                        emitStores(ng);
                     if (sync_every > 0 && ++since_sync >= sync_every)
                     {
                         os << "GRBDA_ALIGN();\n";

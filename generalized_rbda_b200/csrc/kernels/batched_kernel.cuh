@@ -156,6 +156,61 @@ namespace grbda_kernels
         }
     }
 
+    // ---- chunked output staging (kernels with large outputs: FK, H) ------------------------------
+    // The generated body hands over `COUNT` consecutive elements of one output array for the 32
+    // states of the warp through the warp's staging buffer; this writes them with coalesced stores
+    // (for COUNT = 16 doubles every instruction covers two states x 128 contiguous bytes).
+    constexpr int OUT_CHUNK = 16;
+    template <typename real>
+    struct OutStage
+    {
+        real *lane;   // this thread's row of the warp's staging buffer [32][OUT_CHUNK + 1]
+        real *warp;   // the warp's staging buffer
+        real *g[3];   // output rows of the warp's first state
+        int valid;    // number of states of this warp that exist (tail of the batch)
+    };
+    template <typename real, int N, int COUNT>
+    __device__ __forceinline__ void flushChunk(real *__restrict__ g, int base, const real *__restrict__ stg, int valid)
+    {
+        __syncwarp();
+        const int lane = threadIdx.x & 31;
+#pragma unroll 4
+        for (int e = lane; e < 32 * COUNT; e += 32)
+        {
+            const int st = e / COUNT, el = e - st * COUNT;
+            if (st < valid)
+                __stcs(g + (size_t)st * N + base + el, stg[st * (OUT_CHUNK + 1) + el]);
+        }
+        __syncwarp();
+    }
+    template <typename Body>
+    __host__ __device__ constexpr bool bodyChunked()
+    {
+        return Body::N_OUT0 > 64 || Body::N_OUT1 > 64 || Body::N_OUT2 > 64;
+    }
+    template <typename Body, typename real, int BLOCK>
+    __host__ __device__ constexpr size_t stageBytes()
+    {
+        return bodyChunked<Body>() ? (size_t)BLOCK * (OUT_CHUNK + 1) * sizeof(real) : 0;
+    }
+    template <typename Body, typename real>
+    __device__ __forceinline__ OutStage<real> makeOutStage(unsigned char *stage_base, real *out0, real *out1,
+                                                           real *out2, int64_t first, int rows)
+    {
+        OutStage<real> o;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        real *buf = reinterpret_cast<real *>(stage_base) + (size_t)warp * 32 * (OUT_CHUNK + 1);
+        o.warp = buf;
+        o.lane = buf + lane * (OUT_CHUNK + 1);
+        const int64_t s0 = first + 32 * warp;
+        o.g[0] = out0 ? out0 + s0 * Body::N_OUT0 : nullptr;
+        o.g[1] = out1 ? out1 + s0 * Body::N_OUT1 : nullptr;
+        o.g[2] = out2 ? out2 + s0 * Body::N_OUT2 : nullptr;
+        const int v = rows - 32 * warp;
+        o.valid = v < 0 ? 0 : (v > 32 ? 32 : v);
+        return o;
+    }
+
     // Shared-memory budget of one CTA: all input tiles plus the tile of output array 0 when it is
     // small (dynamics: nv values). Large outputs (FK, H) are streamed chunk-wise by the body itself
     // through OUTk(), see below.
@@ -171,10 +226,11 @@ namespace grbda_kernels
         static constexpr int OFF2 = OFF1 + S1 * BLOCK;
         static constexpr int OFFO = OFF2 + S2 * BLOCK;
         static constexpr int ELEMS = OFFO + SO * BLOCK;
-        static constexpr size_t BYTES = (size_t)ELEMS * sizeof(real);
+        static constexpr size_t TILE_BYTES = ((size_t)ELEMS * sizeof(real) + 15) & ~(size_t)15;
+        static constexpr size_t BYTES = TILE_BYTES + stageBytes<Body, real, BLOCK>();
     };
 
-    // One state per thread. Body::run(in0, in1, in2, out0, out1, out2) is generated code.
+    // One state per thread. Body::run(in0, in1, in2, out0, out1, out2, stage) is generated code.
     // STAGED = true : inN address the thread's own row of the staged shared-memory tiles and out0
     //                 the thread's row of the staged output tile (small outputs);
     // STAGED = false: inN / outN address global memory directly (x + state * n).
@@ -193,10 +249,11 @@ namespace grbda_kernels
         const int t = min((int)threadIdx.x, rows - 1);
         const int64_t state = first + t;
 
+        extern __shared__ __align__(16) unsigned char smem_raw[];
         if constexpr (STAGED)
         {
-            extern __shared__ __align__(16) unsigned char smem_raw[];
             real *smem = reinterpret_cast<real *>(smem_raw);
+            const OutStage<real> stage = makeOutStage<Body, real>(smem_raw + L::TILE_BYTES, out0, out1, out2, first, rows);
             if (Body::N_IN0)
                 stage_in<real, Body::N_IN0 ? Body::N_IN0 : 1, BLOCK>(in0 + first * Body::N_IN0, smem, rows);
             if (Body::N_IN1)
@@ -211,7 +268,7 @@ namespace grbda_kernels
                 real *o1 = Body::N_OUT1 ? out1 + state * Body::N_OUT1 : nullptr;
                 real *o2 = Body::N_OUT2 ? out2 + state * Body::N_OUT2 : nullptr;
                 Body::template run<real>(smem + t * L::S0, smem + L::OFF1 + t * L::S1,
-                                         smem + L::OFF2 + t * L::S2, o0, o1, o2);
+                                         smem + L::OFF2 + t * L::S2, o0, o1, o2, stage);
             }
             if (L::STAGE_OUT0)
             {
@@ -222,9 +279,10 @@ namespace grbda_kernels
         }
         else
         {
+            const OutStage<real> stage = makeOutStage<Body, real>(smem_raw, out0, out1, out2, first, rows);
             Body::template run<real>(in0 + state * Body::N_IN0, in1 + state * Body::N_IN1,
                                      in2 + state * Body::N_IN2, out0 + state * Body::N_OUT0,
-                                     out1 + state * Body::N_OUT1, out2 + state * Body::N_OUT2);
+                                     out1 + state * Body::N_OUT1, out2 + state * Body::N_OUT2, stage);
         }
     }
 
@@ -233,7 +291,7 @@ namespace grbda_kernels
     {
         using L = TileLayout<Body, real, BLOCK>;
         auto kernel = grbda_batched_kernel<real, Body, BLOCK, MIN_BLOCKS, STAGED>;
-        const size_t smem = STAGED ? L::BYTES : 0;
+        const size_t smem = STAGED ? L::BYTES : stageBytes<Body, real, BLOCK>();
         if (smem > 48 * 1024)
         {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -349,7 +407,8 @@ namespace grbda_kernels
         static constexpr size_t OFF1 = align16(OFF0 + (size_t)S0 * BLOCK * sizeof(real));
         static constexpr size_t OFF2 = align16(OFF1 + (size_t)S1 * BLOCK * sizeof(real));
         static constexpr size_t OFFO = align16(OFF2 + (size_t)S2 * BLOCK * sizeof(real));
-        static constexpr size_t BYTES = align16(OFFO + (size_t)SO * BLOCK * sizeof(real));
+        static constexpr size_t TILE_BYTES = align16(OFFO + (size_t)SO * BLOCK * sizeof(real));
+        static constexpr size_t BYTES = TILE_BYTES + stageBytes<Body, real, BLOCK>();
     };
 
     template <typename real, typename Body, int BLOCK, int MIN_BLOCKS>
@@ -391,7 +450,8 @@ namespace grbda_kernels
         real *o0 = L::STAGE_OUT0 ? so + t * L::SO : out0 + state * Body::N_OUT0;
         real *o1 = Body::N_OUT1 ? out1 + state * Body::N_OUT1 : nullptr;
         real *o2 = Body::N_OUT2 ? out2 + state * Body::N_OUT2 : nullptr;
-        Body::template run<real>(s0 + t * L::S0, s1 + t * L::S1, s2 + t * L::S2, o0, o1, o2);
+        const OutStage<real> stage = makeOutStage<Body, real>(smem_raw + L::TILE_BYTES, out0, out1, out2, first, rows);
+        Body::template run<real>(s0 + t * L::S0, s1 + t * L::S1, s2 + t * L::S2, o0, o1, o2, stage);
 
         if (L::STAGE_OUT0)
         {

@@ -21,6 +21,7 @@ namespace
 {
     struct Variant
     {
+        int sync = -1; // alignment barrier period in statements (-1: the --sync-every default)
         char kind; // 'S' one state per thread, software-staged I/O; 'T' the same with TMA bulk-copy staging;
                    // 'D' direct global I/O; 'R' one limb per warp
         int block, min_blocks;
@@ -57,12 +58,16 @@ namespace
         os << "    static __device__ __forceinline__ void run(const real *__restrict__ in0, const real "
               "*__restrict__ in1,\n"
               "        const real *__restrict__ in2, real *__restrict__ out0, real *__restrict__ out1, "
-              "real *__restrict__ out2)\n    {\n";
+              "real *__restrict__ out2,\n        const OutStage<real> &stage)\n    {\n";
         os << "#define KC(x) ((real)(x))\n#define KT(i) kc_table<real>(i)\n#define IN0(i) in0[i]\n#define IN1(i) in1[i]\n#define IN2(i) in2[i]\n"
               "#define OUT0(i, x) out0[i] = (x)\n#define OUT1(i, x) out1[i] = (x)\n#define OUT2(i, x) out2[i] = (x)\n"
-              "#define GRBDA_ALIGN() __syncthreads()\n";
+              "#define GRBDA_ALIGN() __syncthreads()\n"
+              "#define STG_PUT(j, x) stage.lane[j] = (x)\n"
+              "#define STG_FLUSH0(base, count) flushChunk<real, N_OUT0, count>(stage.g[0], base, stage.warp, stage.valid)\n"
+              "#define STG_FLUSH1(base, count) flushChunk<real, N_OUT1, count>(stage.g[1], base, stage.warp, stage.valid)\n"
+              "#define STG_FLUSH2(base, count) flushChunk<real, N_OUT2, count>(stage.g[2], base, stage.warp, stage.valid)\n";
         os << c.body;
-        os << "#undef KC\n#undef KT\n#undef IN0\n#undef IN1\n#undef IN2\n#undef OUT0\n#undef OUT1\n#undef OUT2\n#undef GRBDA_ALIGN\n";
+        os << "#undef KC\n#undef KT\n#undef IN0\n#undef IN1\n#undef IN2\n#undef OUT0\n#undef OUT1\n#undef OUT2\n#undef GRBDA_ALIGN\n#undef STG_PUT\n#undef STG_FLUSH0\n#undef STG_FLUSH1\n#undef STG_FLUSH2\n";
         os << "    }\n};\n";
     }
 
@@ -170,9 +175,15 @@ int main(int argc, char **argv)
         for (auto &v : split(spec, ';'))
         {
             auto p = split(v, ',');
-            if (p.size() != 3 || p[0].size() != 1 || std::string("SDRT").find(p[0][0]) == std::string::npos)
-                throw std::runtime_error("bad --variants entry '" + v + "' (expected KIND,BLOCK,MINBLOCKS)");
-            variants.push_back({p[0][0], std::atoi(p[1].c_str()), std::atoi(p[2].c_str())});
+            if ((p.size() != 3 && p.size() != 4) || p[0].size() != 1 ||
+                std::string("SDRT").find(p[0][0]) == std::string::npos)
+                throw std::runtime_error("bad --variants entry '" + v + "' (expected KIND,BLOCK,MINBLOCKS[,SYNC])");
+            Variant var;
+            var.kind = p[0][0];
+            var.block = std::atoi(p[1].c_str());
+            var.min_blocks = std::atoi(p[2].c_str());
+            var.sync = p.size() == 4 ? std::atoi(p[3].c_str()) : -1;
+            variants.push_back(var);
         }
         if (variants.empty() || variants.size() > 4)
             throw std::runtime_error("between 1 and 4 variants are supported");
@@ -211,7 +222,15 @@ int main(int argc, char **argv)
             if (per_algo.count(algo))
                 variants = parseVariants(per_algo[algo]);
             ConstTable consts;
-            const CompiledAlgo c = compileAlgo(model, a, true, sync_every, &consts);
+            for (auto &v : variants)
+                if (v.sync < 0)
+                    v.sync = sync_every;
+            const int out_chunk = 16; // = grbda_kernels::OUT_CHUNK; only arrays with more than 64 values use it
+            const CompiledAlgo c = compileAlgo(model, a, true, variants[0].sync, &consts, out_chunk);
+            std::map<int, CompiledAlgo> by_sync;
+            for (auto &v : variants)
+                if (v.kind != 'R' && !by_sync.count(v.sync))
+                    by_sync[v.sync] = compileAlgo(model, a, true, v.sync, &consts, out_chunk);
             if (a == ALGO_PHI && c.n_out[0] == 0)
                 continue; // no implicit clusters
             bool want_roles = false, want_single = false;
@@ -224,8 +243,10 @@ int main(int argc, char **argv)
             std::ostringstream os;
             os << header_common;
             os << consts.definition("kc_table");
-            if (want_single || !have_roles)
-                emitBodyStruct(os, "Body", c);
+            if (by_sync.empty())
+                by_sync[variants[0].sync] = c;
+            for (auto &kv : by_sync)
+                emitBodyStruct(os, "Body" + std::to_string(kv.first), kv.second);
             if (have_roles)
                 emitRoleStruct(os, "RoleBody", roles);
             os << "} // namespace\n\n";
@@ -234,10 +255,11 @@ int main(int argc, char **argv)
                 if (v.kind == 'R' && have_roles)
                     l << "&launchRoles<" << real << ", RoleBody, " << v.min_blocks << ">";
                 else if (v.kind == 'T')
-                    l << "&launchBatchedTma<" << real << ", Body, " << v.block << ", " << v.min_blocks << ">";
+                    l << "&launchBatchedTma<" << real << ", Body" << v.sync << ", " << v.block << ", " << v.min_blocks << ">";
                 else
-                    l << "&launchBatched<" << real << ", Body, " << (v.kind == 'R' ? 128 : v.block) << ", "
-                      << (v.kind == 'R' ? 2 : v.min_blocks) << ", " << (v.kind == 'D' ? "false" : "true") << ">";
+                    l << "&launchBatched<" << real << ", Body" << (v.kind == 'R' ? by_sync.begin()->first : v.sync) << ", "
+                      << (v.kind == 'R' ? 128 : v.block) << ", " << (v.kind == 'R' ? 2 : v.min_blocks) << ", "
+                      << (v.kind == 'D' ? "false" : "true") << ">";
                 return l.str();
             };
             os << "static const grbda_runtime::AlgoKernels k_algo = {\n    {";
