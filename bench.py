@@ -204,6 +204,12 @@ def main():
 
     t_fd = time_kernel(lambda: m.forwardDynamics(q, yd, tau, out=ydd), args.steps)
     t_id = time_kernel(lambda: m.inverseDynamics(q, yd, ydd, out=tau_back), args.steps)
+    # the other two kernels of the path (HBM-write bound): a quarter of the batch keeps memory modest
+    Bk = max(1, B // 4)
+    Hbuf = torch.empty((Bk, m.nv, m.nv), dtype=torch.float64, device=dev)
+    t_h = time_kernel(lambda: m.getMassMatrix(q[:Bk], out=Hbuf), 5)
+    t_fk = time_kernel(lambda: m.forwardKinematics(q[:Bk], yd[:Bk]), 5)
+    del Hbuf
 
     # parity spot check + checksum gather (the only collective)
     err = float(((tau_back - tau).abs().amax(1) / tau.abs().amax(1)).median())
@@ -260,7 +266,7 @@ def main():
             f_alg_fd, f_alg_id = fd_prog["flops"], id_prog["flops"]
         alg_bytes = (m.nq + 3 * m.nv) * 8
         line["roofline"] = {
-            "kernel": "forwardDynamics (grbda_batched_kernel<double, Body fd>)",
+            "kernel": "forwardDynamics (grbda_batched_kernel<double, Body fd, 128, 2, staged>)",
             "bound": "fp64", "unit": "TFLOP/s",
             "achieved": f_alg_fd * B / t_fd / 1e12, "peak": fp64_peak / 1e12,
             "frac": (f_alg_fd * B / t_fd) / fp64_peak,
@@ -276,6 +282,12 @@ def main():
                                  "flops_per_state_executed": id_prog["flops"],
                                  "achieved": f_alg_id * B / t_id / 1e12, "frac": (f_alg_id * B / t_id) / fp64_peak,
                                  "hbm_frac": alg_bytes * B / t_id / 1e9 / peaks["hbm_gbs"]}}
+        line["other_kernels"] = {
+            "mass_matrix": {"states": Bk, "kernel_ms": t_h * 1e3, "bytes_per_state": 8 * (m.nq + m.nv * m.nv),
+                            "hbm_frac": 8 * (m.nq + m.nv * m.nv) * Bk / t_h / 1e9 / peaks["hbm_gbs"]},
+            "forward_kinematics": {"states": Bk, "kernel_ms": t_fk * 1e3,
+                                   "bytes_per_state": 8 * (m.nq + m.nv + 18 * m.nb),
+                                   "hbm_frac": 8 * (m.nq + m.nv + 18 * m.nb) * Bk / t_fk / 1e9 / peaks["hbm_gbs"]}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

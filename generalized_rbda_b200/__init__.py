@@ -29,6 +29,7 @@ _lib = C.CDLL(_LIB_PATH)
 
 ALGO_ID, ALGO_FD, ALGO_FK, ALGO_H, ALGO_PHI = 0, 1, 2, 3, 4
 ALGO_NAMES = ["id", "fd", "fk", "h", "phi"]
+PROGRAM_FD_LTL = 5  # dump_program only: forward dynamics as CRBA + bias + sparse L^T D L (kernel variant "ltl")
 
 _vp = C.c_void_p
 _i64 = C.c_int64

@@ -927,6 +927,239 @@ namespace grbda
                 return ydd_out;
             }
 
+            // ---------------------------------------------------------------------------------
+            // forward dynamics, second method: ydd = H^-1 (tau - C) with the cluster CRBA, the cluster
+            // RNEA bias and a branch-sparse L^T D L factorisation, all inside ONE depth-first sweep.
+            // Same result as forwardDynamics() (ClusterTreeModel::forwardDynamics,
+            // ClusterTreeDynamics.cpp:10-19) up to rounding; the operands it must keep between the
+            // upward and the final downward sweep are only the factor L (one value per
+            // (dof, ancestor dof) pair) and z, about half of what the articulated-body sweep keeps
+            // (U, D^-1, S, Xup, c per cluster), and composite inertias stay in 10-parameter form.
+            //   upward step of cluster c (children finished):
+            //     C_c      = G^T f                      (RNEA with ydd = 0, as inverseDynamics())
+            //     H[c, a]  = S_a^T X^T (Ic S_c)         for every ancestor-or-self cluster a (cluster CRBA,
+            //                                           ClusterTreeModel.cpp massMatrix)
+            //     pivots k in c, last to first: row = H[k,:] - Acc[k,:], d = row[k], L[k,a] = row[a]/d,
+            //     Acc[a,a'] += L[k,a] row[a'],  accb[a] += L[k,a] w_k,  w_k = tau_k - C_k - accb[k],  z_k = w_k/d
+            //   final downward sweep: ydd_k = z_k - sum_a L[k,a] ydd_a
+            // ---------------------------------------------------------------------------------
+            std::vector<Sym> forwardDynamicsLTL()
+            {
+                beginKinematics();
+                const int Nb = m_.getNumBodies(), nv = m_.getNumDegreesOfFreedom();
+                std::vector<SV> a(Nb), f(Nb);
+                std::vector<RigidInertia> Ic(Nb);
+                std::vector<Sym> bias(nv, Sym(0.0)), z(nv), ydd_out(nv);
+                std::vector<std::vector<int>> anc_dofs(nv); // ancestor dofs of a dof, ascending
+                std::vector<std::map<int, Sym>> L(nv);
+                std::map<std::pair<int, int>, Sym> Acc;
+                std::vector<Sym> accb(nv, Sym(0.0));
+                auto accumulate = [](std::map<std::pair<int, int>, Sym> &M, int r, int c, const Sym &x) {
+                    auto it = M.find({r, c});
+                    if (it == M.end())
+                        M[{r, c}] = x;
+                    else
+                        it->second = it->second + x;
+                };
+                auto isFree = [](const ClusterDesc &d) {
+                    return d.type == ClusterType::FreeQuaternion || d.type == ClusterType::FreeRollPitchYaw;
+                };
+
+                auto downward = [&](int ci) {
+                    kinematicsCluster(ci, true, true);
+                    const ClusterTreeNode &c = m_.clusters()[ci];
+                    const ClusterDesc &d = c.joint_;
+                    // dof ancestry: the parent cluster's last dof and its ancestors, then own earlier dofs
+                    std::vector<int> path;
+                    if (c.parent_index_ >= 0)
+                    {
+                        const ClusterTreeNode &pc = m_.clusters()[c.parent_index_];
+                        const int last = pc.velocity_index_ + pc.joint_.num_velocities - 1;
+                        path = anc_dofs[last];
+                        path.push_back(last);
+                    }
+                    for (int k = 0; k < d.num_velocities; k++)
+                    {
+                        anc_dofs[c.velocity_index_ + k] = path;
+                        path.push_back(c.velocity_index_ + k);
+                    }
+                    for (int i = 0; i < d.num_bodies; i++)
+                    {
+                        const int bi = c.first_body_ + i;
+                        const Body &body = m_.bodies()[bi];
+                        const BodyKin &b = bk_[bi];
+                        const int p = body.parent_index_;
+                        SV ai = b.Xl.applyMotion(p >= 0 ? a[p] : minusGravity());
+                        if (!isFree(d))
+                        {
+                            // ydd = 0: qdd_s = g
+                            const int axis = (int)d.axes[i];
+                            SV sq;
+                            sq[axis] = b.qd;
+                            ai[axis] = ai[axis] + ck_[ci].g[i];
+                            ai = ai + motionCross(b.v, sq);
+                        }
+                        a[bi] = ai;
+                        Ic[bi] = RigidInertia::fromMatrix(body.inertia_.getMatrix());
+                        f[bi] = Ic[bi].apply(ai) + forceCross(b.v, Ic[bi].apply(b.v));
+                    }
+                };
+
+                auto upward = [&](int ci) {
+                    const ClusterTreeNode &c = m_.clusters()[ci];
+                    const ClusterDesc &d = c.joint_;
+                    const int N = d.num_bodies, n = d.num_velocities, b0 = c.first_body_, v0 = c.velocity_index_;
+                    // ---- bias force of this cluster (spanning-tree RNEA, projected with G) ----
+                    {
+                        std::map<int, SV> to_parent;
+                        for (int i = N - 1; i >= 0; i--)
+                        {
+                            const int bi = b0 + i;
+                            const int p = m_.bodies()[bi].parent_index_;
+                            if (isFree(d))
+                                for (int k = 0; k < 6; k++)
+                                    bias[v0 + k] = f[bi][k];
+                            else
+                            {
+                                const Sym tau_s = f[bi][(int)d.axes[i]];
+                                for (int k = 0; k < n; k++)
+                                    bias[v0 + k] = bias[v0 + k] + ck_[ci].G[i * n + k] * tau_s;
+                            }
+                            if (p >= 0)
+                            {
+                                const SV fp = bk_[bi].Xl.applyForceTranspose(f[bi]);
+                                if (m_.getIndexOfClusterContainingBody(p) == ci)
+                                    f[p] = f[p] + fp;
+                                else if (to_parent.count(p))
+                                    to_parent[p] = to_parent[p] + fp;
+                                else
+                                    to_parent[p] = fp;
+                            }
+                        }
+                        for (auto &kv : to_parent)
+                            f[kv.first] = f[kv.first] + kv.second;
+                    }
+                    // ---- rows of H owned by this cluster (cluster CRBA) ----
+                    std::map<std::pair<int, int>, Sym> H; // (own dof, ancestor-or-own dof <= it)
+                    for (int k = 0; k < n; k++)
+                    {
+                        std::map<int, SV> F_anc;
+                        for (int i = 0; i < N; i++)
+                        {
+                            const BodyKin &b = bk_[b0 + i];
+                            const SV Fi = Ic[b0 + i].apply(b.S[k]);
+                            for (int l = 0; l <= k; l++)
+                                accumulate(H, v0 + k, v0 + l, dot(b.S[l], Fi));
+                            if (b.anc < 0)
+                                continue;
+                            const SV Fp = b.Xup.applyForceTranspose(Fi);
+                            if (F_anc.count(b.anc))
+                                F_anc[b.anc] = F_anc[b.anc] + Fp;
+                            else
+                                F_anc[b.anc] = Fp;
+                        }
+                        for (auto &kv : F_anc)
+                        {
+                            int j = kv.first;
+                            SV F = kv.second;
+                            while (true)
+                            {
+                                const ClusterTreeNode &ac = m_.clusters()[m_.getIndexOfClusterContainingBody(j)];
+                                for (int l = 0; l < ac.joint_.num_velocities; l++)
+                                    accumulate(H, v0 + k, ac.velocity_index_ + l, dot(bk_[j].S[l], F));
+                                if (bk_[j].anc < 0)
+                                    break;
+                                F = bk_[j].Xup.applyForceTranspose(F);
+                                j = bk_[j].anc;
+                            }
+                        }
+                    }
+                    // ---- composite inertia handed to the ancestor bodies ----
+                    {
+                        std::map<int, RigidInertia> Ic_to;
+                        for (int i = 0; i < N; i++)
+                        {
+                            const BodyKin &b = bk_[b0 + i];
+                            if (b.anc < 0)
+                                continue;
+                            const RigidInertia Ip = Ic[b0 + i].toParent(b.Xup);
+                            auto it = Ic_to.find(b.anc);
+                            if (it == Ic_to.end())
+                                Ic_to[b.anc] = Ip;
+                            else
+                                it->second = it->second + Ip;
+                        }
+                        for (auto &kv : Ic_to)
+                            Ic[kv.first] = Ic[kv.first] + kv.second;
+                    }
+                    // ---- pivots of this cluster, last to first ----
+                    for (int k = v0 + n - 1; k >= v0; k--)
+                    {
+                        const std::vector<int> &anc = anc_dofs[k];
+                        auto reduced = [&](int col) {
+                            Sym h(0.0);
+                            auto it = H.find({k, col});
+                            if (it != H.end())
+                                h = it->second;
+                            auto ia = Acc.find({k, col});
+                            if (ia != Acc.end())
+                            {
+                                h = h - ia->second;
+                                Acc.erase(ia);
+                            }
+                            return h;
+                        };
+                        const Sym dk = reduced(k);
+                        if (dk.isZero())
+                            throw std::runtime_error("mass matrix has a structurally zero pivot");
+                        const Sym dinv = Sym(1.0) / dk;
+                        std::vector<Sym> row(anc.size());
+                        for (size_t x = 0; x < anc.size(); x++)
+                            row[x] = reduced(anc[x]);
+                        const Sym w = Sym::input(IN_AUX, k) - bias[k] - accb[k];
+                        z[k] = w * dinv;
+                        for (size_t x = 0; x < anc.size(); x++)
+                        {
+                            if (row[x].isZero())
+                                continue;
+                            const Sym l = row[x] * dinv;
+                            L[k][anc[x]] = l;
+                            for (size_t y = 0; y <= x; y++)
+                                if (!row[y].isZero())
+                                    accumulate(Acc, anc[x], anc[y], l * row[y]);
+                            accb[anc[x]] = accb[anc[x]] + l * w;
+                        }
+                    }
+                };
+                // final downward sweep (ancestors first)
+                auto solve = [&](int ci) {
+                    const ClusterTreeNode &c = m_.clusters()[ci];
+                    for (int k = c.velocity_index_; k < c.velocity_index_ + c.joint_.num_velocities; k++)
+                    {
+                        Sym x = z[k];
+                        for (auto &kv : L[k])
+                            x = x - kv.second * ydd_out[kv.first];
+                        ydd_out[k] = x;
+                    }
+                };
+                std::function<void(int)> visit = [&](int ci) {
+                    downward(ci);
+                    for (int ch : children_[ci])
+                        visit(ch);
+                    upward(ci);
+                };
+                std::function<void(int)> visit2 = [&](int ci) {
+                    solve(ci);
+                    for (int ch : children_[ci])
+                        visit2(ch);
+                };
+                for (int r : roots_)
+                    visit(r);
+                for (int r : roots_)
+                    visit2(r);
+                return ydd_out;
+            }
+
             const std::vector<BodyKin> &bodyKinematics() const { return bk_; }
             const std::vector<ClusterKin> &clusterKinematics() const { return ck_; }
 

@@ -16,11 +16,16 @@ namespace grbda
             ALGO_FK = 2,      // in: q, yd        out: p[3 Nb], R[9 Nb], v[6 Nb]
             ALGO_H = 3,       // in: q            out: H[nv nv]
             ALGO_PHI = 4,     // in: q            out: phi[sum nc], Kd (row-major per implicit cluster)
-            ALGO_COUNT = 5
+            ALGO_COUNT = 5,   // entry points / registry slots
+            // alternative programs of an entry point (selected per kernel variant, same I/O as the entry)
+            PROGRAM_FD_LTL = 5, // forward dynamics as H^-1 (tau - C): CRBA + RNEA bias + sparse L^T D L
+            PROGRAM_COUNT = 6
         };
+        // registry slot a program belongs to
+        inline int algoOfProgram(int program) { return program == PROGRAM_FD_LTL ? ALGO_FD : program; }
         inline const char *algoName(int a)
         {
-            static const char *names[] = {"id", "fd", "fk", "h", "phi"};
+            static const char *names[] = {"id", "fd", "fk", "h", "phi", "fd_ltl"};
             return names[a];
         }
 
@@ -50,6 +55,10 @@ namespace grbda
             case ALGO_FD:
                 p.n_in[0] = nq, p.n_in[1] = nv, p.n_in[2] = nv;
                 p.outputs.push_back(mc.forwardDynamics());
+                break;
+            case PROGRAM_FD_LTL:
+                p.n_in[0] = nq, p.n_in[1] = nv, p.n_in[2] = nv;
+                p.outputs.push_back(mc.forwardDynamicsLTL());
                 break;
             case ALGO_FK:
             {
@@ -166,7 +175,7 @@ namespace grbda
             };
             auto output_role = [&](int array, int element) {
                 int r = -1;
-                switch (algo)
+                switch (algoOfProgram(algo))
                 {
                 case ALGO_ID:
                 case ALGO_FD: r = roleOfCluster(vel_cluster[element]); break;

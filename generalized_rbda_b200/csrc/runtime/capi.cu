@@ -283,7 +283,7 @@ extern "C"
     }
     grbda_status grbda_cuda_dump_program(const grbda_model *m, int algo, const char *path, int64_t *counts8)
     {
-        if (!m || algo < 0 || algo >= compiler::ALGO_COUNT)
+        if (!m || algo < 0 || algo >= compiler::PROGRAM_COUNT)
             return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
         return guarded([&]
                        {
@@ -301,7 +301,7 @@ extern "C"
 
     grbda_status grbda_cuda_dump_role_program(const grbda_model *m, int algo, const char *path, int64_t *info4)
     {
-        if (!m || algo < 0 || algo >= compiler::ALGO_COUNT)
+        if (!m || algo < 0 || algo >= compiler::PROGRAM_COUNT)
             return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
         return guarded([&]
                        {

@@ -25,6 +25,7 @@ namespace
         char kind; // 'S' one state per thread, software-staged I/O; 'T' the same with TMA bulk-copy staging;
                    // 'D' direct global I/O; 'R' one limb per warp
         int block, min_blocks;
+        int program = -1; // alternative program of the entry point (-1: the entry's own), e.g. PROGRAM_FD_LTL
     };
 
     std::vector<std::string> split(const std::string &s, char sep)
@@ -175,14 +176,21 @@ int main(int argc, char **argv)
         for (auto &v : split(spec, ';'))
         {
             auto p = split(v, ',');
-            if ((p.size() != 3 && p.size() != 4) || p[0].size() != 1 ||
+            if (p.size() < 3 || p.size() > 5 || p[0].size() != 1 ||
                 std::string("SDRT").find(p[0][0]) == std::string::npos)
-                throw std::runtime_error("bad --variants entry '" + v + "' (expected KIND,BLOCK,MINBLOCKS[,SYNC])");
+                throw std::runtime_error("bad --variants entry '" + v +
+                                         "' (expected KIND,BLOCK,MINBLOCKS[,SYNC][,ltl])");
             Variant var;
             var.kind = p[0][0];
             var.block = std::atoi(p[1].c_str());
             var.min_blocks = std::atoi(p[2].c_str());
-            var.sync = p.size() == 4 ? std::atoi(p[3].c_str()) : -1;
+            for (size_t t = 3; t < p.size(); t++)
+            {
+                if (p[t] == "ltl")
+                    var.program = PROGRAM_FD_LTL;
+                else
+                    var.sync = std::atoi(p[t].c_str());
+            }
             variants.push_back(var);
         }
         if (variants.empty() || variants.size() > 4)
@@ -226,11 +234,16 @@ int main(int argc, char **argv)
                 if (v.sync < 0)
                     v.sync = sync_every;
             const int out_chunk = 16; // = grbda_kernels::OUT_CHUNK; only arrays with more than 64 values use it
-            const CompiledAlgo c = compileAlgo(model, a, true, variants[0].sync, &consts, out_chunk);
-            std::map<int, CompiledAlgo> by_sync;
             for (auto &v : variants)
-                if (v.kind != 'R' && !by_sync.count(v.sync))
-                    by_sync[v.sync] = compileAlgo(model, a, true, v.sync, &consts, out_chunk);
+                if (v.program >= 0 && algoOfProgram(v.program) != a)
+                    v.program = -1; // "ltl" only applies to fd
+            auto programOf = [&](const Variant &v) { return v.program >= 0 ? v.program : a; };
+            auto bodyKey = [&](const Variant &v) { return v.sync * 16 + programOf(v); };
+            const CompiledAlgo c = compileAlgo(model, programOf(variants[0]), true, variants[0].sync, &consts, out_chunk);
+            std::map<int, CompiledAlgo> by_sync; // distinct (alignment period, program) bodies
+            for (auto &v : variants)
+                if (v.kind != 'R' && !by_sync.count(bodyKey(v)))
+                    by_sync[bodyKey(v)] = compileAlgo(model, programOf(v), true, v.sync, &consts, out_chunk);
             if (a == ALGO_PHI && c.n_out[0] == 0)
                 continue; // no implicit clusters
             bool want_roles = false, want_single = false;
@@ -238,13 +251,18 @@ int main(int argc, char **argv)
                 (v.kind == 'R' ? want_roles : want_single) = true;
             CompiledRoles roles;
             if (want_roles && a != ALGO_PHI)
-                roles = compileAlgoRoles(model, a, true, &consts);
+                for (auto &v : variants)
+                    if (v.kind == 'R')
+                    {
+                        roles = compileAlgoRoles(model, programOf(v), true, &consts);
+                        break;
+                    }
             const bool have_roles = want_roles && a != ALGO_PHI && roles.W > 1;
             std::ostringstream os;
             os << header_common;
             os << consts.definition("kc_table");
             if (by_sync.empty())
-                by_sync[variants[0].sync] = c;
+                by_sync[bodyKey(variants[0])] = c;
             for (auto &kv : by_sync)
                 emitBodyStruct(os, "Body" + std::to_string(kv.first), kv.second);
             if (have_roles)
@@ -255,9 +273,9 @@ int main(int argc, char **argv)
                 if (v.kind == 'R' && have_roles)
                     l << "&launchRoles<" << real << ", RoleBody, " << v.min_blocks << ">";
                 else if (v.kind == 'T')
-                    l << "&launchBatchedTma<" << real << ", Body" << v.sync << ", " << v.block << ", " << v.min_blocks << ">";
+                    l << "&launchBatchedTma<" << real << ", Body" << bodyKey(v) << ", " << v.block << ", " << v.min_blocks << ">";
                 else
-                    l << "&launchBatched<" << real << ", Body" << (v.kind == 'R' ? by_sync.begin()->first : v.sync) << ", "
+                    l << "&launchBatched<" << real << ", Body" << (v.kind == 'R' ? by_sync.begin()->first : bodyKey(v)) << ", "
                       << (v.kind == 'R' ? 128 : v.block) << ", " << (v.kind == 'R' ? 2 : v.min_blocks) << ", "
                       << (v.kind == 'D' ? "false" : "true") << ">";
                 return l.str();

@@ -73,6 +73,12 @@ def test_emitted_programs_match_oracle(grbda, oracle, robot, tmp_path):
     ins = [q, yd, aux]
     assert rel(run_tape(tapes["id"], ins)[0], o.inverse_dynamics(q, yd, aux)) < TOL
     assert rel(run_tape(tapes["fd"], ins)[0], o.forward_dynamics(q, yd, aux)) < TOL
+    # second forward-dynamics program (CRBA + bias + sparse L^T D L in one sweep): same answer, fewer operations
+    path = str(tmp_path / "fd_ltl.tape")
+    ltl_counts = m.dump_program(grbda.PROGRAM_FD_LTL, path)
+    assert rel(run_tape(load_tape(path), ins)[0], o.forward_dynamics(q, yd, aux)) < TOL
+    if o.nv >= 12:
+        assert ltl_counts["flops"] < m.dump_program(1)["flops"]
     assert rel(run_tape(tapes["h"], ins)[0].reshape(-1, o.nv, o.nv), o.mass_matrix(q)) < TOL
     p, R, v = o.forward_kinematics(q, yd)
     fk = run_tape(tapes["fk"], ins)
@@ -152,6 +158,12 @@ def test_urdf_models_against_mirrored_oracle(grbda, oracle, robot, tmp_path):
         tapes[name] = load_tape(path)
     assert rel(run_tape(tapes["id"], ins)[0], o.inverse_dynamics(q, yd, aux)) < TOL
     assert rel(run_tape(tapes["fd"], ins)[0], o.forward_dynamics(q, yd, aux)) < TOL
+    # second forward-dynamics program (CRBA + bias + sparse L^T D L in one sweep): same answer, fewer operations
+    path = str(tmp_path / "fd_ltl.tape")
+    ltl_counts = m.dump_program(grbda.PROGRAM_FD_LTL, path)
+    assert rel(run_tape(load_tape(path), ins)[0], o.forward_dynamics(q, yd, aux)) < TOL
+    if o.nv >= 12:
+        assert ltl_counts["flops"] < m.dump_program(1)["flops"]
     assert rel(run_tape(tapes["h"], ins)[0].reshape(-1, o.nv, o.nv), o.mass_matrix(q)) < TOL
     p, R, v = o.forward_kinematics(q, yd)
     fk = run_tape(tapes["fk"], ins)
