@@ -25,6 +25,10 @@
 //     6N x 6N products; rigid 10-parameter inertias are kept as long as possible;
 //   * D^-1 is an unrolled LDL^T (D = S^T IA S is SPD); the reference uses ColPivHouseholderQR.
 #pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <algorithm>
 #include <functional>
 #include <map>
 #include "../host/model.h"
@@ -179,7 +183,17 @@ namespace grbda
         class ModelCompiler
         {
         public:
-            explicit ModelCompiler(const ClusterTreeModel &model) : m_(model) {}
+            explicit ModelCompiler(const ClusterTreeModel &model) : m_(model) { findAxisymmetricLeaves(); }
+
+            // A leaf body whose inertia is symmetric about its own joint axis (a motor rotor: centre of
+            // mass on the axis, equal transverse moments, no products of inertia) exerts the same force
+            // on its parent and the same joint torque at every joint angle: with R the joint rotation,
+            // R I = I R and R s = s, hence v = R v', a = R a', f = R f' and X^T f = Xtree^T f', where the
+            // primed quantities are computed with the angle held at zero. Dynamics programs (ID, FD, H)
+            // therefore evaluate such bodies at angle zero: no sin/cos, constant transforms. Forward
+            // kinematics, whose outputs are the body poses themselves, keeps the angles.
+            void setFreezeAxisymmetricLeaves(bool on) { freeze_leaves_ = on; }
+            bool isAxisymmetricLeaf(int body) const { return axisym_leaf_[body] != 0; }
 
             // ---------------------------------------------------------------------------------
             // per-cluster constraint quantities
@@ -392,7 +406,9 @@ namespace grbda
                         const Body &body = c.bodies_[i];
                         BodyKin &b = bk_[body.index_];
                         const int axis = (int)d.axes[i];
-                        const Sym s = sym::sin(ck.q_s[i]), co = sym::cos(ck.q_s[i]);
+                        const bool frozen = freeze_leaves_ && axisym_leaf_[body.index_];
+                        const Sym s = frozen ? Sym(0.0) : sym::sin(ck.q_s[i]);
+                        const Sym co = frozen ? Sym(1.0) : sym::cos(ck.q_s[i]);
                         // XJ * Xtree  (Joint.h:94-97)
                         b.Xl.E = mul(coordinateRotation(d.axes[i], s, co), constM3(body.Xtree_.E));
                         b.Xl.r = constV3(body.Xtree_.r);
@@ -965,8 +981,17 @@ namespace grbda
                     return d.type == ClusterType::FreeQuaternion || d.type == ClusterType::FreeRollPitchYaw;
                 };
 
+                std::map<std::string, long> trace;
+                long mark = (long)Sym::G().nodes.size();
+                auto phase = [&](const char *name) {
+                    const long now = (long)Sym::G().nodes.size();
+                    trace[name] += now - mark;
+                    mark = now;
+                };
                 auto downward = [&](int ci) {
+                    phase("other");
                     kinematicsCluster(ci, true, true);
+                    phase("kinematics");
                     const ClusterTreeNode &c = m_.clusters()[ci];
                     const ClusterDesc &d = c.joint_;
                     // dof ancestry: the parent cluster's last dof and its ancestors, then own earlier dofs
@@ -1003,6 +1028,7 @@ namespace grbda
                         Ic[bi] = RigidInertia::fromMatrix(body.inertia_.getMatrix());
                         f[bi] = Ic[bi].apply(ai) + forceCross(b.v, Ic[bi].apply(b.v));
                     }
+                    phase("bias_down");
                 };
 
                 auto upward = [&](int ci) {
@@ -1039,6 +1065,7 @@ namespace grbda
                         for (auto &kv : to_parent)
                             f[kv.first] = f[kv.first] + kv.second;
                     }
+                    phase("bias_up");
                     // ---- rows of H owned by this cluster (cluster CRBA) ----
                     std::map<std::pair<int, int>, Sym> H; // (own dof, ancestor-or-own dof <= it)
                     for (int k = 0; k < n; k++)
@@ -1074,6 +1101,7 @@ namespace grbda
                             }
                         }
                     }
+                    phase("crba_rows");
                     // ---- composite inertia handed to the ancestor bodies ----
                     {
                         std::map<int, RigidInertia> Ic_to;
@@ -1092,6 +1120,7 @@ namespace grbda
                         for (auto &kv : Ic_to)
                             Ic[kv.first] = Ic[kv.first] + kv.second;
                     }
+                    phase("crba_inertia");
                     // ---- pivots of this cluster, last to first ----
                     for (int k = v0 + n - 1; k >= v0; k--)
                     {
@@ -1130,6 +1159,7 @@ namespace grbda
                             accb[anc[x]] = accb[anc[x]] + l * w;
                         }
                     }
+                    phase("pivots");
                 };
                 // final downward sweep (ancestors first)
                 auto solve = [&](int ci) {
@@ -1157,6 +1187,10 @@ namespace grbda
                     visit(r);
                 for (int r : roots_)
                     visit2(r);
+                phase("solve");
+                if (std::getenv("GRBDA_LTL_TRACE"))
+                    for (auto &kv : trace)
+                        std::fprintf(stderr, "ltl nodes %-14s %ld\n", kv.first.c_str(), kv.second);
                 return ydd_out;
             }
 
@@ -1205,7 +1239,45 @@ namespace grbda
                     it->second = it->second + Mk;
             }
 
+            void findAxisymmetricLeaves()
+            {
+                const int Nb = m_.getNumBodies();
+                axisym_leaf_.assign(Nb, 0);
+                std::vector<char> has_child(Nb, 0);
+                for (const Body &b : m_.bodies())
+                    if (b.parent_index_ >= 0)
+                        has_child[b.parent_index_] = 1;
+                for (const ClusterTreeNode &c : m_.clusters())
+                {
+                    const ClusterDesc &d = c.joint_;
+                    if (d.type == ClusterType::FreeQuaternion || d.type == ClusterType::FreeRollPitchYaw)
+                        continue;
+                    for (int i = 0; i < d.num_bodies; i++)
+                    {
+                        const int bi = c.first_body_ + i;
+                        if (has_child[bi])
+                            continue;
+                        const Mat6 &I = m_.bodies()[bi].inertia_.getMatrix();
+                        const int a = (int)d.axes[i], o1 = (a + 1) % 3, o2 = (a + 2) % 3;
+                        const double h[3] = {0.5 * (I[6 * 2 + 4] - I[6 * 1 + 5]), 0.5 * (I[6 * 0 + 5] - I[6 * 2 + 3]),
+                                             0.5 * (I[6 * 1 + 3] - I[6 * 0 + 4])};
+                        double scale = 0.0;
+                        for (int r = 0; r < 3; r++)
+                            for (int cc = 0; cc < 3; cc++)
+                                scale = std::max(scale, std::fabs(I[6 * r + cc]));
+                        const double tol = 1e-12 * scale, htol = 1e-12 * std::max(scale, std::fabs(I[35]));
+                        const bool ok = std::fabs(h[o1]) <= htol && std::fabs(h[o2]) <= htol &&
+                                        std::fabs(I[6 * a + o1]) <= tol && std::fabs(I[6 * a + o2]) <= tol &&
+                                        std::fabs(I[6 * o1 + o2]) <= tol &&
+                                        std::fabs(I[6 * o1 + o1] - I[6 * o2 + o2]) <= tol;
+                        axisym_leaf_[bi] = ok ? 1 : 0;
+                    }
+                }
+            }
+
             const ClusterTreeModel &m_;
+            bool freeze_leaves_ = true;
+            std::vector<char> axisym_leaf_;
             std::vector<BodyKin> bk_;
             std::vector<ClusterKin> ck_;
             std::vector<std::vector<int>> children_;

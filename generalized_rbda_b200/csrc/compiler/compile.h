@@ -64,6 +64,7 @@ namespace grbda
             {
                 p.n_in[0] = nq, p.n_in[1] = nv;
                 std::vector<sym::Sym> pp, R, v;
+                mc.setFreezeAxisymmetricLeaves(false); // the outputs are the poses themselves
                 mc.forwardKinematics(pp, R, v);
                 p.outputs = {pp, R, v};
                 break;
