@@ -195,6 +195,50 @@ namespace grbda
             void setFreezeAxisymmetricLeaves(bool on) { freeze_leaves_ = on; }
             bool isAxisymmetricLeaf(int body) const { return axisym_leaf_[body] != 0; }
 
+            // Gyrostat reduction (ID, H and the L^T D L forward dynamics): such a body r with parent p,
+            // axis z (in p's frame) and axial moment J obeys, with I_r s = [J z; 0] and s x* I_r = I_r s x,
+            //     f_r = [I_r a_p' + v_p' x* I_r v_p']  +  [J (qdd_r z + qd_r w_p x z); 0],
+            //     tau_r = J (z . wdot_p + qdd_r),
+            // so its inertia is merged into its parent's once, at compile time (X0^T I_r X0 with the
+            // constant Xtree), and what remains per rotor is a couple on the parent and one dot product.
+            // In the mass matrix it contributes J G_k G_l on its own dofs and the couple [J z G_k; 0]
+            // on p for the coupling with every dof that moves p.
+            void setGyrostatReduction(bool on) { gyrostats_ = on; }
+            bool isGyrostat(int body) const
+            {
+                return gyrostats_ && freeze_leaves_ && axisym_leaf_[body] && m_.bodies()[body].parent_index_ >= 0;
+            }
+            int jointAxisOfBody(int body) const
+            {
+                const ClusterTreeNode &c = m_.clusters()[m_.getIndexOfClusterContainingBody(body)];
+                return (int)c.joint_.axes[body - c.first_body_];
+            }
+            V3 gyrostatAxis(int body) const // joint axis of the rotor in its parent's frame
+            {
+                V3 e;
+                e[jointAxisOfBody(body)] = Sym(1.0);
+                return mulT(constM3(m_.bodies()[body].Xtree_.E), e);
+            }
+            Sym gyrostatInertia(int body) const
+            {
+                const int a = jointAxisOfBody(body);
+                return Sym(m_.bodies()[body].inertia_.getMatrix()[6 * a + a]);
+            }
+            // rigid inertia of a body, with the inertias of its gyrostat children merged in
+            RigidInertia bodyInertia(int body) const
+            {
+                RigidInertia I = RigidInertia::fromMatrix(m_.bodies()[body].inertia_.getMatrix());
+                for (const Body &r : m_.bodies())
+                    if (r.parent_index_ == body && isGyrostat(r.index_))
+                    {
+                        Xf X0;
+                        X0.E = constM3(r.Xtree_.E);
+                        X0.r = constV3(r.Xtree_.r);
+                        I = I + RigidInertia::fromMatrix(r.inertia_.getMatrix()).toParent(X0);
+                    }
+                return I;
+            }
+
             // ---------------------------------------------------------------------------------
             // per-cluster constraint quantities
             // ---------------------------------------------------------------------------------
@@ -451,6 +495,17 @@ namespace grbda
                 }
             }
 
+            // couple of a gyrostat on its parent (added to f_parent) and its own spanning joint torque
+            Sym gyrostatForces(int body, const Sym &qd, const Sym &qdd, const SV &a_parent, SV &f_parent) const
+            {
+                const int p = m_.bodies()[body].parent_index_;
+                const V3 z = gyrostatAxis(body);
+                const Sym J = gyrostatInertia(body);
+                const V3 n = J * (qdd * z + qd * cross(bk_[p].v.ang(), z));
+                f_parent = f_parent + SV::make(n, V3());
+                return J * (dot(z, a_parent.ang()) + qdd);
+            }
+
             SV minusGravity() const
             {
                 SV a;
@@ -492,7 +547,7 @@ namespace grbda
                 beginKinematics();
                 const int Nb = m_.getNumBodies(), nv = m_.getNumDegreesOfFreedom();
                 std::vector<SV> a(Nb), f(Nb);
-                std::vector<Sym> tau(nv, Sym(0.0));
+                std::vector<Sym> tau(nv, Sym(0.0)), gyro_tau(Nb);
 
                 auto downward = [&](int ci) {
                     kinematicsCluster(ci, true, false);
@@ -510,6 +565,15 @@ namespace grbda
                         const Body &body = m_.bodies()[bi];
                         const BodyKin &b = bk_[bi];
                         const int p = body.parent_index_;
+                        if (isGyrostat(bi))
+                        {
+                            const ClusterKin &ck = ck_[c.index_];
+                            Sym qdd = ck.g[i];
+                            for (int k = 0; k < n; k++)
+                                qdd = qdd + ck.G[i * n + k] * ydd[k];
+                            gyro_tau[bi] = gyrostatForces(bi, b.qd, qdd, a[p], f[p]);
+                            continue;
+                        }
                         SV ai = b.Xl.applyMotion(p >= 0 ? a[p] : minusGravity());
                         if (is_free)
                         {
@@ -530,7 +594,7 @@ namespace grbda
                             ai = ai + motionCross(b.v, sq);
                         }
                         a[bi] = ai;
-                        const RigidInertia I = RigidInertia::fromMatrix(body.inertia_.getMatrix());
+                        const RigidInertia I = bodyInertia(bi);
                         f[bi] = I.apply(ai) + forceCross(b.v, I.apply(b.v));
                     }
                 };
@@ -551,11 +615,11 @@ namespace grbda
                         else
                         {
                             const ClusterKin &ck = ck_[c.index_];
-                            const Sym tau_s = f[bi][(int)d.axes[i]];
+                            const Sym tau_s = isGyrostat(bi) ? gyro_tau[bi] : f[bi][(int)d.axes[i]];
                             for (int k = 0; k < n; k++)
                                 tau[c.velocity_index_ + k] = tau[c.velocity_index_ + k] + ck.G[i * n + k] * tau_s;
                         }
-                        if (p >= 0)
+                        if (p >= 0 && !isGyrostat(bi))
                         {
                             const SV fp = bk_[bi].Xl.applyForceTranspose(f[bi]);
                             if (m_.getIndexOfClusterContainingBody(p) == ci)
@@ -590,11 +654,11 @@ namespace grbda
                 const int Nb = m_.getNumBodies(), nv = m_.getNumDegreesOfFreedom();
                 std::vector<RigidInertia> Ic(Nb);
                 for (int i = 0; i < Nb; i++)
-                    Ic[i] = RigidInertia::fromMatrix(m_.bodies()[i].inertia_.getMatrix());
+                    Ic[i] = bodyInertia(i);
                 for (int i = Nb - 1; i >= 0; i--)
                 {
                     const int p = m_.bodies()[i].parent_index_;
-                    if (p >= 0)
+                    if (p >= 0 && !isGyrostat(i))
                         Ic[p] = Ic[p] + Ic[i].toParent(bk_[i].Xl);
                 }
                 // spanning dofs: body i owns dof columns sdof[i] .. (+6 for the free body, +1 else)
@@ -618,23 +682,38 @@ namespace grbda
                 for (int i = 0; i < Nb; i++)
                     for (int k = 0; k < sn[i]; k++)
                     {
-                        SV s;
-                        s[sn[i] == 6 ? k : axisOf(i)] = Sym(1.0);
-                        SV F = Ic[i].apply(s);
                         const int col = sdof[i] + k;
-                        for (int l = 0; l < sn[i]; l++)
-                            Hs[(sdof[i] + l) * ns + col] = F[sn[i] == 6 ? l : axisOf(i)];
+                        SV F;
                         int j = i;
-                        while (m_.bodies()[j].parent_index_ >= 0)
-                        {
-                            F = bk_[j].Xl.applyForceTranspose(F);
-                            j = m_.bodies()[j].parent_index_;
+                        auto record = [&]() {
                             for (int l = 0; l < sn[j]; l++)
                             {
                                 const Sym h = F[sn[j] == 6 ? l : axisOf(j)];
                                 Hs[(sdof[j] + l) * ns + col] = h;
                                 Hs[col * ns + sdof[j] + l] = h;
                             }
+                        };
+                        if (isGyrostat(i))
+                        {
+                            // own entry J, then the couple [J z; 0] on the parent
+                            Hs[col * ns + col] = gyrostatInertia(i);
+                            F = SV::make(gyrostatInertia(i) * gyrostatAxis(i), V3());
+                            j = m_.bodies()[i].parent_index_;
+                            record();
+                        }
+                        else
+                        {
+                            SV s;
+                            s[sn[i] == 6 ? k : axisOf(i)] = Sym(1.0);
+                            F = Ic[i].apply(s);
+                            for (int l = 0; l < sn[i]; l++)
+                                Hs[(sdof[i] + l) * ns + col] = F[sn[i] == 6 ? l : axisOf(i)];
+                        }
+                        while (m_.bodies()[j].parent_index_ >= 0)
+                        {
+                            F = bk_[j].Xl.applyForceTranspose(F);
+                            j = m_.bodies()[j].parent_index_;
+                            record();
                         }
                     }
                 // projection with the block-diagonal G
@@ -965,7 +1044,7 @@ namespace grbda
                 const int Nb = m_.getNumBodies(), nv = m_.getNumDegreesOfFreedom();
                 std::vector<SV> a(Nb), f(Nb);
                 std::vector<RigidInertia> Ic(Nb);
-                std::vector<Sym> bias(nv, Sym(0.0)), z(nv), ydd_out(nv);
+                std::vector<Sym> bias(nv, Sym(0.0)), z(nv), ydd_out(nv), gyro_tau(Nb);
                 std::vector<std::vector<int>> anc_dofs(nv); // ancestor dofs of a dof, ascending
                 std::vector<std::map<int, Sym>> L(nv);
                 std::map<std::pair<int, int>, Sym> Acc;
@@ -1014,6 +1093,11 @@ namespace grbda
                         const Body &body = m_.bodies()[bi];
                         const BodyKin &b = bk_[bi];
                         const int p = body.parent_index_;
+                        if (isGyrostat(bi))
+                        {
+                            gyro_tau[bi] = gyrostatForces(bi, b.qd, ck_[ci].g[i], a[p], f[p]);
+                            continue;
+                        }
                         SV ai = b.Xl.applyMotion(p >= 0 ? a[p] : minusGravity());
                         if (!isFree(d))
                         {
@@ -1025,7 +1109,7 @@ namespace grbda
                             ai = ai + motionCross(b.v, sq);
                         }
                         a[bi] = ai;
-                        Ic[bi] = RigidInertia::fromMatrix(body.inertia_.getMatrix());
+                        Ic[bi] = bodyInertia(bi);
                         f[bi] = Ic[bi].apply(ai) + forceCross(b.v, Ic[bi].apply(b.v));
                     }
                     phase("bias_down");
@@ -1047,11 +1131,11 @@ namespace grbda
                                     bias[v0 + k] = f[bi][k];
                             else
                             {
-                                const Sym tau_s = f[bi][(int)d.axes[i]];
+                                const Sym tau_s = isGyrostat(bi) ? gyro_tau[bi] : f[bi][(int)d.axes[i]];
                                 for (int k = 0; k < n; k++)
                                     bias[v0 + k] = bias[v0 + k] + ck_[ci].G[i * n + k] * tau_s;
                             }
-                            if (p >= 0)
+                            if (p >= 0 && !isGyrostat(bi))
                             {
                                 const SV fp = bk_[bi].Xl.applyForceTranspose(f[bi]);
                                 if (m_.getIndexOfClusterContainingBody(p) == ci)
@@ -1074,6 +1158,43 @@ namespace grbda
                         for (int i = 0; i < N; i++)
                         {
                             const BodyKin &b = bk_[b0 + i];
+                            if (isGyrostat(b0 + i))
+                            {
+                                // J G_k G_l on the own dofs; the couple [J z G_k; 0] on the parent body
+                                const Sym Gk = ck_[ci].G[i * n + k];
+                                if (Gk.isZero())
+                                    continue;
+                                const Sym JG = gyrostatInertia(b0 + i) * Gk;
+                                const int p = m_.bodies()[b0 + i].parent_index_;
+                                const SV Fc = SV::make(JG * gyrostatAxis(b0 + i), V3());
+                                for (int l = 0; l <= k; l++)
+                                    accumulate(H, v0 + k, v0 + l, JG * ck_[ci].G[i * n + l]);
+                                int target = p;
+                                SV Ft = Fc;
+                                if (p >= b0 && p < b0 + N)
+                                {
+                                    // parent inside this cluster: it moves with the own dofs as well
+                                    for (int l = 0; l < n; l++)
+                                    {
+                                        const Sym h = dot(bk_[p].S[l], Fc);
+                                        if (l <= k)
+                                            accumulate(H, v0 + k, v0 + l, h);
+                                        if (l >= k)
+                                            accumulate(H, v0 + l, v0 + k, h);
+                                    }
+                                    target = bk_[p].anc;
+                                    if (target >= 0)
+                                        Ft = bk_[p].Xup.applyForceTranspose(Fc);
+                                }
+                                if (target >= 0)
+                                {
+                                    if (F_anc.count(target))
+                                        F_anc[target] = F_anc[target] + Ft;
+                                    else
+                                        F_anc[target] = Ft;
+                                }
+                                continue;
+                            }
                             const SV Fi = Ic[b0 + i].apply(b.S[k]);
                             for (int l = 0; l <= k; l++)
                                 accumulate(H, v0 + k, v0 + l, dot(b.S[l], Fi));
@@ -1108,7 +1229,7 @@ namespace grbda
                         for (int i = 0; i < N; i++)
                         {
                             const BodyKin &b = bk_[b0 + i];
-                            if (b.anc < 0)
+                            if (b.anc < 0 || isGyrostat(b0 + i))
                                 continue;
                             const RigidInertia Ip = Ic[b0 + i].toParent(b.Xup);
                             auto it = Ic_to.find(b.anc);
@@ -1276,7 +1397,7 @@ namespace grbda
             }
 
             const ClusterTreeModel &m_;
-            bool freeze_leaves_ = true;
+            bool freeze_leaves_ = true, gyrostats_ = true;
             std::vector<char> axisym_leaf_;
             std::vector<BodyKin> bk_;
             std::vector<ClusterKin> ck_;
