@@ -50,6 +50,7 @@ _lib.grbda_cuda_cluster_G.argtypes = [_vp, C.c_int, _vp]
 _lib.grbda_cuda_model_gravity.argtypes = [_vp, _vp]
 _lib.grbda_cuda_cluster_phi.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp]
 _lib.grbda_cuda_dump_program.argtypes = [_vp, C.c_int, C.c_char_p, _vp]
+_lib.grbda_cuda_kernel_counts.argtypes = [_vp, C.c_int, _vp]
 _lib.grbda_cuda_dump_role_program.argtypes = [_vp, C.c_int, C.c_char_p, _vp]
 for _p in ("f64", "f32"):
     getattr(_lib, "grbda_cuda_inverse_dynamics_" + _p).argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp]
@@ -68,7 +69,7 @@ EXPORTED_SYMBOLS = [
     "grbda_cuda_model_create_from_urdf", "grbda_cuda_model_create_from_robot", "grbda_cuda_model_destroy",
     "grbda_cuda_num_positions", "grbda_cuda_num_degrees_of_freedom", "grbda_cuda_num_bodies",
     "grbda_cuda_num_clusters", "grbda_cuda_model_hash", "grbda_cuda_cluster_info", "grbda_cuda_body_info",
-    "grbda_cuda_cluster_G", "grbda_cuda_model_gravity", "grbda_cuda_cluster_phi", "grbda_cuda_dump_program", "grbda_cuda_dump_role_program",
+    "grbda_cuda_cluster_G", "grbda_cuda_model_gravity", "grbda_cuda_cluster_phi", "grbda_cuda_dump_program", "grbda_cuda_dump_role_program", "grbda_cuda_kernel_counts",
     "grbda_cuda_inverse_dynamics_f64", "grbda_cuda_inverse_dynamics_f32",
     "grbda_cuda_forward_dynamics_f64", "grbda_cuda_forward_dynamics_f32",
     "grbda_cuda_mass_matrix_f64", "grbda_cuda_mass_matrix_f32",
@@ -230,6 +231,15 @@ class ClusterTreeModel:
         d["flops"] = d["add"] + d["mul"] + d["div"] + d["sqrt"]
         return d
 
+    def kernel_counts(self, algo):
+        """Operation counts of the program the default compiled kernel of `algo` runs per state."""
+        counts = (C.c_int64 * 8)()
+        _check(_lib.grbda_cuda_kernel_counts(self._h, algo, counts))
+        keys = ("nodes", "add", "mul", "div", "sqrt", "sin", "cos", "fusable")
+        d = dict(zip(keys, [int(x) for x in counts]))
+        d["flops"] = d["add"] + d["mul"] + d["div"] + d["sqrt"]
+        return d
+
     def dump_role_program(self, algo, path=None):
         info = (C.c_int64 * 4)()
         _check(_lib.grbda_cuda_dump_role_program(self._h, algo, path.encode() if path else None, info))
@@ -289,16 +299,24 @@ class ClusterTreeModel:
         import torch
         return self.inverseDynamics(q, yd, torch.zeros_like(yd))
 
-    def forwardKinematics(self, q, yd):
+    def forwardKinematics(self, q, yd, out=None):
         """(p[batch, nb, 3], R[batch, nb, 3, 3], v[batch, nb, 6]) per body: world position,
-        body-to-world rotation, [world angular; world linear] velocity of the body origin."""
+        body-to-world rotation, [world angular; world linear] velocity of the body origin.
+        out: optional (p, R, v) tensors of those shapes to write into."""
         import torch
         q = self._prep(q, self.nq)
         yd = self._prep(yd, self.nv, q.dtype)
         B = q.shape[0]
-        p = torch.empty((B, self.nb, 3), dtype=q.dtype, device=q.device)
-        R = torch.empty((B, self.nb, 3, 3), dtype=q.dtype, device=q.device)
-        v = torch.empty((B, self.nb, 6), dtype=q.dtype, device=q.device)
+        if out is not None:
+            p, R, v = out
+            for t, shape in ((p, (B, self.nb, 3)), (R, (B, self.nb, 3, 3)), (v, (B, self.nb, 6))):
+                if tuple(t.shape) != shape or t.dtype != q.dtype or not t.is_cuda or not t.is_contiguous():
+                    raise ValueError("forwardKinematics: out tensors must be contiguous CUDA tensors of shape "
+                                     "(B, nb, 3), (B, nb, 3, 3), (B, nb, 6) and the dtype of q")
+        else:
+            p = torch.empty((B, self.nb, 3), dtype=q.dtype, device=q.device)
+            R = torch.empty((B, self.nb, 3, 3), dtype=q.dtype, device=q.device)
+            v = torch.empty((B, self.nb, 6), dtype=q.dtype, device=q.device)
         fn = getattr(_lib, "grbda_cuda_forward_kinematics_" + self._suffix(q))
         _check(fn(self._h, _ptr(q), _ptr(yd), _ptr(p), _ptr(R), _ptr(v), B, _stream()))
         return p, R, v

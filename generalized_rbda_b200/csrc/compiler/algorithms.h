@@ -444,7 +444,11 @@ namespace grbda
                         return;
                     }
 
+                    const long n0 = (long)Sym::G().nodes.size();
                     ClusterKin ck = clusterConstraint(c, with_velocity);
+                    if (std::getenv("GRBDA_LTL_TRACE"))
+                        std::fprintf(stderr, "constraint nodes cluster %d type %d: %ld\n", ci, (int)d.type,
+                                     (long)Sym::G().nodes.size() - n0);
                     for (int i = 0; i < d.num_bodies; i++)
                     {
                         const Body &body = c.bodies_[i];
@@ -1299,10 +1303,11 @@ namespace grbda
                         visit(ch);
                     upward(ci);
                 };
+                // last limb first: its factor entries were produced last and are still in registers
                 std::function<void(int)> visit2 = [&](int ci) {
                     solve(ci);
-                    for (int ch : children_[ci])
-                        visit2(ch);
+                    for (auto it = children_[ci].rbegin(); it != children_[ci].rend(); ++it)
+                        visit2(*it);
                 };
                 for (int r : roots_)
                     visit(r);

@@ -299,6 +299,16 @@ extern "C"
             return (grbda_status)GRBDA_OK; });
     }
 
+    grbda_status grbda_cuda_kernel_counts(const grbda_model *m, int algo, int64_t *counts8)
+    {
+        if (!m || !counts8 || algo < 0 || algo >= compiler::ALGO_COUNT)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        if (!m->kernels || !m->kernels->algo[algo].f64[0])
+            return fail(GRBDA_ERR_NOT_COMPILED, "no compiled kernel for this model / algorithm");
+        std::memcpy(counts8, m->kernels->algo[algo].counts, 8 * sizeof(int64_t));
+        return GRBDA_OK;
+    }
+
     grbda_status grbda_cuda_dump_role_program(const grbda_model *m, int algo, const char *path, int64_t *info4)
     {
         if (!m || algo < 0 || algo >= compiler::PROGRAM_COUNT)

@@ -136,10 +136,18 @@ grbda_status grbda_cuda_cluster_phi(const grbda_model *m, int cluster, grbda_phi
                                     uint8_t *independent, int32_t *sizes2);
 /* explicit cluster: G (num_bodies x num_independent, row-major) */
 grbda_status grbda_cuda_cluster_G(const grbda_model *m, int cluster, double *G);
-/* Emitted program of one algorithm (0 ID, 1 FD, 2 FK, 3 H, 4 phi/Kd) written as a binary tape to
+/* Emitted program of one algorithm (0 ID, 1 FD (articulated-body sweep), 2 FK, 3 H, 4 phi/Kd,
+ * 5 FD as H^-1 (tau - C): cluster CRBA + RNEA bias + branch-sparse L^T D L) written as a binary tape to
  * `path` (format: csrc/compiler/compile.h); counts[8] = {nodes, add, mul, div, sqrt, sin, cos,
  * fusable mul+add pairs} of the straight-line program each thread executes. */
 grbda_status grbda_cuda_dump_program(const grbda_model *m, int algo, const char *path, int64_t *counts8);
+
+/* Operation counts (same 8 fields) of the program the DEFAULT compiled kernel of entry point `algo`
+ * (0 ID, 1 FD, 2 FK, 3 H, 4 phi) executes per state. It can differ from dump_program(algo): the default
+ * forward-dynamics kernel of a model may run program 5 (CRBA + bias + sparse L^T D L) instead of the
+ * articulated-body sweep (program 1); both are ClusterTreeModel::forwardDynamics
+ * (ClusterTreeDynamics.cpp:10-19 / :59-155) up to rounding. */
+grbda_status grbda_cuda_kernel_counts(const grbda_model *m, int algo, int64_t *counts8);
 
 /* The limb-parallel (one warp per limb, compiler/partition.h) form of the same program, written as a
  * role tape; info4 = {W (warps per state), communication slots, max per-role flops, sum of per-role

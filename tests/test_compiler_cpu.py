@@ -89,6 +89,24 @@ def test_emitted_programs_match_oracle(grbda, oracle, robot, tmp_path):
         assert np.abs(phi).max() < 1e-8  # generated states satisfy the loop constraints
 
 
+def test_rotor_reductions(grbda, oracle, tmp_path):
+    """Axisymmetric leaf bodies (motor rotors) are evaluated at angle zero and folded into their parent
+    as gyrostats in the dynamics programs; forward kinematics keeps their angles. The oracle (which does
+    neither) is the judge; here: the reductions really happened, and the default kernels run the
+    programs the counts describe."""
+    m = grbda.ClusterTreeModel.from_robot("tello_with_arms", device=None)
+    o = oracle.OracleModel("tello_with_arms")
+    n_rotors = sum(1 for b in m.bodies() if "rotor" in b["name"])
+    assert n_rotors == 18
+    revolute = o.nb - 1
+    idc, fkc = m.dump_program(grbda.ALGO_ID), m.dump_program(grbda.ALGO_FK)
+    assert idc["sin"] <= revolute - n_rotors + 18   # 18 link joints + the sines inside the four phi programs
+    assert fkc["sin"] > idc["sin"]                  # FK still evaluates the rotor angles
+    assert idc["flops"] < o.count_flops(0)["flops_alg"]
+    assert m.kernel_counts(grbda.ALGO_FD) == m.dump_program(grbda.PROGRAM_FD_LTL)
+    assert m.kernel_counts(grbda.ALGO_ID) == idc
+
+
 @pytest.mark.parametrize("robot", ["tello", "tello_with_arms"])
 def test_limb_parallel_programs_match_oracle(grbda, oracle, robot, tmp_path):
     """One warp per limb: each role may only use values it computed or received through a

@@ -80,6 +80,31 @@ def test_dynamics_parity_f64(grbda, oracle, torch, robot):
     assert relrows(C, o.inverse_dynamics(qn, ydn, np.zeros_like(ydn))) < TOL64
 
 
+@pytest.mark.parametrize("robot", ["tello_with_arms", "mit_humanoid", "four_bar", "revolute_pair_chain_with_rotor_4"])
+def test_every_compiled_kernel_variant(grbda, oracle, torch, robot, monkeypatch):
+    """Every launch shape / program compiled for a model (GRBDA_KERNEL_VARIANT): the forward-dynamics slots
+    hold both programs (CRBA + sparse LTDL, and the articulated-body sweep); all must agree with the oracle."""
+    m = grbda.ClusterTreeModel.from_robot(robot)
+    o = oracle_for(oracle, m, robot)
+    q, yd, aux, _ = m.generateStates(777, seed=11)
+    qn, ydn, auxn = q.cpu().numpy(), yd.cpu().numpy(), aux.cpu().numpy()
+    ydd_o, tau_o = o.forward_dynamics(qn, ydn, auxn), o.inverse_dynamics(qn, ydn, auxn)
+    ran = 0
+    for variant in range(4):
+        monkeypatch.setenv("GRBDA_KERNEL_VARIANT", str(variant))
+        try:
+            ydd = m.forwardDynamics(q, yd, aux)
+        except grbda.GrbdaError:
+            continue  # fewer than 4 variants compiled for this model
+        ran += 1
+        assert relrows(ydd.cpu().numpy(), ydd_o) < TOL64
+        try:
+            assert relrows(m.inverseDynamics(q, yd, aux).cpu().numpy(), tau_o) < TOL64
+        except grbda.GrbdaError:
+            pass
+    assert ran >= 2
+
+
 @pytest.mark.parametrize("robot", ["tello_with_arms", "mini_cheetah", "mit_humanoid", "revolute_chain_with_rotor_2"])
 def test_dynamics_parity_f32(grbda, oracle, torch, robot):
     """FP32 variant against the FP64 oracle on float-rounded states."""
