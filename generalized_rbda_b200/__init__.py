@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libgrbda_cuda.so")
+_LIB_PATH = os.environ.get("GRBDA_LIB_PATH") or os.path.join(_HERE, "libgrbda_cuda.so")  # override: kernel experiments
 URDF_DIR = os.path.join(_HERE, "robot-models")
 
 if not os.path.exists(_LIB_PATH):

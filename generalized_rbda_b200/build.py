@@ -31,7 +31,7 @@ LIB = os.path.join(HERE, "libgrbda_cuda.so")
 DEFAULT_VARIANTS = "id=T,128,2;S,128,2|fd=S,128,2,ltl;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2"
 SYNC_EVERY = int(os.environ.get("GRBDA_SYNC_EVERY", "0"))  # alignment barriers measured useless (profiles/)
 MODELS = {
-    "tello_with_arms": ("id,fd,fk,h,phi,gen", "id=T,128,2;S,128,2|fd=S,128,2,ltl;D,128,2,ltl;S,128,2;T,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2", True),
+    "tello_with_arms": ("id,fd,fk,h,phi,gen", "id=T,128,2;S,128,2|fd=D,128,2,ltl;T,128,2,ltl;S,128,2,ltl;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2", True),
     "tello": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
     "mini_cheetah": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
     "mit_humanoid": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
@@ -48,7 +48,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXXFLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-variable", "-Wno-sign-compare"]
 NVCCFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
              "-Xcompiler", "-fPIC", "-I", CSRC, "-ccbin", CXX,
-             "-DGRBDA_DEFAULT_URDF_DIR=\"%s\"" % URDF_DIR]
+             "-DGRBDA_DEFAULT_URDF_DIR=\"%s\"" % URDF_DIR] + os.environ.get("GRBDA_EXTRA_NVCCFLAGS", "").split()
 
 HOST_SOURCES = ["host/robots.cpp", "host/robot_factory.cpp", "host/urdf.cpp"]
 

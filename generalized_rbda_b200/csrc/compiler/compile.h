@@ -35,6 +35,7 @@ namespace grbda
             int n_in[3] = {0, 0, 0};
             int n_out[3] = {0, 0, 0};
             std::string body;
+            std::string range_check; // expression: may the fast sin/cos forms be used for this state
             ProgramStats stats;
             Tape tape;
         };
@@ -119,7 +120,10 @@ namespace grbda
             out.stats = em.stats();
             out.tape = em.tape();
             if (want_body)
+            {
                 out.body = em.cudaBody(sync_every, out_chunk);
+                out.range_check = em.cudaRangeCheck();
+            }
             return out;
         }
 

@@ -4,6 +4,9 @@
 //       compiler self-tests in tests/ (a numpy interpreter replays it against the oracle),
 //   (c) exact operation counts of the emitted program.
 #pragma once
+#include <iomanip>
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <sstream>
 #include <algorithm>
@@ -139,6 +142,120 @@ namespace grbda
                 return t;
             }
 
+            // Range condition of the fast sin/cos forms (kernels/batched_kernel.cuh): every live sin/cos
+            // argument is bounded as |arg| <= a Y + b when all inputs it depends on satisfy |x| <= Y
+            // (affine interval propagation through +, -, negation and products / quotients with
+            // constants). cudaRangeCheck() returns the generated test "all such inputs are within Y",
+            // with Y = min over the arguments of (limit - b) / a; an argument that is not affine in the
+            // inputs (never the case for joint angles) disables the fast forms for the program.
+            struct TrigRange
+            {
+                std::vector<std::pair<int, int>> inputs; // (array, element) feeding a sin/cos argument
+                bool affine = true;
+                double max_gain = 0.0, max_offset = 0.0;  // over the arguments
+                double bound(double limit) const          // admissible |input|
+                {
+                    double Y = 1e300;
+                    for (auto &ab : args)
+                        if (ab.first > 0)
+                            Y = std::min(Y, (limit - ab.second) / ab.first);
+                    return Y;
+                }
+                std::vector<std::pair<double, double>> args; // (a, b) per argument
+            };
+            TrigRange trigRange() const
+            {
+                const size_t n = g_.nodes.size();
+                const double INF = 1e300;
+                std::vector<double> A(n, 0.0), B(n, 0.0);
+                std::vector<std::vector<int32_t>> deps(n); // inputs a node depends on (only kept while small)
+                TrigRange tr;
+                std::vector<char> is_arg(n, 0), feeds(n, 0);
+                for (size_t i = 0; i < n; i++)
+                    if (live_[i] && (g_.nodes[i].op == sym::OP_SIN || g_.nodes[i].op == sym::OP_COS))
+                        is_arg[g_.nodes[i].a] = 1;
+                for (size_t i = 0; i < n; i++)
+                {
+                    const sym::Node &nd = g_.nodes[i];
+                    switch (nd.op)
+                    {
+                    case sym::OP_CONST: A[i] = 0, B[i] = std::fabs(nd.val); break;
+                    case sym::OP_INPUT: A[i] = 1, B[i] = 0; break;
+                    case sym::OP_ADD:
+                    case sym::OP_SUB: A[i] = A[nd.a] + A[nd.b], B[i] = B[nd.a] + B[nd.b]; break;
+                    case sym::OP_NEG: A[i] = A[nd.a], B[i] = B[nd.a]; break;
+                    case sym::OP_MUL:
+                        if (A[nd.a] == 0) // bounded factor (a constant, or e.g. a sine) times an affine one
+                            A[i] = B[nd.a] * A[nd.b], B[i] = B[nd.a] * B[nd.b];
+                        else if (A[nd.b] == 0)
+                            A[i] = B[nd.b] * A[nd.a], B[i] = B[nd.b] * B[nd.a];
+                        else
+                            A[i] = INF, B[i] = INF;
+                        break;
+                    case sym::OP_DIV:
+                        if (g_.nodes[nd.b].op == sym::OP_CONST && g_.nodes[nd.b].val != 0.0)
+                            A[i] = A[nd.a] / std::fabs(g_.nodes[nd.b].val), B[i] = B[nd.a] / std::fabs(g_.nodes[nd.b].val);
+                        else
+                            A[i] = INF, B[i] = INF;
+                        break;
+                    case sym::OP_SIN:
+                    case sym::OP_COS: A[i] = 0, B[i] = 1; break;
+                    default: A[i] = INF, B[i] = INF; break;
+                    }
+                    if (A[i] > INF)
+                        A[i] = INF;
+                    if (B[i] > INF)
+                        B[i] = INF;
+                }
+                // inputs feeding the arguments: backward marking
+                for (size_t i = n; i-- > 0;)
+                {
+                    if (is_arg[i])
+                        feeds[i] = 1;
+                    if (!feeds[i])
+                        continue;
+                    const sym::Node &nd = g_.nodes[i];
+                    if (nd.op == sym::OP_INPUT)
+                    {
+                        tr.inputs.push_back({nd.a, nd.b});
+                        continue;
+                    }
+                    if (nd.op == sym::OP_CONST)
+                        continue;
+                    for (int32_t o : {nd.a, nd.b, nd.c, nd.e})
+                        if (o >= 0)
+                            feeds[o] = 1;
+                }
+                std::sort(tr.inputs.begin(), tr.inputs.end());
+                for (size_t i = 0; i < n; i++)
+                    if (is_arg[i])
+                    {
+                        if (A[i] >= INF || B[i] >= INF)
+                            tr.affine = false;
+                        tr.args.push_back({A[i], B[i]});
+                        tr.max_gain = std::max(tr.max_gain, A[i]);
+                        tr.max_offset = std::max(tr.max_offset, B[i]);
+                    }
+                return tr;
+            }
+            // expression (over IN0/IN1/IN2 and `real`) that is true when the fast forms may be used
+            std::string cudaRangeCheck(double limit64 = 1.0e12, double limit32 = 1.0e6) const
+            {
+                const TrigRange tr = trigRange();
+                if (tr.args.empty())
+                    return "true";
+                if (!tr.affine || tr.bound(limit32) <= 0)
+                    return "false";
+                std::ostringstream os;
+                os << std::setprecision(17);
+                os << "[&]() { unsigned m = 0u;";
+                for (auto &in : tr.inputs)
+                    os << " m = max(m, absKey(IN" << in.first << "(" << in.second << ")));";
+                os << " return m < absKey(sizeof(real) == 8 ? KC(" << tr.bound(limit64) << ") : KC(" << tr.bound(limit32)
+                   << ")); }()";
+                return os.str();
+            }
+
             // Body text. Inputs are read through IN0(i)/IN1(i)/IN2(i), results written through
             // OUT0(i, x)/OUT1/OUT2; `real` is the arithmetic type; KC(x) makes a literal of type real.
             // sync_every > 0: emit GRBDA_ALIGN() after every `sync_every` statements. All warps of a CTA
@@ -236,6 +353,15 @@ namespace grbda
                             neg_outputs_of[k].push_back(id);
                     }
 
+                // the two most recent arithmetic results: anchor of GRBDA_PIN (kernels: pinAfter) for the
+                // sin/cos evaluations, which would otherwise all be hoisted to the top of the program
+                int32_t last_temp[2] = {-1, -1};
+                auto pinned = [&](int32_t arg) {
+                    const int32_t anchor = last_temp[0] != arg ? last_temp[0] : last_temp[1];
+                    if (anchor < 0)
+                        return ref(arg);
+                    return "GRBDA_PIN(" + ref(arg) + ", t" + std::to_string(anchor) + ")";
+                };
                 for (size_t i = 0; i < g_.nodes.size(); i++)
                 {
                     if (!live_[i])
@@ -277,7 +403,7 @@ namespace grbda
                         os << "const real t" << i << " = " << ref(n.a) << " * " << ref(n.b) << ";\n";
                         break;
                     case sym::OP_DIV:
-                        os << "const real t" << i << " = " << ref(n.a) << " / " << ref(n.b) << ";\n";
+                        os << "const real t" << i << " = GRBDA_DIV(" << ref(n.a) << ", " << ref(n.b) << ");\n";
                         break;
                     case sym::OP_SQRT:
                         os << "const real t" << i << " = sqrt(" << ref(n.a) << ");\n";
@@ -295,19 +421,24 @@ namespace grbda
                         {
                             const int32_t s = n.op == sym::OP_SIN ? (int32_t)i : other;
                             const int32_t c = n.op == sym::OP_SIN ? other : (int32_t)i;
-                            os << "real t" << s << ", t" << c << "; grbda_sincos(" << ref(n.a) << ", &t" << s
+                            os << "real t" << s << ", t" << c << "; grbda_sincos<FAST>(" << pinned(n.a) << ", &t" << s
                                << ", &t" << c << ");\n";
                             done[other] = 1;
                         }
                         else
-                            os << "const real t" << i << " = " << (n.op == sym::OP_SIN ? "grbda_sin(" : "grbda_cos(")
-                               << ref(n.a) << ");\n";
+                            os << "const real t" << i << " = " << (n.op == sym::OP_SIN ? "grbda_sin<FAST>(" : "grbda_cos<FAST>(")
+                               << pinned(n.a) << ");\n";
                         break;
                     }
                     default:
                         throw std::runtime_error("emit: unknown op");
                     }
                     done[i] = 1;
+                    if (n.op == sym::OP_ADD || n.op == sym::OP_SUB || n.op == sym::OP_MUL || n.op == sym::OP_DIV)
+                    {
+                        last_temp[1] = last_temp[0];
+                        last_temp[0] = (int32_t)i;
+                    }
                     emitStores(i);
                     for (int32_t ng : neg_outputs_of[i])
                         emitStores(ng);

@@ -384,7 +384,7 @@ namespace grbda
                         os << "const real t" << i << " = " << ref(n.a) << " * " << ref(n.b) << ";\n";
                         break;
                     case sym::OP_DIV:
-                        os << "const real t" << i << " = " << ref(n.a) << " / " << ref(n.b) << ";\n";
+                        os << "const real t" << i << " = GRBDA_DIV(" << ref(n.a) << ", " << ref(n.b) << ");\n";
                         break;
                     case sym::OP_SQRT:
                         os << "const real t" << i << " = sqrt(" << ref(n.a) << ");\n";
@@ -402,12 +402,12 @@ namespace grbda
                         {
                             const int32_t sN = n.op == sym::OP_SIN ? i : it->second;
                             const int32_t cN = n.op == sym::OP_SIN ? it->second : i;
-                            os << "real t" << sN << ", t" << cN << "; grbda_sincos(" << ref(n.a) << ", &t" << sN
+                            os << "real t" << sN << ", t" << cN << "; grbda_sincos<false>(" << ref(n.a) << ", &t" << sN
                                << ", &t" << cN << ");\n";
                             defined[it->second] = 1;
                         }
                         else
-                            os << "const real t" << i << " = " << (n.op == sym::OP_SIN ? "grbda_sin(" : "grbda_cos(") << ref(n.a)
+                            os << "const real t" << i << " = " << (n.op == sym::OP_SIN ? "grbda_sin<false>(" : "grbda_cos<false>(") << ref(n.a)
                                << ");\n";
                         break;
                     }

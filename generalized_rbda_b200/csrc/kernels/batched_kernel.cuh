@@ -13,6 +13,7 @@
 // shared memory (stage_in), the threads then read their own state from shared memory with an odd
 // stride (bank-conflict free), and results go back the same way (stage_out).
 #pragma once
+#include <algorithm>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <type_traits>
@@ -25,13 +26,32 @@ namespace grbda_kernels
         void *out[3];
         int64_t batch;
         cudaStream_t stream;
+        int *launched = nullptr; // optional: incremented by the number of kernels enqueued
+        // scratch for the per-tile flags of the sin/cos range decision: at least ceil(batch / 32) bytes,
+        // owned by the caller, private to `stream` (launches on one stream are ordered)
+        unsigned char *flags = nullptr;
+        size_t flags_bytes = 0;
     };
 
-    // sin and cos of a joint angle in FP64, branch-free on the fast path (~40 instructions instead of
-    // the ~100 + slow-path call of the library sincos; the kernels are instruction-issue bound, so
-    // this matters). Cody-Waite reduction by pi/2 with three FMA steps, then the fdlibm kernel
-    // polynomials on [-pi/4, pi/4] (error < 1 ulp for |x| < 1e5, far inside the 1e-10 parity budget).
-    // Joint angles are a few radians; anything beyond 1e5 falls back to the library.
+    // ---- scalar math of the generated bodies -------------------------------------------------------
+    // The generated per-state program is ONE basic block of several thousand FP64 instructions. Any
+    // branch inside it (the library sincos and the IEEE division both carry a slow-path call) cuts it
+    // into pieces: ptxas then schedules, hoists loads and allocates registers per piece, and every
+    // branch drains the instruction buffer. So the body uses branch-free forms only, and the one range
+    // decision is hoisted in front of it: Body::inRange() (generated: every input that feeds a sin/cos
+    // argument is bounded so that each argument stays below the limit of the fast reduction) is
+    // evaluated once per CTA tile. The FAST kernel runs run<real, true> on tiles that pass and records
+    // the others in a per-launch flag array; a second, small launch (run<real, false>: library sincos)
+    // scans the flags and recomputes exactly those tiles. Keeping the two bodies in different kernels
+    // matters: one kernel holding both (or calling the slow one) compiles to a much worse fast path.
+    //
+    // FP64 sincos, fast form: Cody-Waite reduction by pi/2 with three FMA steps (pi/2 split into three
+    // doubles, 159 bits), then the fdlibm kernel polynomials on [-pi/4, pi/4]. Every step is an FMA, so
+    // the products k * pi/2_i are exact and the reduced argument carries an ABSOLUTE error of a few
+    // 1e-16 as long as k = round(x 2/pi) is exact in the 2^52 rounding trick and k * 2^-159 is
+    // negligible: |x| <= 1e12 leaves orders of magnitude on both (sincosFastLimit). What the fast form
+    // gives up against the library beyond ~1e5 is the RELATIVE accuracy of results that are themselves
+    // ~1e-16 (arguments within 1e-16 of a multiple of pi/2); the dynamics need absolute accuracy.
     static __constant__ double grbda_sc_k[18] = {
         0.63661977236758138, 6755399441055744.0, -1.5707963267948966, -6.123233995736766e-17,
         1.4973849048591698e-33,
@@ -39,17 +59,19 @@ namespace grbda_kernels
         -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
         -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
         2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02, 1.0e5};
+    // largest |argument| the fast reductions are used for (generated inRange() keeps arguments below it)
+    template <typename real>
+    __host__ __device__ constexpr double sincosFastLimit() { return sizeof(real) == 8 ? 1.0e12 : 1.0e6; }
 
-    static __device__ __noinline__ void grbda_sincos_slow(double x, double *s, double *c) { sincos(x, s, c); }
-
+    template <bool FAST>
     __device__ __forceinline__ void grbda_sincos(double x, double *s, double *c)
     {
-        const double *K = grbda_sc_k; // constant-bank operands: no instruction spent on literals
-        if (fabs(x) > K[17])
+        if (!FAST)
         {
-            grbda_sincos_slow(x, s, c);
+            sincos(x, s, c);
             return;
         }
+        const double *K = grbda_sc_k; // constant-bank operands: no instruction spent on literals
         const double t = fma(x, K[0], K[1]); // round-to-nearest-integer trick (1.5 * 2^52)
         const int k = __double2loint(t);
         const double kd = t - K[1];
@@ -73,11 +95,108 @@ namespace grbda_kernels
         *s = (k & 2) ? -a : a;
         *c = ((k + 1) & 2) ? -b : b;
     }
-    __device__ __forceinline__ void grbda_sincos(float x, float *s, float *c) { sincosf(x, s, c); }
-    __device__ __forceinline__ double grbda_sin(double x) { double s, c; grbda_sincos(x, &s, &c); return s; }
-    __device__ __forceinline__ double grbda_cos(double x) { double s, c; grbda_sincos(x, &s, &c); return c; }
-    __device__ __forceinline__ float grbda_sin(float x) { return sinf(x); }
-    __device__ __forceinline__ float grbda_cos(float x) { return cosf(x); }
+    // FP32: the same scheme (three-constant reduction, 72 bits of pi/2; degree-7/8 minimax kernels);
+    // absolute error ~1e-7 for |x| <= 1e6 (k < 2^22 in the 2^23 rounding trick). FP32 parity budget: 1e-4.
+    template <bool FAST>
+    __device__ __forceinline__ void grbda_sincos(float x, float *s, float *c)
+    {
+        if (!FAST)
+        {
+            sincosf(x, s, c);
+            return;
+        }
+        const float t = fmaf(x, 0.636619772f, 12582912.0f); // 1.5 * 2^23
+        const int k = __float_as_int(t);
+        const float kd = t - 12582912.0f;
+        float r = fmaf(kd, -1.57079601e+00f, x);
+        r = fmaf(kd, -3.13916473e-07f, r);
+        r = fmaf(kd, -5.39030253e-15f, r);
+        const float z = r * r;
+        float ps = fmaf(z, 2.86567956e-6f, -1.98559923e-4f);
+        ps = fmaf(z, ps, 8.33338592e-3f);
+        ps = fmaf(z, ps, -1.66666672e-1f);
+        const float sr = fmaf(z * r, ps, r);
+        float pc = fmaf(z, 2.44677067e-5f, -1.38877297e-3f);
+        pc = fmaf(z, pc, 4.16666567e-2f);
+        pc = fmaf(z, pc, -0.5f);
+        const float cr = fmaf(z, pc, 1.0f);
+        const float a = (k & 1) ? cr : sr, b = (k & 1) ? sr : cr;
+        *s = (k & 2) ? -a : a;
+        *c = ((k + 1) & 2) ? -b : b;
+    }
+    template <bool FAST, typename real>
+    __device__ __forceinline__ real grbda_sin(real x) { real s, c; grbda_sincos<FAST>(x, &s, &c); return s; }
+    template <bool FAST, typename real>
+    __device__ __forceinline__ real grbda_cos(real x) { real s, c; grbda_sincos<FAST>(x, &s, &c); return c; }
+
+    // Scheduling pin. ptxas (and LLVM before it) may move any computation whose operands are ready as
+    // far up the straight-line program as it likes; it does so with the sin/cos evaluations (their
+    // operands are inputs), computing dozens of them at the top of the kernel and spilling the results
+    // until the joint is reached. pinAfter(x, late, zero) returns x, bit for bit, but through an integer
+    // operation on `late` (a value computed just before in program order) that the compiler cannot
+    // remove, because `zero` is only known to be 0 at run time: the evaluation stays where the
+    // depth-first program put it. One LOP3 per pinned value; NaN / inf in `late` do not propagate.
+    __device__ __forceinline__ double pinAfter(double x, double late, int zero)
+    {
+        return __hiloint2double(__double2hiint(x) ^ (__double2hiint(late) & zero), __double2loint(x));
+    }
+    __device__ __forceinline__ float pinAfter(float x, float late, int zero)
+    {
+        return __int_as_float(__float_as_int(x) ^ (__float_as_int(late) & zero));
+    }
+    // |x| as an ordered unsigned key (IEEE: the magnitude order of finite values is the integer order of
+    // their high words); NaN and inf give the largest keys. Used by the generated range checks.
+    __device__ __forceinline__ unsigned absKey(double x) { return (unsigned)__double2hiint(x) & 0x7fffffffu; }
+    __device__ __forceinline__ unsigned absKey(float x) { return __float_as_uint(x) & 0x7fffffffu; }
+
+#ifdef GRBDA_NO_RANGE_CHECK /* experiment switch: fast forms unconditionally */
+#define GRBDA_RANGE_CHECKED(Body) false
+#else
+#define GRBDA_RANGE_CHECKED(Body) Body::RANGE_CHECKED
+#endif
+    // Division of the generated bodies. FP64 keeps the IEEE division: measured on B200, the bodies are
+    // FASTER with it than with the branch-free grbda_div below (forward dynamics 0.93-1.16 ms against
+    // 1.46-2.4 ms per 2^20 Tello states) - the slow-path call sites of the 26 divisions cut the body
+    // into pieces at the pivots of the factorisation, which keeps ptxas from hoisting work (and its
+    // live values) across them. FP32 bodies are faster with the branch-free form.
+    // (GRBDA_EXTRA_NVCCFLAGS=-DGRBDA_FAST_DIV / -DGRBDA_NO_PIN: experiment switches of build.py)
+#ifdef GRBDA_FAST_DIV
+#define GRBDA_DIV(a, b) grbda_div(a, b)
+#else
+#define GRBDA_DIV(a, b) grbda_div_default(a, b)
+#endif
+#ifdef GRBDA_NO_PIN
+#define GRBDA_PIN_IMPL(x, late, zero) (x)
+#else
+#define GRBDA_PIN_IMPL(x, late, zero) pinAfter(x, late, zero)
+#endif
+
+    // a / b without the slow-path call of the IEEE division: hardware reciprocal seed (MUFU.RCP64H, about
+    // 20 good bits), two Newton steps, one residual correction of the quotient. Error <= ~1 ulp for
+    // normal operands (the divisors are pivots of positive definite blocks and constraint Jacobians);
+    // zero / infinite / denormal divisors give inf or nan like the division would, without trapping.
+    __device__ __forceinline__ double grbda_div(double a, double b)
+    {
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+        double e = fma(-b, r, 1.0);
+        r = fma(r, e, r);
+        e = fma(-b, r, 1.0);
+        r = fma(r, e, r);
+        const double q = a * r;
+        return fma(fma(-b, q, a), r, q);
+    }
+    __device__ __forceinline__ double grbda_div_default(double a, double b) { return a / b; }
+    __device__ __forceinline__ float grbda_div(float a, float b);
+    __device__ __forceinline__ float grbda_div_default(float a, float b) { return grbda_div(a, b); }
+    __device__ __forceinline__ float grbda_div(float a, float b)
+    {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+        r = fmaf(r, fmaf(-b, r, 1.0f), r);
+        const float q = a * r;
+        return fmaf(fmaf(-b, q, a), r, q);
+    }
 
     // Row stride (in elements) of a staged tile: odd, so that thread t reading element i of its
     // own state (address t * stride + i) hits 32 distinct banks for 4-byte and 16 distinct bank
@@ -168,6 +287,7 @@ namespace grbda_kernels
         real *warp;   // the warp's staging buffer
         real *g[3];   // output rows of the warp's first state
         int valid;    // number of states of this warp that exist (tail of the batch)
+        int zero;     // 0 at run time, unknown at compile time (see pinAfter)
     };
     template <typename real, int N, int COUNT>
     __device__ __forceinline__ void flushChunk(real *__restrict__ g, int base, const real *__restrict__ stg, int valid)
@@ -195,9 +315,10 @@ namespace grbda_kernels
     }
     template <typename Body, typename real>
     __device__ __forceinline__ OutStage<real> makeOutStage(unsigned char *stage_base, real *out0, real *out1,
-                                                           real *out2, int64_t first, int rows)
+                                                           real *out2, int64_t first, int rows, int64_t batch)
     {
         OutStage<real> o;
+        o.zero = (int)((uint64_t)batch >> 62); // batch < 2^62: always 0, but the compiler cannot know
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         real *buf = reinterpret_cast<real *>(stage_base) + (size_t)warp * 32 * (OUT_CHUNK + 1);
         o.warp = buf;
@@ -234,63 +355,141 @@ namespace grbda_kernels
     // STAGED = true : inN address the thread's own row of the staged shared-memory tiles and out0
     //                 the thread's row of the staged output tile (small outputs);
     // STAGED = false: inN / outN address global memory directly (x + state * n).
-    template <typename real, typename Body, int BLOCK, int MIN_BLOCKS, bool STAGED>
+    template <typename real, typename Body, int BLOCK, int MIN_BLOCKS, bool STAGED, bool FAST>
     __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
         grbda_batched_kernel(const real *__restrict__ in0, const real *__restrict__ in1,
                              const real *__restrict__ in2, real *__restrict__ out0,
-                             real *__restrict__ out1, real *__restrict__ out2, int64_t batch)
+                             real *__restrict__ out1, real *__restrict__ out2, int64_t batch,
+                             unsigned char *__restrict__ flags)
     {
         using L = TileLayout<Body, real, BLOCK>;
-        const int64_t first = (int64_t)blockIdx.x * BLOCK;
-        const int64_t remaining = batch - first;
-        const int rows = remaining < BLOCK ? (int)remaining : BLOCK;
-        // Every thread runs the body (it contains CTA-wide alignment barriers); threads past the end of
-        // the batch recompute the last valid state, so their duplicate stores are benign.
-        const int t = min((int)threadIdx.x, rows - 1);
-        const int64_t state = first + t;
-
         extern __shared__ __align__(16) unsigned char smem_raw[];
-        if constexpr (STAGED)
+        const int64_t num_tiles = (batch + BLOCK - 1) / BLOCK;
+        // FAST: one tile per CTA (grid = number of tiles). !FAST: a few CTAs scan the flags the FAST
+        // kernel left and recompute the flagged tiles with the library forms.
+        // FAST: tile = blockIdx.x. !FAST: CTA b owns tiles [b * BLOCK, (b + 1) * BLOCK); its threads read
+        // one flag each, and the CTA leaves at once when none is set (the normal case).
+        int64_t tile = FAST ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * BLOCK;
+        int64_t tile_end = tile + 1;
+        if (!FAST)
         {
-            real *smem = reinterpret_cast<real *>(smem_raw);
-            const OutStage<real> stage = makeOutStage<Body, real>(smem_raw + L::TILE_BYTES, out0, out1, out2, first, rows);
-            if (Body::N_IN0)
-                stage_in<real, Body::N_IN0 ? Body::N_IN0 : 1, BLOCK>(in0 + first * Body::N_IN0, smem, rows);
-            if (Body::N_IN1)
-                stage_in<real, Body::N_IN1 ? Body::N_IN1 : 1, BLOCK>(in1 + first * Body::N_IN1,
-                                                                    smem + L::OFF1, rows);
-            if (Body::N_IN2)
-                stage_in<real, Body::N_IN2 ? Body::N_IN2 : 1, BLOCK>(in2 + first * Body::N_IN2,
-                                                                    smem + L::OFF2, rows);
-            __syncthreads();
+            tile_end = min(num_tiles, tile + BLOCK);
+            const int64_t mine = tile + threadIdx.x;
+            if (!__syncthreads_or(mine < num_tiles && flags[mine]))
+                return;
+        }
+        do
+        {
+            if (!FAST && !flags[tile])
             {
-                real *o0 = L::STAGE_OUT0 ? smem + L::OFFO + t * L::SO : out0 + state * Body::N_OUT0;
-                real *o1 = Body::N_OUT1 ? out1 + state * Body::N_OUT1 : nullptr;
-                real *o2 = Body::N_OUT2 ? out2 + state * Body::N_OUT2 : nullptr;
-                Body::template run<real>(smem + t * L::S0, smem + L::OFF1 + t * L::S1,
-                                         smem + L::OFF2 + t * L::S2, o0, o1, o2, stage);
+                tile++;
+                continue;
             }
-            if (L::STAGE_OUT0)
+            const int64_t first = tile * BLOCK;
+            const int64_t remaining = batch - first;
+            const int rows = remaining < BLOCK ? (int)remaining : BLOCK;
+            // Every thread runs the body (it may contain CTA-wide alignment barriers); threads past the end
+            // of the batch recompute the last valid state, so their duplicate stores are benign.
+            const int t = min((int)threadIdx.x, rows - 1);
+            const int64_t state = first + t;
+
+            if constexpr (STAGED)
             {
+                real *smem = reinterpret_cast<real *>(smem_raw);
+                const OutStage<real> stage = makeOutStage<Body, real>(smem_raw + L::TILE_BYTES, out0, out1, out2, first, rows, batch);
+                if (Body::N_IN0)
+                    stage_in<real, Body::N_IN0 ? Body::N_IN0 : 1, BLOCK>(in0 + first * Body::N_IN0, smem, rows);
+                if (Body::N_IN1)
+                    stage_in<real, Body::N_IN1 ? Body::N_IN1 : 1, BLOCK>(in1 + first * Body::N_IN1,
+                                                                        smem + L::OFF1, rows);
+                if (Body::N_IN2)
+                    stage_in<real, Body::N_IN2 ? Body::N_IN2 : 1, BLOCK>(in2 + first * Body::N_IN2,
+                                                                        smem + L::OFF2, rows);
                 __syncthreads();
-                stage_out<real, Body::N_OUT0 ? Body::N_OUT0 : 1, BLOCK>(out0 + first * Body::N_OUT0,
-                                                                       smem + L::OFFO, rows);
+                const real *i0 = smem + t * L::S0, *i1 = smem + L::OFF1 + t * L::S1, *i2 = smem + L::OFF2 + t * L::S2;
+                bool ok = true;
+                if (FAST && GRBDA_RANGE_CHECKED(Body))
+                {
+                    ok = __syncthreads_and(Body::template inRange<real>(i0, i1, i2));
+                    if (threadIdx.x == 0)
+                        flags[tile] = ok ? 0 : 1;
+                }
+                if (ok)
+                {
+                    real *o0 = L::STAGE_OUT0 ? smem + L::OFFO + t * L::SO : out0 + state * Body::N_OUT0;
+                    real *o1 = Body::N_OUT1 ? out1 + state * Body::N_OUT1 : nullptr;
+                    real *o2 = Body::N_OUT2 ? out2 + state * Body::N_OUT2 : nullptr;
+                    Body::template run<real, FAST>(i0, i1, i2, o0, o1, o2, stage);
+                    if (L::STAGE_OUT0)
+                    {
+                        __syncthreads();
+                        stage_out<real, Body::N_OUT0 ? Body::N_OUT0 : 1, BLOCK>(out0 + first * Body::N_OUT0,
+                                                                               smem + L::OFFO, rows);
+                    }
+                }
             }
-        }
-        else
+            else
+            {
+                const OutStage<real> stage = makeOutStage<Body, real>(smem_raw, out0, out1, out2, first, rows, batch);
+                const real *i0 = in0 + state * Body::N_IN0, *i1 = in1 + state * Body::N_IN1, *i2 = in2 + state * Body::N_IN2;
+                bool ok = true;
+                if (FAST && GRBDA_RANGE_CHECKED(Body))
+                {
+                    ok = __syncthreads_and(Body::template inRange<real>(i0, i1, i2));
+                    if (threadIdx.x == 0)
+                        flags[tile] = ok ? 0 : 1;
+                }
+                if (ok)
+                    Body::template run<real, FAST>(i0, i1, i2, out0 + state * Body::N_OUT0,
+                                                   out1 + state * Body::N_OUT1, out2 + state * Body::N_OUT2, stage);
+            }
+            if (!FAST)
+                __syncthreads(); // the shared-memory tiles are reused by the next flagged tile
+            tile++;
+        } while (!FAST && tile < tile_end);
+    }
+
+    template <typename Body>
+    cudaError_t acquireFlags(const LaunchArgs &a, int64_t tiles, unsigned char **flags)
+    {
+        *flags = nullptr;
+        if (!GRBDA_RANGE_CHECKED(Body))
+            return cudaSuccess;
+        if (!a.flags || a.flags_bytes < (size_t)tiles)
+            return cudaErrorInvalidValue;
+        *flags = a.flags;
+        return cudaSuccess;
+    }
+
+    // second pass: tiles the FAST kernel flagged (a joint angle beyond the range of the fast sin/cos
+    // reduction) are recomputed with the library forms by the software-staged shell
+    template <typename real, typename Body, int BLOCK, int MIN_BLOCKS>
+    cudaError_t launchSlowPass(const LaunchArgs &a, int64_t tiles, unsigned char *flags)
+    {
+        if (!GRBDA_RANGE_CHECKED(Body))
+            return cudaSuccess;
+        using L = TileLayout<Body, real, BLOCK>;
+        auto kernel = grbda_batched_kernel<real, Body, BLOCK, MIN_BLOCKS, true, false>;
+        if (L::BYTES > 48 * 1024)
         {
-            const OutStage<real> stage = makeOutStage<Body, real>(smem_raw, out0, out1, out2, first, rows);
-            Body::template run<real>(in0 + state * Body::N_IN0, in1 + state * Body::N_IN1,
-                                     in2 + state * Body::N_IN2, out0 + state * Body::N_OUT0,
-                                     out1 + state * Body::N_OUT1, out2 + state * Body::N_OUT2, stage);
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES);
+            if (e != cudaSuccess)
+                return e;
         }
+        const int64_t grid = (tiles + BLOCK - 1) / BLOCK;
+        kernel<<<(unsigned)grid, BLOCK, L::BYTES, a.stream>>>(
+            (const real *)a.in[0], (const real *)a.in[1], (const real *)a.in[2], (real *)a.out[0],
+            (real *)a.out[1], (real *)a.out[2], a.batch, flags);
+        if (a.launched)
+            ++*a.launched;
+        return cudaGetLastError();
     }
 
     template <typename real, typename Body, int BLOCK, int MIN_BLOCKS, bool STAGED>
     cudaError_t launchBatched(const LaunchArgs &a)
     {
         using L = TileLayout<Body, real, BLOCK>;
-        auto kernel = grbda_batched_kernel<real, Body, BLOCK, MIN_BLOCKS, STAGED>;
+        auto kernel = grbda_batched_kernel<real, Body, BLOCK, MIN_BLOCKS, STAGED, true>;
         const size_t smem = STAGED ? L::BYTES : stageBytes<Body, real, BLOCK>();
         if (smem > 48 * 1024)
         {
@@ -301,10 +500,18 @@ namespace grbda_kernels
         if (a.batch <= 0)
             return cudaSuccess;
         const int64_t grid = (a.batch + BLOCK - 1) / BLOCK;
+        unsigned char *flags = nullptr;
+        cudaError_t e = acquireFlags<Body>(a, grid, &flags);
+        if (e != cudaSuccess)
+            return e;
         kernel<<<(unsigned)grid, BLOCK, smem, a.stream>>>(
             (const real *)a.in[0], (const real *)a.in[1], (const real *)a.in[2], (real *)a.out[0],
-            (real *)a.out[1], (real *)a.out[2], a.batch);
-        return cudaGetLastError();
+            (real *)a.out[1], (real *)a.out[2], a.batch, flags);
+        e = cudaGetLastError();
+        if (a.launched)
+            ++*a.launched;
+        const cudaError_t e2 = launchSlowPass<real, Body, BLOCK, MIN_BLOCKS>(a, grid, flags);
+        return e != cudaSuccess ? e : e2;
     }
 
     // ---------------------------------------------------------------------------------------------
@@ -415,7 +622,8 @@ namespace grbda_kernels
     __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
         grbda_batched_kernel_tma(const real *__restrict__ in0, const real *__restrict__ in1,
                                  const real *__restrict__ in2, real *__restrict__ out0,
-                                 real *__restrict__ out1, real *__restrict__ out2, int64_t batch)
+                                 real *__restrict__ out1, real *__restrict__ out2, int64_t batch,
+                                 unsigned char *__restrict__ flags)
     {
         using L = TmaLayout<Body, real, BLOCK>;
         extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -450,8 +658,17 @@ namespace grbda_kernels
         real *o0 = L::STAGE_OUT0 ? so + t * L::SO : out0 + state * Body::N_OUT0;
         real *o1 = Body::N_OUT1 ? out1 + state * Body::N_OUT1 : nullptr;
         real *o2 = Body::N_OUT2 ? out2 + state * Body::N_OUT2 : nullptr;
-        const OutStage<real> stage = makeOutStage<Body, real>(smem_raw + L::TILE_BYTES, out0, out1, out2, first, rows);
-        Body::template run<real>(s0 + t * L::S0, s1 + t * L::S1, s2 + t * L::S2, o0, o1, o2, stage);
+        const OutStage<real> stage = makeOutStage<Body, real>(smem_raw + L::TILE_BYTES, out0, out1, out2, first, rows, batch);
+        const real *i0 = s0 + t * L::S0, *i1 = s1 + t * L::S1, *i2 = s2 + t * L::S2;
+        if (GRBDA_RANGE_CHECKED(Body))
+        {
+            const bool ok = __syncthreads_and(Body::template inRange<real>(i0, i1, i2));
+            if (tid == 0)
+                flags[blockIdx.x] = ok ? 0 : 1;
+            if (!ok)
+                return; // CTA-uniform: the second pass recomputes this tile
+        }
+        Body::template run<real, true>(i0, i1, i2, o0, o1, o2, stage);
 
         if (L::STAGE_OUT0)
         {
@@ -500,10 +717,18 @@ namespace grbda_kernels
         if (a.batch <= 0)
             return cudaSuccess;
         const int64_t grid = (a.batch + BLOCK - 1) / BLOCK;
+        unsigned char *flags = nullptr;
+        cudaError_t e = acquireFlags<Body>(a, grid, &flags);
+        if (e != cudaSuccess)
+            return e;
         kernel<<<(unsigned)grid, BLOCK, L::BYTES, a.stream>>>(
             (const real *)a.in[0], (const real *)a.in[1], (const real *)a.in[2], (real *)a.out[0],
-            (real *)a.out[1], (real *)a.out[2], a.batch);
-        return cudaGetLastError();
+            (real *)a.out[1], (real *)a.out[2], a.batch, flags);
+        e = cudaGetLastError();
+        if (a.launched)
+            ++*a.launched;
+        const cudaError_t e2 = launchSlowPass<real, Body, BLOCK, MIN_BLOCKS>(a, grid, flags);
+        return e != cudaSuccess ? e : e2;
     }
 
     // ---------------------------------------------------------------------------------------------

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include "../../../include/grbda_cuda.h"
@@ -31,6 +32,35 @@ struct grbda_model
     cudaStream_t streams[NSTREAM] = {nullptr, nullptr, nullptr};
     double *dev_buf[NSTREAM] = {nullptr, nullptr, nullptr};
     int64_t dev_capacity = 0; // states per stream buffer
+    // per-stream scratch of the kernels (tile flags of the sin/cos range decision). Launches on one
+    // stream are ordered, so they can share a buffer; different streams get different buffers.
+    struct Scratch
+    {
+        unsigned char *ptr = nullptr;
+        size_t bytes = 0;
+    };
+    mutable std::mutex scratch_mutex;
+    mutable std::map<cudaStream_t, Scratch> scratch;
+    unsigned char *scratchFor(cudaStream_t stream, size_t bytes) const
+    {
+        std::lock_guard<std::mutex> lock(scratch_mutex);
+        Scratch &sc = scratch[stream];
+        if (sc.bytes < bytes)
+        {
+            if (sc.ptr)
+            {
+                cudaStreamSynchronize(stream); // earlier launches on this stream may still use it
+                cudaFree(sc.ptr);
+            }
+            sc.ptr = nullptr;
+            sc.bytes = 0;
+            const size_t want = std::max<size_t>(bytes * 2, 1 << 16);
+            if (cudaMalloc((void **)&sc.ptr, want) != cudaSuccess)
+                return nullptr;
+            sc.bytes = want;
+        }
+        return sc.ptr;
+    }
 };
 
 namespace
@@ -149,10 +179,16 @@ namespace
         }
         a.batch = batch;
         a.stream = (cudaStream_t)stream;
+        a.flags_bytes = (size_t)((batch + 31) / 32);
+        a.flags = m->scratchFor(a.stream, a.flags_bytes);
+        if (!a.flags)
+            return fail(GRBDA_ERR_CUDA, "cannot allocate the kernel scratch buffer");
+        int launched = 0;
+        a.launched = &launched;
         cudaError_t e = fn(a);
         if (e != cudaSuccess)
             return cudaFail(e, "kernel launch");
-        g_launches++;
+        g_launches += launched ? launched : 1;
         return GRBDA_OK;
     }
 } // namespace
@@ -191,6 +227,9 @@ extern "C"
             if (m->streams[i])
                 cudaStreamDestroy(m->streams[i]);
         }
+        for (auto &kv : m->scratch)
+            if (kv.second.ptr)
+                cudaFree(kv.second.ptr);
         delete m;
         return GRBDA_OK;
     }

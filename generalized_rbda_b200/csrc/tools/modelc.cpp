@@ -55,20 +55,25 @@ namespace
            << ", N_IN2 = " << c.n_in[2] << ";\n";
         os << "    static constexpr int N_OUT0 = " << c.n_out[0] << ", N_OUT1 = " << c.n_out[1]
            << ", N_OUT2 = " << c.n_out[2] << ";\n";
-        os << "    template <typename real>\n";
+        os << "    static constexpr bool RANGE_CHECKED = " << (c.range_check == "true" ? "false" : "true") << ";\n";
+        os << "    template <typename real>\n    static __device__ __forceinline__ bool inRange(const real "
+              "*__restrict__ in0, const real *__restrict__ in1,\n        const real *__restrict__ in2)\n    {\n"
+              "#define KC(x) ((real)(x))\n#define IN0(i) in0[i]\n#define IN1(i) in1[i]\n#define IN2(i) in2[i]\n"
+              "        return " << c.range_check << ";\n#undef KC\n#undef IN0\n#undef IN1\n#undef IN2\n    }\n";
+        os << "    template <typename real, bool FAST>\n";
         os << "    static __device__ __forceinline__ void run(const real *__restrict__ in0, const real "
               "*__restrict__ in1,\n"
               "        const real *__restrict__ in2, real *__restrict__ out0, real *__restrict__ out1, "
               "real *__restrict__ out2,\n        const OutStage<real> &stage)\n    {\n";
         os << "#define KC(x) ((real)(x))\n#define KT(i) kc_table<real>(i)\n#define IN0(i) in0[i]\n#define IN1(i) in1[i]\n#define IN2(i) in2[i]\n"
               "#define OUT0(i, x) out0[i] = (x)\n#define OUT1(i, x) out1[i] = (x)\n#define OUT2(i, x) out2[i] = (x)\n"
-              "#define GRBDA_ALIGN() __syncthreads()\n"
+              "#define GRBDA_ALIGN() __syncwarp()\n#define GRBDA_PIN(x, late) GRBDA_PIN_IMPL(x, late, stage.zero)\n"
               "#define STG_PUT(j, x) stage.lane[j] = (x)\n"
               "#define STG_FLUSH0(base, count) flushChunk<real, N_OUT0, count>(stage.g[0], base, stage.warp, stage.valid)\n"
               "#define STG_FLUSH1(base, count) flushChunk<real, N_OUT1, count>(stage.g[1], base, stage.warp, stage.valid)\n"
               "#define STG_FLUSH2(base, count) flushChunk<real, N_OUT2, count>(stage.g[2], base, stage.warp, stage.valid)\n";
         os << c.body;
-        os << "#undef KC\n#undef KT\n#undef IN0\n#undef IN1\n#undef IN2\n#undef OUT0\n#undef OUT1\n#undef OUT2\n#undef GRBDA_ALIGN\n#undef STG_PUT\n#undef STG_FLUSH0\n#undef STG_FLUSH1\n#undef STG_FLUSH2\n";
+        os << "#undef KC\n#undef KT\n#undef IN0\n#undef IN1\n#undef IN2\n#undef OUT0\n#undef OUT1\n#undef OUT2\n#undef GRBDA_ALIGN\n#undef GRBDA_PIN\n#undef STG_PUT\n#undef STG_FLUSH0\n#undef STG_FLUSH1\n#undef STG_FLUSH2\n";
         os << "    }\n};\n";
     }
 
@@ -344,11 +349,11 @@ int main(int argc, char **argv)
                     os << dep[i] << (i + 1 < dep.size() ? ", " : "");
                 os << "}; return t[i]; }\n";
                 os << "    static __device__ __noinline__ void eval(const double *q, double *phi, double *Kd)\n    {\n"
-                      "        typedef double real;\n"
-                      "#define KC(x) ((real)(x))\n#define IN0(i) q[i]\n#define OUT0(i, x) phi[i] = (x)\n"
+                      "        typedef double real;\n        constexpr bool FAST = false;\n"
+                      "#define KC(x) ((real)(x))\n#define GRBDA_PIN(x, late) (x)\n#define GRBDA_DIV(a, b) ((a) / (b))\n#define IN0(i) q[i]\n#define OUT0(i, x) phi[i] = (x)\n"
                       "#define OUT1(i, x) Kd[i] = (x)\n";
                 os << em.cudaBody();
-                os << "#undef KC\n#undef KT\n#undef IN0\n#undef OUT0\n#undef OUT1\n    }\n};\n\n";
+                os << "#undef KC\n#undef KT\n#undef GRBDA_PIN\n#undef GRBDA_DIV\n#undef IN0\n#undef OUT0\n#undef OUT1\n    }\n};\n\n";
             }
             os << "struct Gen\n{\n    static constexpr int NQ = " << nq << ", NV = " << nv << ";\n";
             os << "    static __device__ bool run(Philox &rng, double *q, double *yd, double *aux)\n    {\n"

@@ -105,6 +105,45 @@ def test_every_compiled_kernel_variant(grbda, oracle, torch, robot, monkeypatch)
     assert ran >= 2
 
 
+@pytest.mark.parametrize("dtype_name", ["float64", "float32"])
+def test_angles_beyond_the_fast_sincos_range(grbda, oracle, torch, dtype_name):
+    """Joint angles beyond the range of the branch-free sin/cos reduction (arguments up to 1e12 in FP64, 1e6 in FP32):
+    the fast kernel flags the 128-state tile, the second pass recomputes it with the library forms.
+    Tiles 0 and 2 of a 3.x-tile batch are flagged, tile 1 and the ragged tail stay on the fast path."""
+    m = grbda.ClusterTreeModel.from_robot("tello_with_arms")
+    o = oracle.OracleModel("tello_with_arms")
+    dtype = getattr(torch, dtype_name)
+    B = 3 * 128 + 40
+    q, yd, aux, _ = m.generateStates(B, seed=5)
+    q = q.clone()
+    turns = 4.0e11 if dtype_name == "float64" else 4.0e5       # whole turns: 2.5e12 rad / 2.5e6 rad
+    hip_clamp = m.clusters()[1]["position_index"]
+    arm = m.clusters()[7]["position_index"]
+    q[5, hip_clamp] += 2.0 * np.pi * turns
+    q[300, arm] -= 2.0 * np.pi * turns
+    # large but inside the fast range (tile 1 stays on the fast path): the FMA reduction must hold up
+    q[200, hip_clamp] += 2.0 * np.pi * (1.0e8 if dtype_name == "float64" else 1.0e3)
+    q, yd, aux = q.to(dtype), yd.to(dtype), aux.to(dtype)
+    qn, ydn, auxn = (x.double().cpu().numpy() for x in (q, yd, aux))
+    tol = TOL64 if dtype_name == "float64" else TOL32
+    before = grbda.launch_count()
+    tau = m.inverseDynamics(q, yd, aux)
+    assert grbda.launch_count() - before == 2       # fast kernel + flagged-tile pass
+    assert relrows(tau.double().cpu().numpy(), o.inverse_dynamics(qn, ydn, auxn)) < tol
+    assert relrows(m.getMassMatrix(q).double().cpu().numpy(), o.mass_matrix(qn)) < tol
+    if dtype_name == "float64":
+        # (FP32 angles of this size carry ~0.1 rad of rounding in the rotor angle 6 q: FK and FD are FP64-only here)
+        p, R, v = m.forwardKinematics(q, yd)
+        po, Ro, vo = o.forward_kinematics(qn, ydn)
+        assert rel(R.cpu().numpy(), Ro) < tol and rel(v.cpu().numpy(), vo) < tol
+        assert relrows(m.forwardDynamics(q, yd, aux).cpu().numpy(), o.forward_dynamics(qn, ydn, auxn)) < tol
+    # NaN / inf positions: flagged like any other out-of-range value, results are NaN for that state only
+    q2 = q.clone()
+    q2[130, hip_clamp] = float("nan")
+    tau2 = m.inverseDynamics(q2, yd, aux)
+    assert torch.isnan(tau2[130]).any() and not torch.isnan(tau2[131]).any() and not torch.isnan(tau2[0]).any()
+
+
 @pytest.mark.parametrize("robot", ["tello_with_arms", "mini_cheetah", "mit_humanoid", "revolute_chain_with_rotor_2"])
 def test_dynamics_parity_f32(grbda, oracle, torch, robot):
     """FP32 variant against the FP64 oracle on float-rounded states."""

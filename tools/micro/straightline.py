@@ -9,11 +9,12 @@ import ctypes
 
 N_LIST = [4000, 16000]
 MIX = int(os.environ.get("MIX", "0"))
+CHAINS = int(os.environ.get("CHAINS", "8"))  # independent dependency chains per thread (ILP)
 src = ['#include <cuda_runtime.h>\n#include <cstdio>\n']
 for n in N_LIST:
     body = []
     for i in range(n):
-        k = i % 8
+        k = i % CHAINS
         body.append(f"x{k} = fma(x{k}, a, b);")
         if MIX:
             body.append(f"j{k} = j{k} * 3 + {i};")  # one integer IMAD per DFMA
@@ -64,4 +65,4 @@ for n in N_LIST:
         ms = lib.run(which, n, grid)
         warps = grid * 4
         ipc = n * warps / (ms * 1e-3 * 1.965e9 * 148 * 4)
-        print(f"MIX={MIX} {name:9s} n={n:6d}  {ms:8.3f} ms   DFMA per SMSP-cycle = {ipc:.3f}  total instr per SMSP-cycle = {ipc*(1+MIX):.3f}  ({2*n*grid*128/ms/1e9:.1f} TFLOP/s)")
+        print(f"MIX={MIX} CHAINS={CHAINS if which == 0 else 8} {name:9s} n={n:6d}  {ms:8.3f} ms   DFMA per SMSP-cycle = {ipc:.3f}  total instr per SMSP-cycle = {ipc*(1+MIX):.3f}  ({2*n*grid*128/ms/1e9:.1f} TFLOP/s)")
