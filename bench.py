@@ -117,10 +117,45 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d states x %d steps" % (n, args.steps)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def ncu_traffic(kernel, states):
+    """DRAM bytes of one launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu
+    --set full capture of this round, scaled to `states`; None when no capture is on file."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_roofline_traffic.json")
+    try:
+        rec = json.load(open(path))[kernel]
+        return rec["dram_bytes_per_launch"] * states / rec["states"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+_RESULT_FD = None
+
+
+def _stdout_for_the_result_only():
+    """Libraries write to stdout (NCCL prints its version banner there). The contract is ONE JSON line on
+    stdout, so everything else is sent to stderr: fd 1 is pointed at fd 2 and the JSON line is written to a
+    saved copy of the real stdout by emit()."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    text = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(text.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, text)
 
 
 def main():
+    _stdout_for_the_result_only()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -279,7 +314,7 @@ def main():
                            "MEASURED_PEAKS.json has no FP64 entry",
             "flops_per_state_alg": f_alg_fd, "flops_per_state_executed": fd_prog["flops"],
             "achieved_executed": fd_prog["flops"] * B / t_fd / 1e12,
-            "kernel_ms": t_fd * 1e3, "traffic": None,
+            "kernel_ms": t_fd * 1e3, "traffic": ncu_traffic("forward_dynamics", B),
             "hbm": {"achieved": alg_bytes * B / t_fd / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": alg_bytes * B / t_fd / 1e9 / peaks["hbm_gbs"], "peak_source": peaks_kind,
                     "bytes_per_state": alg_bytes},
@@ -293,7 +328,7 @@ def main():
             "forward_kinematics": {"states": Bk, "kernel_ms": t_fk * 1e3,
                                    "bytes_per_state": 8 * (m.nq + m.nv + 18 * m.nb),
                                    "hbm_frac": 8 * (m.nq + m.nv + 18 * m.nb) * Bk / t_fk / 1e9 / peaks["hbm_gbs"]}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

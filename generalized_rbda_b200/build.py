@@ -28,10 +28,10 @@ LIB = os.path.join(HERE, "libgrbda_cuda.so")
 # Measured on B200 (profiles/): ID and the kinematics kernels do not spill and are fastest with TMA
 # staging; FD spills ~2.5 KB per thread to local memory and needs the L1 capacity that the TMA tiles
 # would take, so it keeps the smaller software-staged tiles.
-DEFAULT_VARIANTS = "id=T,128,2;S,128,2|fd=S,128,2,ltl;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2"
+DEFAULT_VARIANTS = "id=T,128,2;S,128,2|fd=T,128,2,ltl;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2"
 SYNC_EVERY = int(os.environ.get("GRBDA_SYNC_EVERY", "0"))  # alignment barriers measured useless (profiles/)
 MODELS = {
-    "tello_with_arms": ("id,fd,fk,h,phi,gen", "id=T,128,2;S,128,2|fd=D,128,2,ltl;T,128,2,ltl;S,128,2,ltl;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2", True),
+    "tello_with_arms": ("id,fd,fk,h,phi,gen", "id=T,128,2;S,128,2|fd=T,128,2,ltl;D,128,2,ltl;S,128,2,ltl;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2", True),
     "tello": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
     "mini_cheetah": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
     "mit_humanoid": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
