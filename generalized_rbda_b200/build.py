@@ -25,9 +25,11 @@ LIB = os.path.join(HERE, "libgrbda_cuda.so")
 # KIND = T (TMA bulk-copy staged tiles), S (software-staged tiles), D (direct global access),
 # R (one limb per warp); up to four ';'-separated variants per kernel, the first is the default,
 # GRBDA_KERNEL_VARIANT selects another one at run time (tools/sweep_variants.py).
-# Measured on B200 (profiles/): ID and the kinematics kernels do not spill and are fastest with TMA
-# staging; FD spills ~2.5 KB per thread to local memory and needs the L1 capacity that the TMA tiles
-# would take, so it keeps the smaller software-staged tiles.
+# Kernel variants per entry point: KIND,BLOCK,MIN_BLOCKS[,SYNC][,ltl] separated by ';' (first = default,
+# GRBDA_KERNEL_VARIANT=k selects the k-th). KIND: T = TMA-staged tiles, S = software-staged tiles,
+# D = direct global I/O, R = one warp per limb. 'ltl' = forward dynamics as CRBA + bias + sparse LTDL
+# (otherwise the articulated-body sweep). Measured on B200 (profiles/README.md): T,128,2 is the fastest
+# and the most device-independent shape for every entry point.
 DEFAULT_VARIANTS = "id=T,128,2;S,128,2|fd=T,128,2,ltl;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2"
 SYNC_EVERY = int(os.environ.get("GRBDA_SYNC_EVERY", "0"))  # alignment barriers measured useless (profiles/)
 MODELS = {
@@ -36,6 +38,10 @@ MODELS = {
     "mini_cheetah": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
     "mit_humanoid": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
     "four_bar": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, True),
+    "six_bar": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
+    "planar_leg_linkage": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
+    "mit_humanoid_leg": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
+    "jvrc1_humanoid": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
     "revolute_rotor_chain": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, False),
     "revolute_chain_with_rotor_2": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_4": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, False),

@@ -289,19 +289,46 @@ namespace grbda_kernels
         int valid;    // number of states of this warp that exist (tail of the batch)
         int zero;     // 0 at run time, unknown at compile time (see pinAfter)
     };
-    template <typename real, int N, int COUNT>
-    __device__ __forceinline__ void flushChunk(real *__restrict__ g, int base, const real *__restrict__ stg, int valid)
+    // Flush of one staged chunk: 32 states x COUNT values, COUNT * sizeof(real) contiguous bytes per
+    // state. Deliberately NOT inlined: FK / H bodies flush 40-70 chunks, and the inlined copies made
+    // the kernels 15-19 k instructions long (3 k of them arithmetic) and instruction-fetch bound
+    // (ncu: no_instructions 39 %); one shared copy per kernel removes that.
+    template <typename real, int COUNT>
+    __device__ __noinline__ void flushChunkShared(real *__restrict__ g, int row_stride, const real *__restrict__ stg,
+                                                  int valid)
     {
         __syncwarp();
         const int lane = threadIdx.x & 31;
-#pragma unroll 4
-        for (int e = lane; e < 32 * COUNT; e += 32)
+        if (COUNT == OUT_CHUNK)
         {
-            const int st = e / COUNT, el = e - st * COUNT;
-            if (st < valid)
-                __stcs(g + (size_t)st * N + base + el, stg[st * (OUT_CHUNK + 1) + el]);
+            // full chunk: lane -> (state lane / 16 + 2 k, element lane % 16)
+            const int el = lane & (OUT_CHUNK - 1);
+            int st = lane / OUT_CHUNK;
+            const real *src = stg + st * (OUT_CHUNK + 1) + el;
+            real *dst = g + (size_t)st * row_stride + el;
+#pragma unroll 4
+            for (; st < valid; st += 32 / OUT_CHUNK)
+            {
+                __stcs(dst, *src);
+                src += (32 / OUT_CHUNK) * (OUT_CHUNK + 1);
+                dst += (size_t)(32 / OUT_CHUNK) * row_stride;
+            }
+        }
+        else
+        {
+            for (int e = lane; e < 32 * COUNT; e += 32)
+            {
+                const int st = e / COUNT, el = e - st * COUNT;
+                if (st < valid)
+                    __stcs(g + (size_t)st * row_stride + el, stg[st * (OUT_CHUNK + 1) + el]);
+            }
         }
         __syncwarp();
+    }
+    template <typename real, int N, int COUNT>
+    __device__ __forceinline__ void flushChunk(real *__restrict__ g, int base, const real *__restrict__ stg, int valid)
+    {
+        flushChunkShared<real, COUNT>(g + base, N, stg, valid);
     }
     template <typename Body>
     __host__ __device__ constexpr bool bodyChunked()
