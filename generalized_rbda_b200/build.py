@@ -28,12 +28,13 @@ LIB = os.path.join(HERE, "libgrbda_cuda.so")
 # Kernel variants per entry point: KIND,BLOCK,MIN_BLOCKS[,SYNC][,ltl] separated by ';' (first = default,
 # GRBDA_KERNEL_VARIANT=k selects the k-th). KIND: T = TMA-staged tiles, S = software-staged tiles,
 # D = direct global I/O, R = one warp per limb. 'ltl' = forward dynamics as CRBA + bias + sparse LTDL
-# (otherwise the articulated-body sweep). Measured on B200 (profiles/README.md): T,128,2 is the fastest
+# (otherwise the articulated-body sweep); 'park' = long-lived values parked in dead slots of the thread's
+# shared-memory tile row instead of being spilled (T and S only). Measured on B200 (profiles/README.md): T,128,2 is the fastest
 # and the most device-independent shape for every entry point.
-DEFAULT_VARIANTS = "id=T,128,2;S,128,2|fd=T,128,2,ltl;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2"
+DEFAULT_VARIANTS = "id=T,128,2;S,128,2|fd=T,128,2,ltl,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2"
 SYNC_EVERY = int(os.environ.get("GRBDA_SYNC_EVERY", "0"))  # alignment barriers measured useless (profiles/)
 MODELS = {
-    "tello_with_arms": ("id,fd,fk,h,phi,gen", "id=T,128,2;S,128,2|fd=T,128,2,ltl;D,128,2,ltl;S,128,2,ltl;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2", True),
+    "tello_with_arms": ("id,fd,fk,h,phi,gen", "id=T,128,2;S,128,2|fd=T,128,2,ltl,park;T,128,2,ltl;S,128,2,ltl,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2", True),
     "tello": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
     "mini_cheetah": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
     "mit_humanoid": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),

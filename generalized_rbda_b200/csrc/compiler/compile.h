@@ -36,6 +36,8 @@ namespace grbda
             int n_out[3] = {0, 0, 0};
             std::string body;
             std::string range_check; // expression: may the fast sin/cos forms be used for this state
+            bool parked = false;     // body parks long-lived values in the thread's shared-memory row
+            int num_parked = 0;
             ProgramStats stats;
             Tape tape;
         };
@@ -105,7 +107,8 @@ namespace grbda
         }
 
         inline CompiledAlgo compileAlgo(const ClusterTreeModel &model, int algo, bool want_body = true,
-                                        int sync_every = 0, ConstTable *consts = nullptr, int out_chunk = 0)
+                                        int sync_every = 0, ConstTable *consts = nullptr, int out_chunk = 0,
+                                        bool park = false)
         {
             sym::Graph graph;
             sym::GraphScope scope(graph);
@@ -121,7 +124,15 @@ namespace grbda
             out.tape = em.tape();
             if (want_body)
             {
-                out.body = em.cudaBody(sync_every, out_chunk);
+                ParkConfig pc;
+                for (int i = 0; i < 3; i++)
+                    pc.n_slots[i] = p.n_in[i];
+                pc.n_slots[3] = out.n_out[0] <= 64 ? out.n_out[0] : 0; // the shells stage output 0 when it is small
+                if (const char *gap = std::getenv("GRBDA_PARK_GAP")) // tuning experiments
+                    pc.min_gap = std::atoi(gap);
+                out.parked = park && sync_every == 0;
+                out.body = em.cudaBody(sync_every, out_chunk, out.parked ? &pc : nullptr);
+                out.num_parked = em.numParked();
                 out.range_check = em.cudaRangeCheck();
             }
             return out;

@@ -104,6 +104,22 @@ namespace grbda
             std::vector<std::vector<sym::Sym>> outputs; // up to 3 output arrays
         };
 
+        // Parking (staged shells only): a value that is produced long before its next use - the factor
+        // entries of the forward-dynamics factorisation wait for the final back-substitution - would be
+        // spilled to local memory by ptxas (through L1 into L2). The thread's own shared-memory row holds
+        // slots that are dead for most of the program: an input element after it has been read, an
+        // element of the staged output row until the result is stored. The emitter parks long-lived
+        // values there (PARK_ST / PARK_LD) instead.
+        struct ParkConfig
+        {
+            int n_slots[4] = {0, 0, 0, 0}; // usable elements of the in0 / in1 / in2 / out0 rows (0: row not staged)
+            // park only across gaps of at least this fraction of the program (in graph nodes). Measured on
+            // B200 (TelloWithArms forward dynamics, 8.9 k nodes): 0.09 -> 0.763 ms, 0.13 -> 0.770, 0.20 -> 0.741,
+            // 0.28 -> 0.729, 0.39 -> 0.766, 0.56 -> 0.782, 0.78 -> 0.841, no parking 0.986 ms
+            double min_gap_fraction = 0.28;
+            int min_gap = 0;               // absolute override (> 0)
+        };
+
         class Emitter
         {
         public:
@@ -114,6 +130,7 @@ namespace grbda
             }
 
             const ProgramStats &stats() const { return stats_; }
+            int numParked() const { return num_parked_; } // after cudaBody(..., park)
 
             Tape tape() const
             {
@@ -268,11 +285,13 @@ namespace grbda
             // `out_chunk` consecutive elements are held until the chunk is complete, written to the
             // warp's shared-memory staging buffer (STG_PUT) and flushed with coalesced stores
             // (STG_FLUSHk: 32 states x chunk, 128 contiguous bytes per state).
-            std::string cudaBody(int sync_every = 0, int out_chunk = 0) const
+            std::string cudaBody(int sync_every = 0, int out_chunk = 0, const ParkConfig *park = nullptr) const
             {
                 std::ostringstream os;
                 int since_sync = 0;
                 std::vector<char> done(g_.nodes.size(), 0);
+                alias_.assign(g_.nodes.size(), std::string());
+                num_parked_ = 0;
                 // node id -> list of (array, element) it must be stored to
                 std::vector<std::vector<std::pair<int, int>>> stores(g_.nodes.size());
                 for (size_t arr = 0; arr < p_.outputs.size(); arr++)
@@ -353,6 +372,120 @@ namespace grbda
                             neg_outputs_of[k].push_back(id);
                     }
 
+                // ---- parking plan (positions are node ids: statements are emitted in id order) ----
+                std::vector<std::vector<Parked>> park_store_after(g_.nodes.size()), park_load_before(g_.nodes.size());
+                bool any_chunked = false;
+                for (size_t arr = 0; arr < n_arr; arr++)
+                    any_chunked = any_chunked || chunked[arr];
+                if (park && !any_chunked)
+                {
+                    const int32_t N = (int32_t)g_.nodes.size();
+                    const int32_t min_gap = park->min_gap > 0 ? park->min_gap
+                                                              : std::max(200, (int)(park->min_gap_fraction * stats_.n_nodes));
+                    auto base = [&](int32_t id) {
+                        while (g_.nodes[id].op == sym::OP_NEG)
+                            id = g_.nodes[id].a;
+                        return id;
+                    };
+                    // accesses of every value: its definition and the statements that read it
+                    std::vector<std::vector<int32_t>> access(N);
+                    for (int32_t i = 0; i < N; i++)
+                    {
+                        if (!live_[i])
+                            continue;
+                        const sym::Node &n = g_.nodes[i];
+                        if (n.op == sym::OP_CONST || n.op == sym::OP_NEG || n.op == sym::OP_INPUT)
+                            continue;
+                        // a cosine emitted together with its sine is defined at the earlier of the two
+                        int32_t pos = i;
+                        if ((n.op == sym::OP_SIN || n.op == sym::OP_COS) && partner_[i] >= 0 && live_[partner_[i]])
+                            pos = std::min<int32_t>(i, partner_[i]);
+                        for (int32_t o : {n.a, n.b, n.c, n.e})
+                            if (o >= 0)
+                            {
+                                const int32_t x = base(o);
+                                if (g_.nodes[x].op != sym::OP_CONST && g_.nodes[x].op != sym::OP_INPUT)
+                                    access[x].push_back(pos);
+                            }
+                    }
+                    // slot availability: [free_from, free_until)
+                    std::vector<Slot> slots;
+                    for (int t = 0; t < 3; t++)
+                    {
+                        std::vector<int32_t> read_at(park->n_slots[t], -1);
+                        for (int32_t i = 0; i < N; i++)
+                            if (live_[i] && g_.nodes[i].op == sym::OP_INPUT && g_.nodes[i].a == t &&
+                                g_.nodes[i].b < park->n_slots[t])
+                                read_at[g_.nodes[i].b] = i;
+                        for (int k = 0; k < park->n_slots[t]; k++)
+                            slots.push_back(Slot{t, k, read_at[k] + 1, N, {}});
+                    }
+                    if (park->n_slots[3] > 0 && n_arr > 0)
+                        for (int k = 0; k < park->n_slots[3] && k < (int)p_.outputs[0].size(); k++)
+                        {
+                            const int32_t b = base(p_.outputs[0][k].id);
+                            if (g_.nodes[b].op == sym::OP_CONST || g_.nodes[b].op == sym::OP_INPUT)
+                                continue;
+                            slots.push_back(Slot{3, k, 0, b, {}});
+                        }
+                    // candidates: the longest gap between consecutive accesses of a value
+                    std::vector<Cand> cands;
+                    for (int32_t x = 0; x < N; x++)
+                    {
+                        if (!live_[x] || access[x].empty())
+                            continue;
+                        const sym::Node &n = g_.nodes[x];
+                        if (n.op == sym::OP_CONST || n.op == sym::OP_NEG || n.op == sym::OP_INPUT)
+                            continue;
+                        std::vector<int32_t> a = access[x];
+                        int32_t def = x;
+                        if ((n.op == sym::OP_SIN || n.op == sym::OP_COS) && partner_[x] >= 0 && live_[partner_[x]])
+                            def = std::min<int32_t>(x, partner_[x]);
+                        a.push_back(def);
+                        // an output store is an access at the definition (emitStores)
+                        std::sort(a.begin(), a.end());
+                        int32_t best = 0, from = -1, to = -1;
+                        for (size_t k = 0; k + 1 < a.size(); k++)
+                            if (a[k + 1] - a[k] > best)
+                                best = a[k + 1] - a[k], from = a[k], to = a[k + 1];
+                        if (best >= min_gap)
+                            cands.push_back(Cand{x, from, to});
+                    }
+                    std::sort(cands.begin(), cands.end(),
+                              [](const Cand &p, const Cand &q) { return (p.to - p.from) > (q.to - q.from); });
+                    for (const Cand &c : cands)
+                    {
+                        // the value is stored after statement `from` and reloaded before statement `to`
+                        for (Slot &sl : slots)
+                        {
+                            if (sl.free_from > c.from || sl.free_until <= c.to)
+                                continue;
+                            bool clash = false;
+                            for (auto &b : sl.busy)
+                                if (!(c.to <= b.first || b.second <= c.from))
+                                    clash = true;
+                            if (clash)
+                                continue;
+                            sl.busy.push_back({c.from, c.to});
+                            park_store_after[c.from].push_back(Parked{c.node, sl.tile, sl.index});
+                            park_load_before[c.to].push_back(Parked{c.node, sl.tile, sl.index});
+                            num_parked_++;
+                            break;
+                        }
+                    }
+                }
+                auto emitParkLoads = [&](size_t pos) {
+                    for (const Parked &pk : park_load_before[pos])
+                    {
+                        alias_[pk.node] = "t" + std::to_string(pk.node) + "p";
+                        os << "const real " << alias_[pk.node] << " = PARK_LD(" << pk.tile << ", " << pk.slot << ");\n";
+                    }
+                };
+                auto emitParkStores = [&](size_t pos) {
+                    for (const Parked &pk : park_store_after[pos])
+                        os << "PARK_ST(" << pk.tile << ", " << pk.slot << ", " << ref(pk.node) << ");\n";
+                };
+
                 // the two most recent arithmetic results: anchor of GRBDA_PIN (kernels: pinAfter) for the
                 // sin/cos evaluations, which would otherwise all be hoisted to the top of the program
                 int32_t last_temp[2] = {-1, -1};
@@ -386,8 +519,10 @@ namespace grbda
                         emitStores(i);
                         for (int32_t ng : neg_outputs_of[i])
                             emitStores(ng);
+                        emitParkStores(i);
                         continue;
                     }
+                    emitParkLoads(i);
                     switch (n.op)
                     {
                     case sym::OP_INPUT:
@@ -442,6 +577,7 @@ namespace grbda
                     emitStores(i);
                     for (int32_t ng : neg_outputs_of[i])
                         emitStores(ng);
+                    emitParkStores(i);
                     if (sync_every > 0 && ++since_sync >= sync_every)
                     {
                         os << "GRBDA_ALIGN();\n";
@@ -452,6 +588,20 @@ namespace grbda
             }
 
         private:
+            struct Parked
+            {
+                int32_t node, tile, slot;
+            };
+            struct Slot
+            {
+                int32_t tile, index, free_from, free_until;
+                std::vector<std::pair<int32_t, int32_t>> busy;
+            };
+            struct Cand
+            {
+                int32_t node, from, to;
+            };
+
             std::string ref(int32_t id) const
             {
                 const sym::Node &n = g_.nodes[id];
@@ -465,6 +615,8 @@ namespace grbda
                 }
                 if (n.op == sym::OP_NEG)
                     return "(-" + ref(n.a) + ")";
+                if ((size_t)id < alias_.size() && !alias_[id].empty())
+                    return alias_[id]; // reloaded from its parking slot
                 return "t" + std::to_string(id);
             }
 
@@ -548,6 +700,8 @@ namespace grbda
             const Program &p_;
             ConstTable *consts_;
             std::vector<char> live_;
+            mutable std::vector<std::string> alias_; // name of a value after it was reloaded from its parking slot
+            mutable int num_parked_ = 0;
             std::vector<int> uses_;
             std::vector<int32_t> partner_;
             ProgramStats stats_;

@@ -446,7 +446,8 @@ namespace grbda_kernels
                     real *o0 = L::STAGE_OUT0 ? smem + L::OFFO + t * L::SO : out0 + state * Body::N_OUT0;
                     real *o1 = Body::N_OUT1 ? out1 + state * Body::N_OUT1 : nullptr;
                     real *o2 = Body::N_OUT2 ? out2 + state * Body::N_OUT2 : nullptr;
-                    Body::template run<real, FAST>(i0, i1, i2, o0, o1, o2, stage);
+                    if (!Body::PARKED || (int)threadIdx.x < rows) // parked rows are private: no tail replicas
+                        Body::template run<real, FAST>(i0, i1, i2, o0, o1, o2, stage);
                     if (L::STAGE_OUT0)
                     {
                         __syncthreads();
@@ -695,7 +696,8 @@ namespace grbda_kernels
             if (!ok)
                 return; // CTA-uniform: the second pass recomputes this tile
         }
-        Body::template run<real, true>(i0, i1, i2, o0, o1, o2, stage);
+        if (!Body::PARKED || tid < rows) // parked rows are private: no tail replicas
+            Body::template run<real, true>(i0, i1, i2, o0, o1, o2, stage);
 
         if (L::STAGE_OUT0)
         {
