@@ -523,24 +523,39 @@ namespace grbda
             // ---------------------------------------------------------------------------------
             void forwardKinematics(std::vector<Sym> &p_out, std::vector<Sym> &R_out, std::vector<Sym> &v_out)
             {
-                kinematics(true, false);
+                // cluster by cluster, depth first: the absolute transform and the outputs of a body are
+                // formed right after its joint transform, so only the transforms along the current path
+                // are alive (forming all joint transforms first kept 37 x 18 values alive, i.e. in local
+                // memory, until the output loop reached them)
+                beginKinematics();
                 const int Nb = m_.getNumBodies();
                 std::vector<Xf> Xa(Nb);
-                for (int i = 0; i < Nb; i++)
-                {
-                    const int p = m_.bodies()[i].parent_index_;
-                    Xa[i] = p >= 0 ? bk_[i].Xl * Xa[p] : bk_[i].Xl;
-                    for (int k = 0; k < 3; k++)
-                        p_out.push_back(Xa[i].r[k]);
-                    for (int r = 0; r < 3; r++)
-                        for (int cc = 0; cc < 3; cc++)
-                            R_out.push_back(Xa[i].E(cc, r));
-                    const V3 w = mulT(Xa[i].E, bk_[i].v.ang()), vl = mulT(Xa[i].E, bk_[i].v.lin());
-                    for (int k = 0; k < 3; k++)
-                        v_out.push_back(w[k]);
-                    for (int k = 0; k < 3; k++)
-                        v_out.push_back(vl[k]);
-                }
+                p_out.assign(3 * Nb, Sym(0.0));
+                R_out.assign(9 * Nb, Sym(0.0));
+                v_out.assign(6 * Nb, Sym(0.0));
+                std::function<void(int)> visit = [&](int ci) {
+                    kinematicsCluster(ci, true, false);
+                    const ClusterTreeNode &c = m_.clusters()[ci];
+                    for (int i = c.first_body_; i < c.first_body_ + c.joint_.num_bodies; i++)
+                    {
+                        const int p = m_.bodies()[i].parent_index_;
+                        Xa[i] = p >= 0 ? bk_[i].Xl * Xa[p] : bk_[i].Xl;
+                        for (int k = 0; k < 3; k++)
+                            p_out[3 * i + k] = Xa[i].r[k];
+                        for (int r = 0; r < 3; r++)
+                            for (int cc = 0; cc < 3; cc++)
+                                R_out[9 * i + 3 * r + cc] = Xa[i].E(cc, r);
+                        const V3 w = mulT(Xa[i].E, bk_[i].v.ang()), vl = mulT(Xa[i].E, bk_[i].v.lin());
+                        for (int k = 0; k < 3; k++)
+                            v_out[6 * i + k] = w[k];
+                        for (int k = 0; k < 3; k++)
+                            v_out[6 * i + 3 + k] = vl[k];
+                    }
+                    for (int ch : children_[ci])
+                        visit(ch);
+                };
+                for (int r : roots_)
+                    visit(r);
             }
 
             // ---------------------------------------------------------------------------------

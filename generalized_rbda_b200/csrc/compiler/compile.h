@@ -38,6 +38,7 @@ namespace grbda
             std::string range_check; // expression: may the fast sin/cos forms be used for this state
             bool parked = false;     // body parks long-lived values in the thread's shared-memory row
             int num_parked = 0;
+            int stage_buffers = 1;   // chunked outputs: staging buffers per warp (1, or one per output array)
             ProgramStats stats;
             Tape tape;
         };
@@ -133,6 +134,7 @@ namespace grbda
                 out.parked = park && sync_every == 0;
                 out.body = em.cudaBody(sync_every, out_chunk, out.parked ? &pc : nullptr);
                 out.num_parked = em.numParked();
+                out.stage_buffers = em.stageBuffers();
                 out.range_check = em.cudaRangeCheck();
             }
             return out;

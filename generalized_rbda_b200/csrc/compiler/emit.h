@@ -130,7 +130,8 @@ namespace grbda
             }
 
             const ProgramStats &stats() const { return stats_; }
-            int numParked() const { return num_parked_; } // after cudaBody(..., park)
+            int numParked() const { return num_parked_; }       // after cudaBody(..., park)
+            int stageBuffers() const { return stage_buffers_; } // after cudaBody: staging buffers per warp
 
             Tape tape() const
             {
@@ -315,6 +316,54 @@ namespace grbda
                             chunk_missing[arr][i / out_chunk]++;
                     }
                 }
+                // Arrays whose elements become ready in ascending order (forward kinematics: body after body)
+                // get their own staging buffer and are drained sequentially: a value is written to the
+                // buffer (STG_PUTK) the moment it exists instead of being held in a register until its
+                // 16-value chunk is complete (three arrays x 16 held values were most of FK's spills).
+                std::vector<char> immediate(n_arr, 0);
+                std::vector<int> drain_next(n_arr, 0);
+                {
+                    auto basePos = [&](int32_t id) {
+                        while (g_.nodes[id].op == sym::OP_NEG)
+                            id = g_.nodes[id].a;
+                        return g_.nodes[id].op == sym::OP_CONST ? (int32_t)-1 : id;
+                    };
+                    int n_imm = 0;
+                    for (size_t arr = 0; arr < n_arr; arr++)
+                    {
+                        if (!chunked[arr])
+                            continue;
+                        bool ascending = true;
+                        int32_t last = -1;
+                        for (auto &o : p_.outputs[arr])
+                        {
+                            const int32_t pos = basePos(o.id);
+                            if (pos < 0)
+                                continue; // constants are put when the drain reaches them
+                            if (pos < last)
+                                ascending = false;
+                            last = pos;
+                        }
+                        immediate[arr] = ascending;
+                        n_imm += ascending;
+                    }
+                    stage_buffers_ = 1;
+                    if (n_imm > 0)
+                        stage_buffers_ = (int)n_arr; // buffer k belongs to array k
+                }
+                auto drain = [&](int arr) {
+                    const int n = (int)p_.outputs[arr].size();
+                    while (drain_next[arr] < n && ready[arr][drain_next[arr]])
+                    {
+                        const int el = drain_next[arr]++;
+                        os << "STG_PUTK(" << arr << ", " << el % out_chunk << ", " << ref(p_.outputs[arr][el].id) << ");\n";
+                        if ((el + 1) % out_chunk == 0 || el + 1 == n)
+                        {
+                            const int base = (el / out_chunk) * out_chunk;
+                            os << "STG_FLUSHI" << arr << "(" << base << ", " << (el + 1 - base) << ");\n";
+                        }
+                    }
+                };
                 auto flushChunk = [&](int arr, int c) {
                     const int n = (int)p_.outputs[arr].size();
                     const int base = c * out_chunk, count = std::min(out_chunk, n - base);
@@ -326,6 +375,11 @@ namespace grbda
                     if (ready[arr][el])
                         return;
                     ready[arr][el] = 1;
+                    if (immediate[arr])
+                    {
+                        drain(arr);
+                        return;
+                    }
                     if (--chunk_missing[arr][el / out_chunk] == 0)
                         flushChunk(arr, el / out_chunk);
                 };
@@ -702,6 +756,7 @@ namespace grbda
             std::vector<char> live_;
             mutable std::vector<std::string> alias_; // name of a value after it was reloaded from its parking slot
             mutable int num_parked_ = 0;
+            mutable int stage_buffers_ = 1;
             std::vector<int> uses_;
             std::vector<int32_t> partner_;
             ProgramStats stats_;

@@ -288,13 +288,16 @@ namespace grbda_kernels
         real *g[3];   // output rows of the warp's first state
         int valid;    // number of states of this warp that exist (tail of the batch)
         int zero;     // 0 at run time, unknown at compile time (see pinAfter)
+        int buf_stride; // elements between the staging buffers of consecutive output arrays (Body::STAGE_BUFFERS > 1)
     };
     // Flush of one staged chunk: 32 states x COUNT values, COUNT * sizeof(real) contiguous bytes per
-    // state. Deliberately NOT inlined: FK / H bodies flush 40-70 chunks, and the inlined copies made
-    // the kernels 15-19 k instructions long (3 k of them arithmetic) and instruction-fetch bound
-    // (ncu: no_instructions 39 %); one shared copy per kernel removes that.
+    // state. FK / H bodies flush 40-70 chunks. Two things were measured on the way: fully unrolled
+    // inline copies with index arithmetic made the kernels 15-19 k instructions long and
+    // instruction-fetch bound (no_instructions 39 %); a shared noinline copy fixed that (FK 0.96 ->
+    // 0.74 ms) but every call spilled the caller's live registers around it (500 local loads per
+    // thread, long_scoreboard 68 %). Hence: inline, pointer-increment loop, NOT unrolled.
     template <typename real, int COUNT>
-    __device__ __noinline__ void flushChunkShared(real *__restrict__ g, int row_stride, const real *__restrict__ stg,
+    __device__ __forceinline__ void flushChunkShared(real *__restrict__ g, int row_stride, const real *__restrict__ stg,
                                                   int valid)
     {
         __syncwarp();
@@ -306,7 +309,7 @@ namespace grbda_kernels
             int st = lane / OUT_CHUNK;
             const real *src = stg + st * (OUT_CHUNK + 1) + el;
             real *dst = g + (size_t)st * row_stride + el;
-#pragma unroll 4
+#pragma unroll 1
             for (; st < valid; st += 32 / OUT_CHUNK)
             {
                 __stcs(dst, *src);
@@ -316,6 +319,7 @@ namespace grbda_kernels
         }
         else
         {
+#pragma unroll 1
             for (int e = lane; e < 32 * COUNT; e += 32)
             {
                 const int st = e / COUNT, el = e - st * COUNT;
@@ -338,7 +342,7 @@ namespace grbda_kernels
     template <typename Body, typename real, int BLOCK>
     __host__ __device__ constexpr size_t stageBytes()
     {
-        return bodyChunked<Body>() ? (size_t)BLOCK * (OUT_CHUNK + 1) * sizeof(real) : 0;
+        return bodyChunked<Body>() ? (size_t)Body::STAGE_BUFFERS * BLOCK * (OUT_CHUNK + 1) * sizeof(real) : 0;
     }
     template <typename Body, typename real>
     __device__ __forceinline__ OutStage<real> makeOutStage(unsigned char *stage_base, real *out0, real *out1,
@@ -350,6 +354,7 @@ namespace grbda_kernels
         real *buf = reinterpret_cast<real *>(stage_base) + (size_t)warp * 32 * (OUT_CHUNK + 1);
         o.warp = buf;
         o.lane = buf + lane * (OUT_CHUNK + 1);
+        o.buf_stride = (int)blockDim.x * (OUT_CHUNK + 1); // layout [array][warp][32][OUT_CHUNK + 1]
         const int64_t s0 = first + 32 * warp;
         o.g[0] = out0 ? out0 + s0 * Body::N_OUT0 : nullptr;
         o.g[1] = out1 ? out1 + s0 * Body::N_OUT1 : nullptr;
