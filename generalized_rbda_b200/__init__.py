@@ -51,6 +51,7 @@ _lib.grbda_cuda_model_gravity.argtypes = [_vp, _vp]
 _lib.grbda_cuda_cluster_phi.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp]
 _lib.grbda_cuda_dump_program.argtypes = [_vp, C.c_int, C.c_char_p, _vp]
 _lib.grbda_cuda_kernel_counts.argtypes = [_vp, C.c_int, _vp]
+_lib.grbda_cuda_emit_source.argtypes = [_vp, C.c_int, C.c_int, C.c_char_p]
 _lib.grbda_cuda_dump_role_program.argtypes = [_vp, C.c_int, C.c_char_p, _vp]
 for _p in ("f64", "f32"):
     getattr(_lib, "grbda_cuda_inverse_dynamics_" + _p).argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp]
@@ -69,7 +70,7 @@ EXPORTED_SYMBOLS = [
     "grbda_cuda_model_create_from_urdf", "grbda_cuda_model_create_from_robot", "grbda_cuda_model_destroy",
     "grbda_cuda_num_positions", "grbda_cuda_num_degrees_of_freedom", "grbda_cuda_num_bodies",
     "grbda_cuda_num_clusters", "grbda_cuda_model_hash", "grbda_cuda_cluster_info", "grbda_cuda_body_info",
-    "grbda_cuda_cluster_G", "grbda_cuda_model_gravity", "grbda_cuda_cluster_phi", "grbda_cuda_dump_program", "grbda_cuda_dump_role_program", "grbda_cuda_kernel_counts",
+    "grbda_cuda_cluster_G", "grbda_cuda_model_gravity", "grbda_cuda_cluster_phi", "grbda_cuda_dump_program", "grbda_cuda_dump_role_program", "grbda_cuda_kernel_counts", "grbda_cuda_emit_source",
     "grbda_cuda_inverse_dynamics_f64", "grbda_cuda_inverse_dynamics_f32",
     "grbda_cuda_forward_dynamics_f64", "grbda_cuda_forward_dynamics_f32",
     "grbda_cuda_mass_matrix_f64", "grbda_cuda_mass_matrix_f32",
@@ -230,6 +231,10 @@ class ClusterTreeModel:
         d = dict(zip(keys, [int(x) for x in counts]))
         d["flops"] = d["add"] + d["mul"] + d["div"] + d["sqrt"]
         return d
+
+    def emit_source(self, program, path, park=False):
+        """Write the CUDA source the model compiler emits for `program` (constant table + struct Body)."""
+        _check(_lib.grbda_cuda_emit_source(self._h, program, int(bool(park)), path.encode()))
 
     def kernel_counts(self, algo):
         """Operation counts of the program the default compiled kernel of `algo` runs per state."""

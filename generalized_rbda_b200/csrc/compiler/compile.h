@@ -1,6 +1,8 @@
 // Device-side model compiler, part 3: driver. Model + algorithm -> emitted CUDA body, tape, counts.
 #pragma once
 #include <fstream>
+#include <ostream>
+#include <sstream>
 #include "algorithms.h"
 #include "emit.h"
 #include "partition.h"
@@ -139,6 +141,58 @@ namespace grbda
             }
             return out;
         }
+
+        // The generated `struct Body` of one program: sizes, range check, run<real, FAST>(). Shared by the
+        // build-time tool (tools/modelc.cpp) and grbda_cuda_emit_source (host-compiled emitter self test).
+            inline void emitBodyStruct(std::ostream &os, const std::string &struct_name, const CompiledAlgo &c)
+        {
+            os << "struct " << struct_name << "\n{\n";
+            os << "    static constexpr int N_IN0 = " << c.n_in[0] << ", N_IN1 = " << c.n_in[1]
+               << ", N_IN2 = " << c.n_in[2] << ";\n";
+            os << "    static constexpr int N_OUT0 = " << c.n_out[0] << ", N_OUT1 = " << c.n_out[1]
+               << ", N_OUT2 = " << c.n_out[2] << ";\n";
+            os << "    static constexpr bool RANGE_CHECKED = " << (c.range_check == "true" ? "false" : "true") << ";\n";
+            os << "    static constexpr int STAGE_BUFFERS = " << c.stage_buffers << ";\n";
+            os << "    static constexpr bool PARKED = " << (c.parked ? "true" : "false") << "; // " << c.num_parked
+               << " values parked in the thread's tile row\n";
+            os << "    template <typename real>\n    static __device__ __forceinline__ bool inRange(const real "
+                  "*__restrict__ in0, const real *__restrict__ in1,\n        const real *__restrict__ in2)\n    {\n"
+                  "#define KC(x) ((real)(x))\n#define IN0(i) in0[i]\n#define IN1(i) in1[i]\n#define IN2(i) in2[i]\n"
+                  "        return " << c.range_check << ";\n#undef KC\n#undef IN0\n#undef IN1\n#undef IN2\n    }\n";
+            os << "    template <typename real, bool FAST>\n";
+            if (c.parked)
+                // the thread's rows are read AND written (parking): no __restrict__, one pointer per row
+                os << "    static __device__ __forceinline__ void run(const real *in0, const real *in1, const real *in2,\n"
+                      "        real *out0, real *out1, real *out2, const OutStage<real> &stage)\n    {\n"
+                      "        real *const row0 = const_cast<real *>(in0), *const row1 = const_cast<real *>(in1),\n"
+                      "                   *const row2 = const_cast<real *>(in2), *const row3 = out0;\n"
+                      "#define IN0(i) row0[i]\n#define IN1(i) row1[i]\n#define IN2(i) row2[i]\n#define OUT0(i, x) row3[i] = (x)\n"
+                      // volatile: otherwise the compiler forwards the stored value to the load and keeps (spills) it itself
+                      "#define PARK_ST(t, i, x) *(volatile real *)(row##t + (i)) = (x)\n"
+                      "#define PARK_LD(t, i) (*(volatile real *)(row##t + (i)))\n";
+            else
+                os << "    static __device__ __forceinline__ void run(const real *__restrict__ in0, const real "
+                      "*__restrict__ in1,\n"
+                      "        const real *__restrict__ in2, real *__restrict__ out0, real *__restrict__ out1, "
+                      "real *__restrict__ out2,\n        const OutStage<real> &stage)\n    {\n"
+                      "#define IN0(i) in0[i]\n#define IN1(i) in1[i]\n#define IN2(i) in2[i]\n#define OUT0(i, x) out0[i] = (x)\n"
+                      "#define PARK_ST(t, i, x)\n#define PARK_LD(t, i) KC(0.0)\n";
+            os << "#define KC(x) ((real)(x))\n#define KT(i) kc_table<real>(i)\n"
+                  "#define OUT1(i, x) out1[i] = (x)\n#define OUT2(i, x) out2[i] = (x)\n"
+                  "#define GRBDA_ALIGN() __syncwarp()\n#define GRBDA_PIN(x, late) GRBDA_PIN_IMPL(x, late, stage.zero)\n"
+                  "#define STG_PUT(j, x) stage.lane[j] = (x)\n"
+                  "#define STG_PUTK(k, j, x) stage.lane[(k) * stage.buf_stride + (j)] = (x)\n"
+                  "#define STG_FLUSHI0(base, count) flushChunk<real, N_OUT0, count>(stage.g[0], base, stage.warp, stage.valid)\n"
+                  "#define STG_FLUSHI1(base, count) flushChunk<real, N_OUT1, count>(stage.g[1], base, stage.warp + stage.buf_stride, stage.valid)\n"
+                  "#define STG_FLUSHI2(base, count) flushChunk<real, N_OUT2, count>(stage.g[2], base, stage.warp + 2 * stage.buf_stride, stage.valid)\n"
+                  "#define STG_FLUSH0(base, count) flushChunk<real, N_OUT0, count>(stage.g[0], base, stage.warp, stage.valid)\n"
+                  "#define STG_FLUSH1(base, count) flushChunk<real, N_OUT1, count>(stage.g[1], base, stage.warp, stage.valid)\n"
+                  "#define STG_FLUSH2(base, count) flushChunk<real, N_OUT2, count>(stage.g[2], base, stage.warp, stage.valid)\n";
+            os << c.body;
+            os << "#undef KC\n#undef KT\n#undef IN0\n#undef IN1\n#undef IN2\n#undef OUT0\n#undef OUT1\n#undef OUT2\n#undef GRBDA_ALIGN\n#undef GRBDA_PIN\n#undef PARK_ST\n#undef PARK_LD\n#undef STG_PUT\n#undef STG_PUTK\n#undef STG_FLUSHI0\n#undef STG_FLUSHI1\n#undef STG_FLUSHI2\n#undef STG_FLUSH0\n#undef STG_FLUSH1\n#undef STG_FLUSH2\n";
+            os << "    }\n};\n";
+        }
+
 
         // ---- limb-parallel (one warp per limb) version of the same program ---------------------------
         struct CompiledRoles

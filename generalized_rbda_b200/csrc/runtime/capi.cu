@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <map>
 #include <mutex>
 #include <string>
@@ -335,6 +336,22 @@ extern "C"
                 const int64_t v[8] = {s.n_nodes, s.n_add, s.n_mul, s.n_div, s.n_sqrt, s.n_sin, s.n_cos, s.n_fusable};
                 std::memcpy(counts8, v, sizeof(v));
             }
+            return (grbda_status)GRBDA_OK; });
+    }
+
+    grbda_status grbda_cuda_emit_source(const grbda_model *m, int program, int park, const char *path)
+    {
+        if (!m || !path || program < 0 || program >= compiler::PROGRAM_COUNT)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        return guarded([&]
+                       {
+            compiler::ConstTable consts;
+            const compiler::CompiledAlgo c = compiler::compileAlgo(m->model, program, true, 0, &consts, 16, park != 0);
+            std::ofstream f(path);
+            if (!f)
+                return fail(GRBDA_ERR_IO, std::string("cannot write ") + path);
+            f << consts.definition("kc_table");
+            compiler::emitBodyStruct(f, "Body", c);
             return (grbda_status)GRBDA_OK; });
     }
 

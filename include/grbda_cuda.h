@@ -142,6 +142,13 @@ grbda_status grbda_cuda_cluster_G(const grbda_model *m, int cluster, double *G);
  * fusable mul+add pairs} of the straight-line program each thread executes. */
 grbda_status grbda_cuda_dump_program(const grbda_model *m, int algo, const char *path, int64_t *counts8);
 
+/* The CUDA source the model compiler emits for one program (0 ID, 1 FD, 2 FK, 3 H, 4 phi, 5 FD/LTDL):
+ * constant table + `struct Body` (sizes, generated range check, run<real, FAST>()), exactly what
+ * build.py feeds to nvcc, written to `path`. park != 0: the variant that parks long-lived values in the
+ * thread's shared-memory tile row. Used by the emitter self test, which compiles this text for the
+ * host with the kernel-side helpers stubbed (tests/host_body_prelude.h) and compares with the oracle. */
+grbda_status grbda_cuda_emit_source(const grbda_model *m, int program, int park, const char *path);
+
 /* Operation counts (same 8 fields) of the program the DEFAULT compiled kernel of entry point `algo`
  * (0 ID, 1 FD, 2 FK, 3 H, 4 phi) executes per state. It can differ from dump_program(algo): the default
  * forward-dynamics kernel of a model may run program 5 (CRBA + bias + sparse L^T D L) instead of the

@@ -270,3 +270,113 @@ def test_schedule_round_trip(grbda):
     arrs["body_parent"][1] = 5
     with pytest.raises(grbda.GrbdaError):
         grbda.ClusterTreeModel.from_schedule(C.byref(s), device=None)
+
+
+# ---- the emitted CUDA text itself, compiled for the host ---------------------------------------------
+HOST_MAIN = r'''
+#include "host_body_prelude.h"
+using namespace host_body;
+#include "body.inc"
+#include <cstdio>
+#include <vector>
+int main(int argc, char **argv)
+{
+    FILE *f = std::fopen(argv[1], "rb");
+    int64_t B = 0;
+    if (!f || std::fread(&B, 8, 1, f) != 1) return 2;
+    constexpr int N0 = Body::N_IN0, N1 = Body::N_IN1, N2 = Body::N_IN2;
+    constexpr int M0 = Body::N_OUT0, M1 = Body::N_OUT1, M2 = Body::N_OUT2;
+    std::vector<double> in0(B * N0 + 1), in1(B * N1 + 1), in2(B * N2 + 1), out0(B * M0 + 1), out1(B * M1 + 1), out2(B * M2 + 1);
+    if (N0 && std::fread(in0.data(), 8, B * N0, f) != (size_t)(B * N0)) return 3;
+    if (N1 && std::fread(in1.data(), 8, B * N1, f) != (size_t)(B * N1)) return 3;
+    if (N2 && std::fread(in2.data(), 8, B * N2, f) != (size_t)(B * N2)) return 3;
+    std::fclose(f);
+    int64_t in_range = 0;
+    for (int64_t b = 0; b < B; b++)
+    {
+        // the thread's private tile rows (the parked variant overwrites them)
+        double r0[N0 + 1], r1[N1 + 1], r2[N2 + 1], o0[M0 + 1];
+        for (int i = 0; i < N0; i++) r0[i] = in0[b * N0 + i];
+        for (int i = 0; i < N1; i++) r1[i] = in1[b * N1 + i];
+        for (int i = 0; i < N2; i++) r2[i] = in2[b * N2 + i];
+        in_range += Body::inRange<double>(r0, r1, r2) ? 1 : 0;
+        double stg[3 * (OUT_CHUNK + 1)] = {0};
+        OutStage<double> st;
+        st.lane = st.warp = stg;
+        st.g[0] = &out0[b * M0], st.g[1] = &out1[b * M1], st.g[2] = &out2[b * M2];
+        st.valid = 1, st.zero = 0, st.buf_stride = OUT_CHUNK + 1;
+        const bool staged_out = M0 <= 64;
+        Body::run<double, true>(r0, r1, r2, staged_out ? o0 : &out0[b * M0], &out1[b * M1], &out2[b * M2], st);
+        if (staged_out)
+            for (int i = 0; i < M0; i++) out0[b * M0 + i] = o0[i];
+    }
+    f = std::fopen(argv[2], "wb");
+    std::fwrite(&in_range, 8, 1, f);
+    std::fwrite(out0.data(), 8, B * M0, f);
+    std::fwrite(out1.data(), 8, B * M1, f);
+    std::fwrite(out2.data(), 8, B * M2, f);
+    std::fclose(f);
+    return 0;
+}
+'''
+
+
+def run_emitted_source(m, program, park, ins, tmp_path, tag):
+    """Compile the emitted `struct Body` of one program for the host and run it over `ins`."""
+    import subprocess
+    d = tmp_path / tag
+    d.mkdir()
+    m.emit_source(program, str(d / "body.inc"), park=park)
+    (d / "main.cpp").write_text(HOST_MAIN)
+    exe = str(d / "run")
+    subprocess.run(["/usr/bin/g++", "-O0", "-std=c++17", "-I", os.path.dirname(os.path.abspath(__file__)), "-I", str(d), "-o", exe, str(d / "main.cpp")],
+                   check=True)
+    B = ins[0].shape[0]
+    with open(d / "in.bin", "wb") as f:
+        f.write(np.int64(B).tobytes())
+        for a in ins:
+            f.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    subprocess.run([exe, str(d / "in.bin"), str(d / "out.bin")], check=True)
+    raw = np.fromfile(d / "out.bin", dtype=np.float64)
+    in_range = int(np.frombuffer(raw[:1].tobytes(), dtype=np.int64)[0])
+    text = (d / "body.inc").read_text()
+    sizes = [int(x) for x in __import__("re").search(r"N_OUT0 = (\d+), N_OUT1 = (\d+), N_OUT2 = (\d+)", text).groups()]
+    outs, off = [], 1
+    for n in sizes:
+        outs.append(raw[off:off + B * n].reshape(B, n) if n else np.zeros((B, 0)))
+        off += B * n
+    return outs, in_range, text
+
+
+@pytest.mark.parametrize("robot", ["tello_with_arms", "four_bar"])
+def test_emitted_cuda_text_on_the_host(grbda, oracle, robot, tmp_path):
+    """What the tapes cannot see: the emitted CUDA text (statement order, sin/cos pairing and pins, chunked
+    output staging, parking of long-lived values in the tile rows, the generated range check) is compiled
+    with g++ against host stand-ins of the kernel helpers (tests/host_body_prelude.h) and compared with the
+    oracle, program by program, plain and parked."""
+    from mirror import mirror_to_oracle
+    m = grbda.ClusterTreeModel.from_robot(robot, device=None)
+    o = oracle.OracleModel(robot) if robot in ROBOTS else mirror_to_oracle(m, oracle)
+    q, yd, aux = o.generate_states(24, seed=29)
+    ins = [q, yd, aux]
+    want = {0: o.inverse_dynamics(q, yd, aux), 1: o.forward_dynamics(q, yd, aux), 5: o.forward_dynamics(q, yd, aux),
+            3: o.mass_matrix(q).reshape(q.shape[0], -1)}
+    for program, park in [(0, False), (0, True), (1, False), (5, False), (5, True), (3, False)]:
+        outs, in_range, text = run_emitted_source(m, program, park, ins[:3 if program != 3 else 1] + [], tmp_path,
+                                                  "p%d_%d" % (program, park))
+        assert rel(outs[0], want[program]) < TOL, (program, park)
+        assert in_range == q.shape[0]
+        if park and robot == "tello_with_arms":
+            assert "PARKED = true" in text and text.count("PARK_ST(") >= (50 if program == 5 else 5)
+    # forward kinematics: three chunk-staged output arrays
+    p, R, v = o.forward_kinematics(q, yd)
+    outs, in_range, text = run_emitted_source(m, 2, False, [q, yd], tmp_path, "fk")
+    assert rel(outs[0].reshape(p.shape), p) < TOL and rel(outs[1].reshape(R.shape), R) < TOL
+    assert rel(outs[2].reshape(v.shape), v) < TOL
+    if robot == "tello_with_arms":
+        assert "STAGE_BUFFERS = 3" in text and "STG_PUTK(" in text
+    # the generated range check rejects a joint angle beyond the fast sin/cos range
+    q_far = q.copy()
+    q_far[3, m.clusters()[-1]["position_index"]] = 3.0e13
+    _, in_range, _ = run_emitted_source(m, 0, False, [q_far, yd, aux], tmp_path, "far")
+    assert in_range == q.shape[0] - 1
