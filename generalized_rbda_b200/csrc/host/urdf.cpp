@@ -14,6 +14,7 @@
 //     Revolute / Free, multi-link clusters -> Generic with a GenericImplicit (<loop>) or Static
 //     (<coupling>) constraint. The casadi::SX constraint function becomes a recorded sym::Sym
 //     program; casadi's which_depends becomes "the recorded row is not a constant".
+#include <cctype>
 #include <algorithm>
 #include <cstring>
 #include <fstream>
@@ -290,7 +291,14 @@ namespace grbda
                     UJoint j;
                     j.name = n.get("name");
                     j.type = n.get("type");
-                    j.independent = n.get("independent", "true") != "false";
+                    {
+                        // "true"/"false" in the hand-written models, "True"/"False" where xacro evaluated a
+                        // Python expression (Benchmarking/urdfs/parallel_chains)
+                        std::string flag = n.get("independent", "true");
+                        for (char &ch : flag)
+                            ch = (char)std::tolower((unsigned char)ch);
+                        j.independent = !(flag == "false" || flag == "0");
+                    }
                     if (!n.child("parent") || !n.child("child"))
                         throw std::runtime_error("URDF: joint '" + j.name + "' needs <parent> and <child>");
                     j.parent = n.child("parent")->get("link");

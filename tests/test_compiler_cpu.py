@@ -380,3 +380,56 @@ def test_emitted_cuda_text_on_the_host(grbda, oracle, robot, tmp_path):
     q_far[3, m.clusters()[-1]["position_index"]] = 3.0e13
     _, in_range, _ = run_emitted_source(m, 0, False, [q_far, yd, aux], tmp_path, "far")
     assert in_range == q.shape[0] - 1
+
+
+# ---- URDF+ regression corpus: samples of the reference's Benchmarking/urdfs families ----
+# (data files copied to tests/urdf_corpus/; branch_B_D = B branches of depth D on a floating base,
+# parallel chains = two 5-link chains closed by one coupling / loop joint after `loop_size` links)
+CORPUS = {
+    # file stem: (nq, nv, bodies, clusters)
+    "revolute_rotor_branch_1_1": (8, 7, 3, 2), "revolute_rotor_branch_2_3": (13, 12, 13, 7),
+    "revolute_rotor_branch_4_2": (15, 14, 17, 9), "approx_revolute_rotor_branch_2_3": (13, 12, 7, 7),
+    "revolute_rotor_pair_branch_1_1": (9, 8, 5, 2), "revolute_rotor_pair_branch_2_3": (19, 18, 25, 7),
+    "approx_revolute_rotor_pair_branch_2_3": (19, 18, 13, 13),
+    "four_bar_branch_1_1": (10, 7, 4, 2), "four_bar_branch_2_3": (25, 12, 19, 7), "four_bar_branch_4_2": (31, 14, 25, 9),
+    "approx_four_bar_branch_2_3": (13, 12, 7, 7),
+    "explicit_parallel_chains_depth5_loop_size2": (9, 9, 10, 9), "explicit_parallel_chains_depth5_loop_size4": (9, 9, 10, 7),
+    "explicit_parallel_chains_depth5_loop_size10": (9, 9, 10, 1),
+    "implicit_parallel_chains_depth5_loop_size3": (11, 9, 11, 9), "implicit_parallel_chains_depth5_loop_size5": (11, 9, 11, 7),
+    "implicit_parallel_chains_depth5_loop_size11": (11, 9, 11, 1),
+    "explicit_parallel_chains_depth5_approx_loop_size10": (10, 10, 10, 10),
+}
+
+
+@pytest.mark.parametrize("stem", sorted(CORPUS))
+def test_urdf_corpus(grbda, oracle, stem, tmp_path):
+    """Front end + compiler over the structural families of the reference's benchmark corpus: sizes as the
+    family formulas give them (bodies = 1 + links per cluster x B x D, one cluster per loop / coupling group,
+    dof = 6 + independent joints), then every program against the oracle assembled from the parsed topology."""
+    from mirror import mirror_to_oracle
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "urdf_corpus", stem + ".urdf")
+    m = grbda.ClusterTreeModel.from_urdf(path, device=None)
+    assert (m.nq, m.nv, m.nb, m.nc) == CORPUS[stem]
+    branch = re.match(r"(approx_)?(revolute_rotor|revolute_rotor_pair|four_bar)_branch_(\d+)_(\d+)", stem)
+    if branch:
+        approx, family, B, D = branch.group(1), branch.group(2), int(branch.group(3)), int(branch.group(4))
+        links = {"revolute_rotor": 1, "revolute_rotor_pair": 2, "four_bar": 3}[family]
+        extra = 0 if approx or family == "four_bar" else links          # one rotor per link
+        per_cluster = (links if not approx else {"revolute_rotor": 1, "revolute_rotor_pair": 2, "four_bar": 1}[family]) + extra
+        n_clusters = B * D * (1 if not approx else {"revolute_rotor": 1, "revolute_rotor_pair": 2, "four_bar": 1}[family])
+        assert m.nc == 1 + n_clusters
+        assert m.nb == 1 + (B * D * per_cluster if not approx else n_clusters)
+    o = mirror_to_oracle(m, oracle)
+    q, yd, aux = o.generate_states(6, seed=3)
+    assert o.validate_states(q).all()
+    ins = [q, yd, aux]
+    want = {0: o.inverse_dynamics(q, yd, aux), 1: o.forward_dynamics(q, yd, aux), 5: o.forward_dynamics(q, yd, aux),
+            3: o.mass_matrix(q).reshape(q.shape[0], -1)}
+    for program, ref_out in want.items():
+        tape = str(tmp_path / ("p%d.tape" % program))
+        m.dump_program(program, tape)
+        assert rel(run_tape(load_tape(tape), ins)[0], ref_out) < 1e-9, program
+    p, R, v = o.forward_kinematics(q, yd)
+    m.dump_program(2, str(tmp_path / "fk.tape"))
+    fk = run_tape(load_tape(str(tmp_path / "fk.tape")), ins)
+    assert rel(fk[0].reshape(p.shape), p) < TOL and rel(fk[1].reshape(R.shape), R) < TOL and rel(fk[2].reshape(v.shape), v) < TOL
