@@ -247,6 +247,14 @@ def main():
     t_h = time_kernel(lambda: m.getMassMatrix(q[:Bk], out=Hbuf), 5)
     t_fk = time_kernel(lambda: m.forwardKinematics(q[:Bk], yd[:Bk], out=fk_out), 5)
     del Hbuf, fk_out
+    # dynamics with external forces on the terminal links: two launches each
+    nf = len(m.externalForceBodies())
+    f_ext = (torch.rand((B, nf, 6), dtype=torch.float64, device=dev) - 0.5) * 20.0
+    ext_out = torch.empty_like(tau)
+    m.forwardDynamics(q, yd, tau, out=ext_out, f_ext=f_ext)
+    t_fd_ext = time_kernel(lambda: m.forwardDynamics(q, yd, tau, out=ext_out, f_ext=f_ext), 5)
+    t_id_ext = time_kernel(lambda: m.inverseDynamics(q, yd, ydd, out=ext_out, f_ext=f_ext), 5)
+    del f_ext, ext_out
 
     # parity spot check + checksum gather (the only collective)
     err = float(((tau_back - tau).abs().amax(1) / tau.abs().amax(1)).median())
@@ -323,6 +331,8 @@ def main():
                                  "achieved": f_alg_id * B / t_id / 1e12, "frac": (f_alg_id * B / t_id) / fp64_peak,
                                  "hbm_frac": alg_bytes * B / t_id / 1e9 / peaks["hbm_gbs"]}}
         line["other_kernels"] = {
+            "dynamics_with_external_forces": {"states": B, "force_bodies": nf, "forward_ms": t_fd_ext * 1e3,
+                                              "inverse_ms": t_id_ext * 1e3},
             "mass_matrix": {"states": Bk, "kernel_ms": t_h * 1e3, "bytes_per_state": 8 * (m.nq + m.nv * m.nv),
                             "hbm_frac": 8 * (m.nq + m.nv * m.nv) * Bk / t_h / 1e9 / peaks["hbm_gbs"]},
             "forward_kinematics": {"states": Bk, "kernel_ms": t_fk * 1e3,

@@ -29,7 +29,8 @@ _lib = C.CDLL(_LIB_PATH)
 
 ALGO_ID, ALGO_FD, ALGO_FK, ALGO_H, ALGO_PHI = 0, 1, 2, 3, 4
 ALGO_NAMES = ["id", "fd", "fk", "h", "phi"]
-PROGRAM_FD_LTL = 5  # dump_program only: forward dynamics as CRBA + bias + sparse L^T D L (kernel variant "ltl")
+ALGO_GFA, ALGO_GFS = 5, 6  # tau_in +/- J^T f_ext (external forces on the terminal links)
+PROGRAM_FD_LTL = 7  # dump_program only: forward dynamics as CRBA + bias + sparse L^T D L (kernel variant "ltl")
 
 _vp = C.c_void_p
 _i64 = C.c_int64
@@ -58,6 +59,9 @@ for _p in ("f64", "f32"):
     getattr(_lib, "grbda_cuda_forward_dynamics_" + _p).argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp]
     getattr(_lib, "grbda_cuda_mass_matrix_" + _p).argtypes = [_vp, _vp, _vp, _i64, _vp]
     getattr(_lib, "grbda_cuda_forward_kinematics_" + _p).argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
+_lib.grbda_cuda_inverse_dynamics_ext_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
+_lib.grbda_cuda_forward_dynamics_ext_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
+_lib.grbda_cuda_external_force_bodies.argtypes = [_vp, _vp, _vp]
 _lib.grbda_cuda_dynamics_host_f64.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _i64]
 _lib.grbda_cuda_forward_inverse_host_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64]
 _lib.grbda_cuda_generate_states.argtypes = [_vp, C.c_uint64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]
@@ -71,6 +75,7 @@ EXPORTED_SYMBOLS = [
     "grbda_cuda_num_positions", "grbda_cuda_num_degrees_of_freedom", "grbda_cuda_num_bodies",
     "grbda_cuda_num_clusters", "grbda_cuda_model_hash", "grbda_cuda_cluster_info", "grbda_cuda_body_info",
     "grbda_cuda_cluster_G", "grbda_cuda_model_gravity", "grbda_cuda_cluster_phi", "grbda_cuda_dump_program", "grbda_cuda_dump_role_program", "grbda_cuda_kernel_counts", "grbda_cuda_emit_source",
+    "grbda_cuda_external_force_bodies", "grbda_cuda_inverse_dynamics_ext_f64", "grbda_cuda_forward_dynamics_ext_f64",
     "grbda_cuda_inverse_dynamics_f64", "grbda_cuda_inverse_dynamics_f32",
     "grbda_cuda_forward_dynamics_f64", "grbda_cuda_forward_dynamics_f32",
     "grbda_cuda_mass_matrix_f64", "grbda_cuda_mass_matrix_f32",
@@ -232,6 +237,28 @@ class ClusterTreeModel:
         d["flops"] = d["add"] + d["mul"] + d["div"] + d["sqrt"]
         return d
 
+    def externalForceBodies(self):
+        """Body indices (terminal links) that accept external forces, in the order f_ext uses."""
+        n = C.c_int32(0)
+        _check(_lib.grbda_cuda_external_force_bodies(self._h, None, C.byref(n)))
+        idx = (C.c_int32 * max(1, n.value))()
+        _check(_lib.grbda_cuda_external_force_bodies(self._h, idx, C.byref(n)))
+        return [int(idx[i]) for i in range(n.value)]
+
+    def _dynamics_ext(self, name, q, yd, in3, f_ext, out):
+        import torch
+        q = self._prep(q, self.nq, torch.float64)
+        yd = self._prep(yd, self.nv, torch.float64)
+        in3 = self._prep(in3, self.nv, torch.float64)
+        B = q.shape[0]
+        nf = len(self.externalForceBodies())
+        f_ext = f_ext.reshape(B, -1)
+        f_ext = self._prep(f_ext, 6 * nf, torch.float64)
+        if out is None:
+            out = torch.empty((B, self.nv), dtype=torch.float64, device=q.device)
+        _check(getattr(_lib, name)(self._h, _ptr(q), _ptr(yd), _ptr(in3), _ptr(f_ext), _ptr(out), B, _stream()))
+        return out
+
     def emit_source(self, program, path, park=False):
         """Write the CUDA source the model compiler emits for `program` (constant table + struct Body)."""
         _check(_lib.grbda_cuda_emit_source(self._h, program, int(bool(park)), path.encode()))
@@ -267,9 +294,12 @@ class ClusterTreeModel:
         import torch
         return "f64" if t.dtype == torch.float64 else "f32"
 
-    def inverseDynamics(self, q, yd, ydd, out=None):
-        """tau[batch, nv] = ID(q, yd, ydd)   (ClusterTreeModel::inverseDynamics)"""
+    def inverseDynamics(self, q, yd, ydd, out=None, f_ext=None):
+        """tau[batch, nv] = ID(q, yd, ydd)   (ClusterTreeModel::inverseDynamics). f_ext[batch, nf, 6]:
+        world-frame spatial forces on externalForceBodies() (TreeModel::setExternalForces), FP64."""
         import torch
+        if f_ext is not None:
+            return self._dynamics_ext("grbda_cuda_inverse_dynamics_ext_f64", q, yd, ydd, f_ext, out)
         q = self._prep(q, self.nq)
         yd, ydd = self._prep(yd, self.nv, q.dtype), self._prep(ydd, self.nv, q.dtype)
         if out is None:
@@ -278,9 +308,11 @@ class ClusterTreeModel:
         _check(fn(self._h, _ptr(q), _ptr(yd), _ptr(ydd), _ptr(out), q.shape[0], _stream()))
         return out
 
-    def forwardDynamics(self, q, yd, tau, out=None):
-        """ydd[batch, nv] = FD(q, yd, tau)   (ClusterTreeModel::forwardDynamics)"""
+    def forwardDynamics(self, q, yd, tau, out=None, f_ext=None):
+        """ydd[batch, nv] = FD(q, yd, tau)   (ClusterTreeModel::forwardDynamics); f_ext as in inverseDynamics."""
         import torch
+        if f_ext is not None:
+            return self._dynamics_ext("grbda_cuda_forward_dynamics_ext_f64", q, yd, tau, f_ext, out)
         q = self._prep(q, self.nq)
         yd, tau = self._prep(yd, self.nv, q.dtype), self._prep(tau, self.nv, q.dtype)
         if out is None:

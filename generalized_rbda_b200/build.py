@@ -31,23 +31,23 @@ LIB = os.path.join(HERE, "libgrbda_cuda.so")
 # (otherwise the articulated-body sweep); 'park' = long-lived values parked in dead slots of the thread's
 # shared-memory tile row instead of being spilled (T and S only). Measured on B200 (profiles/README.md): T,128,2 is the fastest
 # and the most device-independent shape for every entry point.
-DEFAULT_VARIANTS = "id=T,128,2;S,128,2|fd=T,128,2,ltl,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2"
+DEFAULT_VARIANTS = "id=T,128,2;S,128,2|fd=T,128,2,ltl,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2"
 SYNC_EVERY = int(os.environ.get("GRBDA_SYNC_EVERY", "0"))  # alignment barriers measured useless (profiles/)
 MODELS = {
-    "tello_with_arms": ("id,fd,fk,h,phi,gen", "id=T,128,2;S,128,2|fd=T,128,2,ltl,park;T,128,2,ltl;S,128,2,ltl,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2", True),
-    "tello": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
-    "mini_cheetah": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
-    "mit_humanoid": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
-    "four_bar": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, True),
-    "six_bar": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
-    "planar_leg_linkage": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
-    "mit_humanoid_leg": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
-    "jvrc1_humanoid": ("id,fd,fk,h,phi,gen", DEFAULT_VARIANTS, False),
-    "revolute_rotor_chain": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, False),
-    "revolute_chain_with_rotor_2": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, True),
-    "revolute_chain_with_rotor_4": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, False),
-    "revolute_pair_chain_with_rotor_2": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, False),
-    "revolute_pair_chain_with_rotor_4": ("id,fd,fk,h,gen", DEFAULT_VARIANTS, False),
+    "tello_with_arms": ("id,fd,fk,h,phi,gfa,gfs,gen", "id=T,128,2;S,128,2|fd=T,128,2,ltl,park;T,128,2,ltl;S,128,2,ltl,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2", True),
+    "tello": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    "mini_cheetah": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
+    "mit_humanoid": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
+    "four_bar": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, True),
+    "six_bar": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    "planar_leg_linkage": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    "mit_humanoid_leg": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    "jvrc1_humanoid": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    "revolute_rotor_chain": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    "revolute_chain_with_rotor_2": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
+    "revolute_chain_with_rotor_4": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    "revolute_pair_chain_with_rotor_2": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    "revolute_pair_chain_with_rotor_4": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
 }
 
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"

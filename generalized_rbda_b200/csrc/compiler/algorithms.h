@@ -559,6 +559,86 @@ namespace grbda
             }
 
             // ---------------------------------------------------------------------------------
+            // external forces (TreeModel::setExternalForces, TreeModel.cpp:189-193, ClusterTreeDynamics.cpp
+            // :100-105): a world-frame spatial force f on body i enters RNEA and ABA as f_i -= Xa_i^* f. Both
+            // recursions are linear in it, so  ID_ext = ID - J^T f  and  FD_ext(tau) = FD(tau + J^T f)  with
+            // J^T f = the backward force pass over the transformed forces alone. This program evaluates
+            // tau_in + sign J^T f for forces on the model's terminal links (feet, hands, chain tips).
+            // ---------------------------------------------------------------------------------
+            static std::vector<int> externalForceBodies(const ClusterTreeModel &model)
+            {
+                ModelCompiler probe(model);
+                std::vector<char> has_child(model.getNumBodies(), 0);
+                for (const Body &b : model.bodies())
+                    if (b.parent_index_ >= 0)
+                        has_child[b.parent_index_] = 1;
+                std::vector<int> out;
+                for (const Body &b : model.bodies())
+                    if (!has_child[b.index_] && !probe.isAxisymmetricLeaf(b.index_))
+                        out.push_back(b.index_);
+                return out;
+            }
+            std::vector<Sym> generalizedExternalForce(int sign)
+            {
+                beginKinematics();
+                const int Nb = m_.getNumBodies(), nv = m_.getNumDegreesOfFreedom();
+                const std::vector<int> force_bodies = externalForceBodies(m_);
+                std::vector<int> slot(Nb, -1);
+                for (size_t k = 0; k < force_bodies.size(); k++)
+                    slot[force_bodies[k]] = (int)k;
+                std::vector<Xf> Xa(Nb);
+                std::vector<SV> f(Nb);
+                std::vector<Sym> tau(nv, Sym(0.0));
+                auto isFree = [](const ClusterDesc &d) {
+                    return d.type == ClusterType::FreeQuaternion || d.type == ClusterType::FreeRollPitchYaw;
+                };
+                std::function<void(int)> visit = [&](int ci) {
+                    kinematicsCluster(ci, false, false);
+                    const ClusterTreeNode &c = m_.clusters()[ci];
+                    const ClusterDesc &d = c.joint_;
+                    const int N = d.num_bodies, n = d.num_velocities, b0 = c.first_body_;
+                    for (int i = b0; i < b0 + N; i++)
+                    {
+                        const int p = m_.bodies()[i].parent_index_;
+                        Xa[i] = p >= 0 ? bk_[i].Xl * Xa[p] : bk_[i].Xl;
+                        if (slot[i] >= 0)
+                        {
+                            SV fw;
+                            for (int k = 0; k < 6; k++)
+                                fw[k] = Sym::input(IN_YD, 6 * slot[i] + k);
+                            f[i] = Xa[i].applyForce(fw);
+                        }
+                    }
+                    for (int ch : children_[ci])
+                        visit(ch);
+                    for (int i = b0 + N - 1; i >= b0; i--)
+                    {
+                        const int p = m_.bodies()[i].parent_index_;
+                        if (isFree(d))
+                            for (int k = 0; k < 6; k++)
+                                tau[c.velocity_index_ + k] = f[i][k];
+                        else
+                        {
+                            const Sym tau_s = f[i][(int)d.axes[i - b0]];
+                            for (int k = 0; k < n; k++)
+                                tau[c.velocity_index_ + k] = tau[c.velocity_index_ + k] + ck_[ci].G[(i - b0) * n + k] * tau_s;
+                        }
+                        if (p >= 0)
+                            f[p] = f[p] + bk_[i].Xl.applyForceTranspose(f[i]);
+                    }
+                };
+                for (int r : roots_)
+                    visit(r);
+                std::vector<Sym> out(nv);
+                for (int k = 0; k < nv; k++)
+                {
+                    const Sym t = Sym::input(IN_AUX, k);
+                    out[k] = sign > 0 ? t + tau[k] : t - tau[k];
+                }
+                return out;
+            }
+
+            // ---------------------------------------------------------------------------------
             // inverse dynamics: spanning-tree RNEA + projection tau = G^T tau_s
             // ---------------------------------------------------------------------------------
             std::vector<Sym> inverseDynamics()

@@ -18,16 +18,20 @@ namespace grbda
             ALGO_FK = 2,      // in: q, yd        out: p[3 Nb], R[9 Nb], v[6 Nb]
             ALGO_H = 3,       // in: q            out: H[nv nv]
             ALGO_PHI = 4,     // in: q            out: phi[sum nc], Kd (row-major per implicit cluster)
-            ALGO_COUNT = 5,   // entry points / registry slots
+            // generalized force of external forces on the model's terminal links (ModelCompiler::
+            // externalForceBodies): in: q, f_ext[6 nf] (world frame, TreeModel::setExternalForces), tau_in
+            ALGO_GFA = 5,     // out: tau_in + J^T f_ext   (forward dynamics with external forces: FD(.., tau + J^T f))
+            ALGO_GFS = 6,     // out: tau_in - J^T f_ext   (inverse dynamics with external forces: ID(..) - J^T f)
+            ALGO_COUNT = 7,   // entry points / registry slots
             // alternative programs of an entry point (selected per kernel variant, same I/O as the entry)
-            PROGRAM_FD_LTL = 5, // forward dynamics as H^-1 (tau - C): CRBA + RNEA bias + sparse L^T D L
-            PROGRAM_COUNT = 6
+            PROGRAM_FD_LTL = 7, // forward dynamics as H^-1 (tau - C): CRBA + RNEA bias + sparse L^T D L
+            PROGRAM_COUNT = 8
         };
         // registry slot a program belongs to
         inline int algoOfProgram(int program) { return program == PROGRAM_FD_LTL ? ALGO_FD : program; }
         inline const char *algoName(int a)
         {
-            static const char *names[] = {"id", "fd", "fk", "h", "phi", "fd_ltl"};
+            static const char *names[] = {"id", "fd", "fk", "h", "phi", "gfa", "gfs", "fd_ltl"};
             return names[a];
         }
 
@@ -65,6 +69,11 @@ namespace grbda
             case PROGRAM_FD_LTL:
                 p.n_in[0] = nq, p.n_in[1] = nv, p.n_in[2] = nv;
                 p.outputs.push_back(mc.forwardDynamicsLTL());
+                break;
+            case ALGO_GFA:
+            case ALGO_GFS:
+                p.n_in[0] = nq, p.n_in[1] = 6 * (int)ModelCompiler::externalForceBodies(model).size(), p.n_in[2] = nv;
+                p.outputs.push_back(mc.generalizedExternalForce(algo == ALGO_GFA ? 1 : -1));
                 break;
             case ALGO_FK:
             {

@@ -502,15 +502,18 @@ namespace grbda_kernels
         if (!GRBDA_RANGE_CHECKED(Body))
             return cudaSuccess;
         using L = TileLayout<Body, real, BLOCK>;
-        auto kernel = grbda_batched_kernel<real, Body, BLOCK, MIN_BLOCKS, true, false>;
-        if (L::BYTES > 48 * 1024)
+        // staged tiles unless the rows of this program do not fit into shared memory (then direct I/O)
+        constexpr bool STAGED = L::BYTES <= 200 * 1024;
+        constexpr size_t SMEM = STAGED ? L::BYTES : stageBytes<Body, real, BLOCK>();
+        auto kernel = grbda_batched_kernel<real, Body, BLOCK, MIN_BLOCKS, STAGED, false>;
+        if (SMEM > 48 * 1024)
         {
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES);
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
             if (e != cudaSuccess)
                 return e;
         }
         const int64_t grid = (tiles + BLOCK - 1) / BLOCK;
-        kernel<<<(unsigned)grid, BLOCK, L::BYTES, a.stream>>>(
+        kernel<<<(unsigned)grid, BLOCK, SMEM, a.stream>>>(
             (const real *)a.in[0], (const real *)a.in[1], (const real *)a.in[2], (real *)a.out[0],
             (real *)a.out[1], (real *)a.out[2], a.batch, flags);
         if (a.launched)

@@ -41,11 +41,13 @@ struct grbda_model
         size_t bytes = 0;
     };
     mutable std::mutex scratch_mutex;
-    mutable std::map<cudaStream_t, Scratch> scratch;
-    unsigned char *scratchFor(cudaStream_t stream, size_t bytes) const
+    mutable std::string scratch_error;
+    mutable std::map<std::pair<cudaStream_t, int>, Scratch> scratch;
+    // slot 0: tile flags of a launch; slot 1: intermediate generalized forces of the *_ext entry points
+    unsigned char *scratchFor(cudaStream_t stream, size_t bytes, int slot = 0) const
     {
         std::lock_guard<std::mutex> lock(scratch_mutex);
-        Scratch &sc = scratch[stream];
+        Scratch &sc = scratch[{stream, slot}];
         if (sc.bytes < bytes)
         {
             if (sc.ptr)
@@ -56,8 +58,13 @@ struct grbda_model
             sc.ptr = nullptr;
             sc.bytes = 0;
             const size_t want = std::max<size_t>(bytes * 2, 1 << 16);
-            if (cudaMalloc((void **)&sc.ptr, want) != cudaSuccess)
+            const cudaError_t e = cudaMalloc((void **)&sc.ptr, want);
+            if (e != cudaSuccess)
+            {
+                scratch_error = cudaGetErrorString(e);
+                sc.ptr = nullptr;
                 return nullptr;
+            }
             sc.bytes = want;
         }
         return sc.ptr;
@@ -183,7 +190,7 @@ namespace
         a.flags_bytes = (size_t)((batch + 31) / 32);
         a.flags = m->scratchFor(a.stream, a.flags_bytes);
         if (!a.flags)
-            return fail(GRBDA_ERR_CUDA, "cannot allocate the kernel scratch buffer");
+            return fail(GRBDA_ERR_CUDA, "cannot allocate the kernel scratch buffer: " + m->scratch_error);
         int launched = 0;
         a.launched = &launched;
         cudaError_t e = fn(a);
@@ -367,7 +374,7 @@ extern "C"
 
     grbda_status grbda_cuda_dump_role_program(const grbda_model *m, int algo, const char *path, int64_t *info4)
     {
-        if (!m || algo < 0 || algo >= compiler::PROGRAM_COUNT)
+        if (!m || algo < 0 || algo >= compiler::PROGRAM_COUNT || algo == compiler::ALGO_GFA || algo == compiler::ALGO_GFS)
             return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
         return guarded([&]
                        {
@@ -403,6 +410,59 @@ extern "C"
     {
         return launchAlgo(m, compiler::ALGO_FD, false, q, yd, tau, ydd, nullptr, nullptr, batch, stream);
     }
+    // ---- external forces on the terminal links ------------------------------------------------
+    grbda_status grbda_cuda_external_force_bodies(const grbda_model *m, int32_t *body_indices, int32_t *count)
+    {
+        if (!m || !count)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        return guarded([&]
+                       {
+            const std::vector<int> b = compiler::ModelCompiler::externalForceBodies(m->model);
+            *count = (int32_t)b.size();
+            if (body_indices)
+                for (size_t i = 0; i < b.size(); i++)
+                    body_indices[i] = b[i];
+            return (grbda_status)GRBDA_OK; });
+    }
+    grbda_status grbda_cuda_inverse_dynamics_ext_f64(const grbda_model *m, const double *q, const double *yd,
+                                                     const double *ydd, const double *f_ext, double *tau,
+                                                     int64_t batch, void *stream)
+    {
+        if (!f_ext)
+            return launchAlgo(m, compiler::ALGO_ID, false, q, yd, ydd, tau, nullptr, nullptr, batch, stream);
+        if (!m || batch < 0)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        if (batch == 0)
+            return GRBDA_OK;
+        const size_t bytes = (size_t)batch * m->model.getNumDegreesOfFreedom() * sizeof(double);
+        double *tmp = (double *)m->scratchFor((cudaStream_t)stream, bytes, 1);
+        if (!tmp)
+            return fail(GRBDA_ERR_CUDA, "cannot allocate the intermediate generalized-force buffer: " + m->scratch_error);
+        grbda_status st = launchAlgo(m, compiler::ALGO_ID, false, q, yd, ydd, tmp, nullptr, nullptr, batch, stream);
+        if (st != GRBDA_OK)
+            return st;
+        return launchAlgo(m, compiler::ALGO_GFS, false, q, f_ext, tmp, tau, nullptr, nullptr, batch, stream);
+    }
+    grbda_status grbda_cuda_forward_dynamics_ext_f64(const grbda_model *m, const double *q, const double *yd,
+                                                     const double *tau, const double *f_ext, double *ydd,
+                                                     int64_t batch, void *stream)
+    {
+        if (!f_ext)
+            return launchAlgo(m, compiler::ALGO_FD, false, q, yd, tau, ydd, nullptr, nullptr, batch, stream);
+        if (!m || batch < 0)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        if (batch == 0)
+            return GRBDA_OK;
+        const size_t bytes = (size_t)batch * m->model.getNumDegreesOfFreedom() * sizeof(double);
+        double *tmp = (double *)m->scratchFor((cudaStream_t)stream, bytes, 1);
+        if (!tmp)
+            return fail(GRBDA_ERR_CUDA, "cannot allocate the intermediate generalized-force buffer: " + m->scratch_error);
+        grbda_status st = launchAlgo(m, compiler::ALGO_GFA, false, q, f_ext, tau, tmp, nullptr, nullptr, batch, stream);
+        if (st != GRBDA_OK)
+            return st;
+        return launchAlgo(m, compiler::ALGO_FD, false, q, yd, tmp, ydd, nullptr, nullptr, batch, stream);
+    }
+
     grbda_status grbda_cuda_forward_dynamics_f32(const grbda_model *m, const float *q, const float *yd,
                                                  const float *tau, float *ydd, int64_t batch, void *stream)
     {

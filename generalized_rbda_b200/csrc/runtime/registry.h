@@ -41,7 +41,7 @@ namespace grbda_runtime
         uint64_t hash;
         const char *name;
         int nq, nv, nb, nc;
-        AlgoKernels algo[5]; // id, fd, fk, h, phi
+        AlgoKernels algo[7]; // id, fd, fk, h, phi, gfa, gfs (compiler::ALGO_COUNT)
         GenFn generate;
     };
 

@@ -232,7 +232,7 @@ int main(int argc, char **argv)
                 if (v.kind != 'R' && !by_sync.count(bodyKey(v)))
                     by_sync[bodyKey(v)] = compileAlgo(model, programOf(v), true, v.sync, &consts, out_chunk, v.park);
                 const Variant u = f32Variant(v);
-                if (f32 && v.kind != 'R' && !by_sync.count(bodyKey(u)))
+                if (v.kind != 'R' && !by_sync.count(bodyKey(u))) // also the body of the direct-I/O fallback
                     by_sync[bodyKey(u)] = compileAlgo(model, programOf(u), true, u.sync, &consts, out_chunk, false);
             }
             if (a == ALGO_PHI && c.n_out[0] == 0)
@@ -260,7 +260,21 @@ int main(int argc, char **argv)
                 emitRoleStruct(os, "RoleBody", roles);
             os << "} // namespace\n\n";
             auto launcher = [&](const Variant &v0, const char *real) {
-                const Variant v = std::string(real) == "float" ? f32Variant(v0) : v0;
+                Variant v = std::string(real) == "float" ? f32Variant(v0) : v0;
+                // staged shells keep every input row (and a small output row) of the CTA in shared memory;
+                // a program whose rows do not fit twice into an SM falls back to direct global I/O
+                if (v.kind == 'T' || v.kind == 'S')
+                {
+                    const size_t elem = std::string(real) == "float" ? 4 : 8;
+                    const size_t rows = (size_t)c.n_in[0] + c.n_in[1] + c.n_in[2] + 6 + (c.n_out[0] <= 64 ? c.n_out[0] + 2 : 0);
+                    if (rows * elem * v.block > 105 * 1024)
+                    {
+                        v.kind = 'D';
+                        v.park = false;
+                        if (!by_sync.count(bodyKey(v)))
+                            throw std::runtime_error("internal: direct-I/O body missing");
+                    }
+                }
                 std::ostringstream l;
                 if (v.kind == 'R' && have_roles)
                     l << "&launchRoles<" << real << ", RoleBody, " << v.min_blocks << ">";

@@ -137,12 +137,12 @@ grbda_status grbda_cuda_cluster_phi(const grbda_model *m, int cluster, grbda_phi
 /* explicit cluster: G (num_bodies x num_independent, row-major) */
 grbda_status grbda_cuda_cluster_G(const grbda_model *m, int cluster, double *G);
 /* Emitted program of one algorithm (0 ID, 1 FD (articulated-body sweep), 2 FK, 3 H, 4 phi/Kd,
- * 5 FD as H^-1 (tau - C): cluster CRBA + RNEA bias + branch-sparse L^T D L) written as a binary tape to
+ * 5 / 6 tau_in +/- J^T f_ext, 7 FD as H^-1 (tau - C): cluster CRBA + RNEA bias + branch-sparse L^T D L) written as a binary tape to
  * `path` (format: csrc/compiler/compile.h); counts[8] = {nodes, add, mul, div, sqrt, sin, cos,
  * fusable mul+add pairs} of the straight-line program each thread executes. */
 grbda_status grbda_cuda_dump_program(const grbda_model *m, int algo, const char *path, int64_t *counts8);
 
-/* The CUDA source the model compiler emits for one program (0 ID, 1 FD, 2 FK, 3 H, 4 phi, 5 FD/LTDL):
+/* The CUDA source the model compiler emits for one program (0 ID, 1 FD, 2 FK, 3 H, 4 phi, 5/6 external-force programs, 7 FD/LTDL):
  * constant table + `struct Body` (sizes, generated range check, run<real, FAST>()), exactly what
  * build.py feeds to nvcc, written to `path`. park != 0: the variant that parks long-lived values in the
  * thread's shared-memory tile row. Used by the emitter self test, which compiles this text for the
@@ -150,8 +150,8 @@ grbda_status grbda_cuda_dump_program(const grbda_model *m, int algo, const char 
 grbda_status grbda_cuda_emit_source(const grbda_model *m, int program, int park, const char *path);
 
 /* Operation counts (same 8 fields) of the program the DEFAULT compiled kernel of entry point `algo`
- * (0 ID, 1 FD, 2 FK, 3 H, 4 phi) executes per state. It can differ from dump_program(algo): the default
- * forward-dynamics kernel of a model may run program 5 (CRBA + bias + sparse L^T D L) instead of the
+ * (0 ID, 1 FD, 2 FK, 3 H, 4 phi, 5 gfa, 6 gfs) executes per state. It can differ from dump_program(algo): the default
+ * forward-dynamics kernel of a model may run program 7 (CRBA + bias + sparse L^T D L) instead of the
  * articulated-body sweep (program 1); both are ClusterTreeModel::forwardDynamics
  * (ClusterTreeDynamics.cpp:10-19 / :59-155) up to rounding. */
 grbda_status grbda_cuda_kernel_counts(const grbda_model *m, int algo, int64_t *counts8);
@@ -168,6 +168,19 @@ grbda_status grbda_cuda_inverse_dynamics_f64(const grbda_model *m, const double 
                                              const double *ydd, double *tau, int64_t batch, void *stream);
 grbda_status grbda_cuda_inverse_dynamics_f32(const grbda_model *m, const float *q, const float *yd,
                                              const float *ydd, float *tau, int64_t batch, void *stream);
+/* External forces (TreeModel::setExternalForces, src/Dynamics/TreeModel.cpp:215-239; applied at
+ * TreeModel.cpp:189-193 and ClusterTreeDynamics.cpp:100-105). Supported on the model's terminal links
+ * (leaf bodies that are not motor rotors: feet, hands, chain tips): body_indices receives their body
+ * indices in the order the f_ext arrays use; pass body_indices = NULL to query the count.
+ * f_ext[batch][count][6] = one spatial force [n; f] per listed body, in WORLD coordinates as the
+ * reference takes them. f_ext = NULL means no external forces. */
+grbda_status grbda_cuda_external_force_bodies(const grbda_model *m, int32_t *body_indices, int32_t *count);
+grbda_status grbda_cuda_inverse_dynamics_ext_f64(const grbda_model *m, const double *q, const double *yd,
+                                                 const double *ydd, const double *f_ext, double *tau,
+                                                 int64_t batch, void *stream);
+grbda_status grbda_cuda_forward_dynamics_ext_f64(const grbda_model *m, const double *q, const double *yd,
+                                                 const double *tau, const double *f_ext, double *ydd,
+                                                 int64_t batch, void *stream);
 /* ydd = FD(q, yd, tau). Replaces setState + ClusterTreeModel::forwardDynamics(tau),
  * src/Dynamics/ClusterTreeDynamics.cpp:85-191. */
 grbda_status grbda_cuda_forward_dynamics_f64(const grbda_model *m, const double *q, const double *yd,

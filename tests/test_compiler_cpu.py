@@ -12,6 +12,7 @@ from tape import load_role_tape, load_tape, run_role_tape, run_tape
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # product robot name -> oracle robot name
+LTL = 7  # grbda.PROGRAM_FD_LTL
 ROBOTS = {"tello": "tello", "tello_with_arms": "tello_with_arms",
           "revolute_chain_with_rotor_2": "revolute_chain_with_rotor_2",
           "revolute_chain_with_rotor_4": "revolute_chain_with_rotor_4",
@@ -359,15 +360,15 @@ def test_emitted_cuda_text_on_the_host(grbda, oracle, robot, tmp_path):
     o = oracle.OracleModel(robot) if robot in ROBOTS else mirror_to_oracle(m, oracle)
     q, yd, aux = o.generate_states(24, seed=29)
     ins = [q, yd, aux]
-    want = {0: o.inverse_dynamics(q, yd, aux), 1: o.forward_dynamics(q, yd, aux), 5: o.forward_dynamics(q, yd, aux),
+    want = {0: o.inverse_dynamics(q, yd, aux), 1: o.forward_dynamics(q, yd, aux), LTL: o.forward_dynamics(q, yd, aux),
             3: o.mass_matrix(q).reshape(q.shape[0], -1)}
-    for program, park in [(0, False), (0, True), (1, False), (5, False), (5, True), (3, False)]:
+    for program, park in [(0, False), (0, True), (1, False), (LTL, False), (LTL, True), (3, False)]:
         outs, in_range, text = run_emitted_source(m, program, park, ins[:3 if program != 3 else 1] + [], tmp_path,
                                                   "p%d_%d" % (program, park))
         assert rel(outs[0], want[program]) < TOL, (program, park)
         assert in_range == q.shape[0]
         if park and robot == "tello_with_arms":
-            assert "PARKED = true" in text and text.count("PARK_ST(") >= (50 if program == 5 else 5)
+            assert "PARKED = true" in text and text.count("PARK_ST(") >= (50 if program == LTL else 5)
     # forward kinematics: three chunk-staged output arrays
     p, R, v = o.forward_kinematics(q, yd)
     outs, in_range, text = run_emitted_source(m, 2, False, [q, yd], tmp_path, "fk")
@@ -423,7 +424,7 @@ def test_urdf_corpus(grbda, oracle, stem, tmp_path):
     q, yd, aux = o.generate_states(6, seed=3)
     assert o.validate_states(q).all()
     ins = [q, yd, aux]
-    want = {0: o.inverse_dynamics(q, yd, aux), 1: o.forward_dynamics(q, yd, aux), 5: o.forward_dynamics(q, yd, aux),
+    want = {0: o.inverse_dynamics(q, yd, aux), 1: o.forward_dynamics(q, yd, aux), LTL: o.forward_dynamics(q, yd, aux),
             3: o.mass_matrix(q).reshape(q.shape[0], -1)}
     for program, ref_out in want.items():
         tape = str(tmp_path / ("p%d.tape" % program))
@@ -433,3 +434,37 @@ def test_urdf_corpus(grbda, oracle, stem, tmp_path):
     m.dump_program(2, str(tmp_path / "fk.tape"))
     fk = run_tape(load_tape(str(tmp_path / "fk.tape")), ins)
     assert rel(fk[0].reshape(p.shape), p) < TOL and rel(fk[1].reshape(R.shape), R) < TOL and rel(fk[2].reshape(v.shape), v) < TOL
+
+
+@pytest.mark.parametrize("robot", ["tello_with_arms", "mini_cheetah", "four_bar", "revolute_chain_with_rotor_4"])
+def test_external_force_programs(grbda, oracle, robot, tmp_path):
+    """External forces on the terminal links (TreeModel::setExternalForces): the programs tau_in +/- J^T f
+    against the oracle's RNEA / ABA with f_ext (ID_ext = ID - J^T f, FD_ext(tau) = FD(tau + J^T f))."""
+    from mirror import mirror_to_oracle
+    m = grbda.ClusterTreeModel.from_robot(robot, device=None)
+    o = oracle.OracleModel(ROBOTS[robot]) if robot in ROBOTS and robot != "four_bar" else mirror_to_oracle(m, oracle)
+    bodies = m.externalForceBodies()
+    names = [m.bodies()[b]["name"] for b in bodies]
+    assert bodies and not any("rotor" in n for n in names)
+    if robot == "tello_with_arms":
+        assert names == ["left-foot", "right-foot", "left-elbow-link", "right-elbow-link"]
+    q, yd, aux = o.generate_states(16, seed=31)
+    rng = np.random.default_rng(5)
+    f = rng.uniform(-20, 20, size=(q.shape[0], len(bodies), 6))
+    f_full = np.zeros((q.shape[0], o.nb, 6))
+    f_full[:, bodies, :] = f
+    tapes = {}
+    for prog, name in ((grbda.ALGO_GFA, "gfa"), (grbda.ALGO_GFS, "gfs")):
+        path = str(tmp_path / name)
+        m.dump_program(prog, path)
+        tapes[name] = load_tape(path)
+    f_flat = f.reshape(q.shape[0], -1)
+    # inverse dynamics: ID - J^T f
+    tau_plain = o.inverse_dynamics(q, yd, aux)
+    tau_ext = o.dynamics_with_external_forces(q, yd, aux, f_full, forward=False)
+    assert rel(run_tape(tapes["gfs"], [q, f_flat, tau_plain])[0], tau_ext) < TOL
+    assert rel(tau_ext, tau_plain) > 1e-3    # the forces matter
+    # forward dynamics: FD(tau + J^T f)
+    tau_eff = run_tape(tapes["gfa"], [q, f_flat, aux])[0]
+    ydd_ext = o.dynamics_with_external_forces(q, yd, aux, f_full, forward=True)
+    assert rel(o.forward_dynamics(q, yd, tau_eff), ydd_ext) < 1e-9

@@ -111,6 +111,31 @@ def test_every_compiled_kernel_variant(grbda, oracle, torch, robot, monkeypatch)
     assert ran >= 2
 
 
+@pytest.mark.parametrize("robot", ["tello_with_arms", "mini_cheetah", "mit_humanoid", "four_bar", "jvrc1_humanoid"])
+def test_external_forces(grbda, oracle, torch, robot):
+    """grbda_cuda_{inverse,forward}_dynamics_ext_f64: world-frame spatial forces on the terminal links
+    (TreeModel::setExternalForces) against the oracle's RNEA / ABA with external forces."""
+    m = grbda.ClusterTreeModel.from_robot(robot)
+    o = oracle_for(oracle, m, robot)
+    bodies = m.externalForceBodies()
+    B = 300
+    q, yd, aux, _ = m.generateStates(B, seed=17)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    f = (torch.rand((B, len(bodies), 6), dtype=torch.float64, device="cuda", generator=g) - 0.5) * 40.0
+    qn, ydn, auxn = q.cpu().numpy(), yd.cpu().numpy(), aux.cpu().numpy()
+    f_full = np.zeros((B, o.nb, 6))
+    f_full[:, bodies, :] = f.cpu().numpy()
+    tau = m.inverseDynamics(q, yd, aux, f_ext=f)
+    assert relrows(tau.cpu().numpy(), o.dynamics_with_external_forces(qn, ydn, auxn, f_full, forward=False)) < TOL64
+    ydd = m.forwardDynamics(q, yd, aux, f_ext=f)
+    assert relrows(ydd.cpu().numpy(), o.dynamics_with_external_forces(qn, ydn, auxn, f_full, forward=True)) < TOL64
+    # consistency: ID_ext(FD_ext(tau)) = tau, and zero forces reproduce the plain entry points bit for bit
+    back = m.inverseDynamics(q, yd, ydd, f_ext=f)
+    assert float(((back - aux).abs().amax(1) / aux.abs().amax(1)).median()) < 1e-9
+    zero = torch.zeros_like(f)
+    assert torch.equal(m.forwardDynamics(q, yd, aux, f_ext=zero), m.forwardDynamics(q, yd, aux))
+
+
 @pytest.mark.parametrize("dtype_name", ["float64", "float32"])
 def test_angles_beyond_the_fast_sincos_range(grbda, oracle, torch, dtype_name):
     """Joint angles beyond the range of the branch-free sin/cos reduction (arguments up to 1e12 in FP64, 1e6 in FP32):
