@@ -14,8 +14,10 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_fp64.sum", "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_alu.sum",
         "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
-        "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", "sm__cycles_elapsed.max"]
+        "smsp__sass_thread_inst_executed_op_dfma_pred_on.avg.per_cycle_elapsed",
+        "smsp__sass_thread_inst_executed_op_dmul_pred_on.avg.per_cycle_elapsed",
+        "smsp__sass_thread_inst_executed_op_dadd_pred_on.avg.per_cycle_elapsed",
+        "sm__sass_thread_inst_executed_op_dfma_pred_on.avg.peak_sustained", "sm__cycles_elapsed.max"]
 
 
 def summarise(path):
