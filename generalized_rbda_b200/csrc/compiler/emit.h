@@ -4,6 +4,8 @@
 //       compiler self-tests in tests/ (a numpy interpreter replays it against the oracle),
 //   (c) exact operation counts of the emitted program.
 #pragma once
+#include <functional>
+#include <cstdlib>
 #include <iomanip>
 #include <algorithm>
 #include <cmath>
@@ -426,6 +428,107 @@ namespace grbda
                             neg_outputs_of[k].push_back(id);
                     }
 
+                // ---- sums as FMA chains ------------------------------------------------------------
+                // ((a b + c d) + x) compiles to mul, fma, add; (a b + (c d + x)) to two fmas. A sum node
+                // whose only consumer is another sum (possibly through a negation) and that is not an
+                // output is therefore not emitted on its own: it is merged into its consumer, and the
+                // merged n-ary sum is emitted with the non-product terms first and every single-use
+                // product after them, so that each product contracts into one FMA of the running sum.
+                // (Changes the rounding order, not the value; GRBDA_NO_SUM_CHAINS=1 at model-compile
+                // time keeps the binary form for comparison.)
+                std::vector<char> merged(g_.nodes.size(), 0);
+                std::vector<int32_t> host_of(g_.nodes.size(), -1); // statement a node ends up in
+                if (!std::getenv("GRBDA_NO_SUM_CHAINS"))
+                {
+                    const int32_t N = (int32_t)g_.nodes.size();
+                    std::vector<int32_t> single_user(N, -1);
+                    for (int32_t i = 0; i < N; i++)
+                    {
+                        if (!live_[i])
+                            continue;
+                        const sym::Node &n = g_.nodes[i];
+                        if (n.op == sym::OP_CONST || n.op == sym::OP_INPUT)
+                            continue;
+                        for (int32_t o : {n.a, n.b, n.c, n.e})
+                            if (o >= 0 && uses_[o] == 1)
+                                single_user[o] = i;
+                    }
+                    auto isSum = [&](int32_t id) { return g_.nodes[id].op == sym::OP_ADD || g_.nodes[id].op == sym::OP_SUB; };
+                    for (int32_t x = 0; x < N; x++)
+                    {
+                        if (!live_[x] || !isSum(x) || uses_[x] != 1 || !stores[x].empty() || !neg_outputs_of[x].empty())
+                            continue;
+                        int32_t u = single_user[x];
+                        while (u >= 0 && g_.nodes[u].op == sym::OP_NEG)
+                        {
+                            if (uses_[u] != 1 || !stores[u].empty())
+                            {
+                                u = -1;
+                                break;
+                            }
+                            u = single_user[u];
+                        }
+                        // only local merges: a running sum that collects contributions across the whole
+                        // program (Schur complements, forces handed up the tree) must stay a sequence of
+                        // statements, or every product waits for the last one (measured: frame 264 B -> 4.6 KB)
+                        if (u >= 0 && isSum(u) && u - x <= 40)
+                            merged[x] = 1, host_of[x] = u;
+                    }
+                    // a chain of merges must stay local as a whole
+                    for (int32_t x = 0; x < N; x++)
+                        if (merged[x])
+                        {
+                            int32_t h = x;
+                            while (merged[h])
+                                h = host_of[h];
+                            if (h - x > 120)
+                                merged[x] = 0;
+                        }
+                }
+                auto statementOf = [&](int32_t id) {
+                    while (merged[id])
+                        id = host_of[id];
+                    return id;
+                };
+                // terms of the n-ary sum rooted at a (not merged) sum node
+                std::function<void(int32_t, int, std::vector<std::pair<int, int32_t>> &)> sumTerms =
+                    [&](int32_t id, int sign, std::vector<std::pair<int, int32_t>> &terms) {
+                        const sym::Node &n = g_.nodes[id];
+                        const int32_t ops[2] = {n.a, n.b};
+                        const int sg[2] = {sign, n.op == sym::OP_ADD ? sign : -sign};
+                        for (int k = 0; k < 2; k++)
+                        {
+                            int32_t o = ops[k];
+                            int s2 = sg[k];
+                            while (g_.nodes[o].op == sym::OP_NEG)
+                                s2 = -s2, o = g_.nodes[o].a;
+                            if (merged[o])
+                                sumTerms(o, s2, terms);
+                            else
+                                terms.push_back({s2, o});
+                        }
+                    };
+                auto sumExpression = [&](int32_t id) {
+                    std::vector<std::pair<int, int32_t>> terms, ordered;
+                    sumTerms(id, 1, terms);
+                    for (auto &t : terms) // non-products first: they seed the chain
+                        if (!(g_.nodes[t.second].op == sym::OP_MUL && uses_[t.second] == 1))
+                            ordered.push_back(t);
+                    for (auto &t : terms)
+                        if (g_.nodes[t.second].op == sym::OP_MUL && uses_[t.second] == 1)
+                            ordered.push_back(t);
+                    std::string e;
+                    for (size_t k = 0; k < ordered.size(); k++)
+                    {
+                        const std::string r = ref(ordered[k].second);
+                        if (k == 0)
+                            e = ordered[k].first > 0 ? r : "(-" + r + ")";
+                        else
+                            e = "(" + e + (ordered[k].first > 0 ? " + " : " - ") + r + ")";
+                    }
+                    return e;
+                };
+
                 // ---- parking plan (positions are node ids: statements are emitted in id order) ----
                 std::vector<std::vector<Parked>> park_store_after(g_.nodes.size()), park_load_before(g_.nodes.size());
                 bool any_chunked = false;
@@ -450,10 +553,21 @@ namespace grbda
                         const sym::Node &n = g_.nodes[i];
                         if (n.op == sym::OP_CONST || n.op == sym::OP_NEG || n.op == sym::OP_INPUT)
                             continue;
+                        if (merged[i])
+                            continue; // its operands are read by the statement it is merged into (below)
                         // a cosine emitted together with its sine is defined at the earlier of the two
                         int32_t pos = i;
                         if ((n.op == sym::OP_SIN || n.op == sym::OP_COS) && partner_[i] >= 0 && live_[partner_[i]])
                             pos = std::min<int32_t>(i, partner_[i]);
+                        if (n.op == sym::OP_ADD || n.op == sym::OP_SUB)
+                        {
+                            std::vector<std::pair<int, int32_t>> terms;
+                            sumTerms(i, 1, terms);
+                            for (auto &t : terms)
+                                if (g_.nodes[t.second].op != sym::OP_CONST && g_.nodes[t.second].op != sym::OP_INPUT)
+                                    access[t.second].push_back(pos);
+                            continue;
+                        }
                         for (int32_t o : {n.a, n.b, n.c, n.e})
                             if (o >= 0)
                             {
@@ -486,7 +600,7 @@ namespace grbda
                     std::vector<Cand> cands;
                     for (int32_t x = 0; x < N; x++)
                     {
-                        if (!live_[x] || access[x].empty())
+                        if (!live_[x] || access[x].empty() || merged[x])
                             continue;
                         const sym::Node &n = g_.nodes[x];
                         if (n.op == sym::OP_CONST || n.op == sym::OP_NEG || n.op == sym::OP_INPUT)
@@ -568,6 +682,8 @@ namespace grbda
                             }
                         continue;
                     }
+                    if (merged[i])
+                        continue; // part of the sum statement of statementOf(i)
                     if (done[i])
                     {
                         emitStores(i);
@@ -583,10 +699,8 @@ namespace grbda
                         os << "const real t" << i << " = IN" << n.a << "(" << n.b << ");\n";
                         break;
                     case sym::OP_ADD:
-                        os << "const real t" << i << " = " << ref(n.a) << " + " << ref(n.b) << ";\n";
-                        break;
                     case sym::OP_SUB:
-                        os << "const real t" << i << " = " << ref(n.a) << " - " << ref(n.b) << ";\n";
+                        os << "const real t" << i << " = " << sumExpression((int32_t)i) << ";\n";
                         break;
                     case sym::OP_MUL:
                         os << "const real t" << i << " = " << ref(n.a) << " * " << ref(n.b) << ";\n";

@@ -262,12 +262,12 @@ int main(int argc, char **argv)
             auto launcher = [&](const Variant &v0, const char *real) {
                 Variant v = std::string(real) == "float" ? f32Variant(v0) : v0;
                 // staged shells keep every input row (and a small output row) of the CTA in shared memory;
-                // a program whose rows do not fit twice into an SM falls back to direct global I/O
+                // a program whose rows do not fit into an SM at all falls back to direct global I/O
                 if (v.kind == 'T' || v.kind == 'S')
                 {
                     const size_t elem = std::string(real) == "float" ? 4 : 8;
                     const size_t rows = (size_t)c.n_in[0] + c.n_in[1] + c.n_in[2] + 6 + (c.n_out[0] <= 64 ? c.n_out[0] + 2 : 0);
-                    if (rows * elem * v.block > 105 * 1024)
+                    if (rows * elem * v.block > 220 * 1024) // not even one CTA per SM
                     {
                         v.kind = 'D';
                         v.park = false;
