@@ -441,6 +441,8 @@ namespace grbda
                 if (!std::getenv("GRBDA_NO_SUM_CHAINS"))
                 {
                     const int32_t N = (int32_t)g_.nodes.size();
+                    const char *dist = std::getenv("GRBDA_SUM_CHAIN_DIST"); // tuning experiments
+                    const int32_t local = dist ? std::atoi(dist) : 40;
                     std::vector<int32_t> single_user(N, -1);
                     for (int32_t i = 0; i < N; i++)
                     {
@@ -471,7 +473,7 @@ namespace grbda
                         // only local merges: a running sum that collects contributions across the whole
                         // program (Schur complements, forces handed up the tree) must stay a sequence of
                         // statements, or every product waits for the last one (measured: frame 264 B -> 4.6 KB)
-                        if (u >= 0 && isSum(u) && u - x <= 40)
+                        if (u >= 0 && isSum(u) && u - x <= local)
                             merged[x] = 1, host_of[x] = u;
                     }
                     // a chain of merges must stay local as a whole
@@ -481,7 +483,7 @@ namespace grbda
                             int32_t h = x;
                             while (merged[h])
                                 h = host_of[h];
-                            if (h - x > 120)
+                            if (h - x > 3 * local)
                                 merged[x] = 0;
                         }
                 }
