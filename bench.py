@@ -282,7 +282,7 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * n_e2e / float(dt.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(B * (m.nq + 2 * m.nv) * 8), "d2h_bytes_per_step": int(2 * B * m.nv * 8),
-               "steps": n_e2e, "api": "grbda_cuda_forward_inverse_host_f64 (pinned host buffers, 64k-state "
+               "steps": n_e2e, "api": "grbda_cuda_forward_inverse_host_f64 (pinned host buffers, 128k-state "
                                       "chunks pipelined over 3 streams)"}
         assert torch.equal(yddh, ydd.cpu())
 

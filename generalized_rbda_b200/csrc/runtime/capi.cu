@@ -502,8 +502,12 @@ extern "C"
             return cudaFail(e, "cudaSetDevice");
         const int nq = m->model.getNumPositions(), nv = m->model.getNumDegreesOfFreedom();
         const int64_t per_state = nq + 4 * (int64_t)nv; // q, yd, in3, out, out2 (doubles)
-        const int64_t chunk = 1 << 16;
-        if (m->dev_capacity < chunk)
+        // measured (tools/e2e_sweep.py, 2^20 Tello states): 16 k -> 57.6, 32 k -> 67.0, 64 k -> 70.7, 128 k -> 72.3,
+        // 256 k -> 68.6 M fwd+inv/s; the call is bound by the host link (47 GB/s in, 28 GB/s out, concurrently)
+        int64_t chunk = 1 << 17;
+        if (const char *c = std::getenv("GRBDA_HOST_CHUNK")) // tuning knob (states per pipelined chunk)
+            chunk = std::max<int64_t>(1024, std::atoll(c));
+        if (m->dev_capacity != chunk)
         {
             for (int i = 0; i < grbda_model::NSTREAM; i++)
             {
