@@ -269,6 +269,33 @@ def test_host_buffer_path(grbda, oracle, torch):
     assert torch.equal(a, ydd_h) and torch.equal(b, out)
 
 
+def test_cuda_graph_capture(grbda, oracle, torch):
+    """The batched entry points only enqueue kernels on the caller's stream (their scratch is allocated on
+    first use), so a control-loop sized step can be captured once in a CUDA graph and replayed."""
+    m = grbda.ClusterTreeModel.from_robot("tello_with_arms")
+    o = oracle.OracleModel("tello_with_arms")
+    B = 4096
+    q, yd, tau, _ = m.generateStates(B, seed=9)
+    ydd, back = torch.empty_like(tau), torch.empty_like(tau)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):               # warm-up on the capture stream: scratch buffers exist afterwards
+        m.forwardDynamics(q, yd, tau, out=ydd)
+        m.inverseDynamics(q, yd, ydd, out=back)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        m.forwardDynamics(q, yd, tau, out=ydd)
+        m.inverseDynamics(q, yd, ydd, out=back)
+    ydd.zero_(), back.zero_()
+    q2, yd2, tau2, _ = m.generateStates(B, seed=10)
+    q.copy_(q2), yd.copy_(yd2), tau.copy_(tau2)   # new inputs in the captured buffers
+    graph.replay()
+    torch.cuda.synchronize()
+    assert relrows(ydd.cpu().numpy(), o.forward_dynamics(q.cpu().numpy(), yd.cpu().numpy(), tau.cpu().numpy())) < TOL64
+    assert float(((back - tau).abs().amax(1) / tau.abs().amax(1)).median()) < 1e-9
+
+
 def test_empty_and_error_paths(grbda, torch):
     m = grbda.ClusterTreeModel.from_robot("tello")
     q = torch.zeros((0, m.nq), dtype=torch.float64, device="cuda")
