@@ -92,8 +92,10 @@ namespace grbda_kernels
         pc = fma(z, pc, K[16]);
         const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
         const double a = (k & 1) ? cr : sr, b = (k & 1) ? sr : cr;
-        *s = (k & 2) ? -a : a;
-        *c = ((k + 1) & 2) ? -b : b;
+        // quadrant signs: flip the sign bit with integer logic on the high word (one shift + one XOR per
+        // result) instead of two more 64-bit selects
+        *s = __hiloint2double(__double2hiint(a) ^ ((k & 2) << 30), __double2loint(a));
+        *c = __hiloint2double(__double2hiint(b) ^ (((k + 1) & 2) << 30), __double2loint(b));
     }
     // FP32: the same scheme (three-constant reduction, 72 bits of pi/2; degree-7/8 minimax kernels);
     // absolute error ~1e-7 for |x| <= 1e6 (k < 2^22 in the 2^23 rounding trick). FP32 parity budget: 1e-4.
@@ -121,8 +123,8 @@ namespace grbda_kernels
         pc = fmaf(z, pc, -0.5f);
         const float cr = fmaf(z, pc, 1.0f);
         const float a = (k & 1) ? cr : sr, b = (k & 1) ? sr : cr;
-        *s = (k & 2) ? -a : a;
-        *c = ((k + 1) & 2) ? -b : b;
+        *s = __int_as_float(__float_as_int(a) ^ ((k & 2) << 30));
+        *c = __int_as_float(__float_as_int(b) ^ (((k + 1) & 2) << 30));
     }
     template <bool FAST, typename real>
     __device__ __forceinline__ real grbda_sin(real x) { real s, c; grbda_sincos<FAST>(x, &s, &c); return s; }
