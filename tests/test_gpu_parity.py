@@ -296,6 +296,27 @@ def test_cuda_graph_capture(grbda, oracle, torch):
     assert float(((back - tau).abs().amax(1) / tau.abs().amax(1)).median()) < 1e-9
 
 
+def test_concurrent_streams_share_a_model(grbda, torch):
+    """Launches of one model handle on different streams use different scratch buffers (tile flags) and may
+    overlap; results equal the single-stream ones bit for bit."""
+    m = grbda.ClusterTreeModel.from_robot("tello_with_arms")
+    B = 1 << 16
+    q, yd, tau, _ = m.generateStates(B, seed=23)
+    q = q.clone()
+    q[::4099, m.clusters()[1]["position_index"]] = 5.0e13       # some tiles need the second pass
+    ref_fd, ref_id = m.forwardDynamics(q, yd, tau), m.inverseDynamics(q, yd, tau)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    outs = []
+    for rep in range(4):
+        for s in streams:
+            with torch.cuda.stream(s):
+                outs.append((m.forwardDynamics(q, yd, tau), m.inverseDynamics(q, yd, tau)))
+    torch.cuda.synchronize()
+    for fd, idn in outs:
+        assert torch.equal(fd, ref_fd) and torch.equal(idn, ref_id)
+
+
 def test_empty_and_error_paths(grbda, torch):
     m = grbda.ClusterTreeModel.from_robot("tello")
     q = torch.zeros((0, m.nq), dtype=torch.float64, device="cuda")
