@@ -297,7 +297,8 @@ namespace grbda_kernels
     // inline copies with index arithmetic made the kernels 15-19 k instructions long and
     // instruction-fetch bound (no_instructions 39 %); a shared noinline copy fixed that (FK 0.96 ->
     // 0.74 ms) but every call spilled the caller's live registers around it (500 local loads per
-    // thread, long_scoreboard 68 %). Hence: inline, pointer-increment loop, NOT unrolled.
+    // thread, long_scoreboard 68 %). Hence: inline; full warps load the 16 values of a lane first and
+    // store them afterwards (one shared-memory latency per flush), the ragged last tile uses a plain loop.
     template <typename real, int COUNT>
     __device__ __forceinline__ void flushChunkShared(real *__restrict__ g, int row_stride, const real *__restrict__ stg,
                                                   int valid)
@@ -311,12 +312,28 @@ namespace grbda_kernels
             int st = lane / OUT_CHUNK;
             const real *src = stg + st * (OUT_CHUNK + 1) + el;
             real *dst = g + (size_t)st * row_stride + el;
-#pragma unroll 1
-            for (; st < valid; st += 32 / OUT_CHUNK)
+            if (valid == 32)
             {
-                __stcs(dst, *src);
-                src += (32 / OUT_CHUNK) * (OUT_CHUNK + 1);
-                dst += (size_t)(32 / OUT_CHUNK) * row_stride;
+                // full warp (every tile but the last): all loads first, then all stores, so that the
+                // shared-memory latency is paid once per flush and not once per element
+                constexpr int STEPS = OUT_CHUNK; // 32 states / (32 / OUT_CHUNK states per step)
+                real v[STEPS];
+#pragma unroll
+                for (int k = 0; k < STEPS; k++)
+                    v[k] = src[k * (32 / OUT_CHUNK) * (OUT_CHUNK + 1)];
+#pragma unroll
+                for (int k = 0; k < STEPS; k++)
+                    __stcs(dst + (size_t)k * (32 / OUT_CHUNK) * row_stride, v[k]);
+            }
+            else
+            {
+#pragma unroll 1
+                for (; st < valid; st += 32 / OUT_CHUNK)
+                {
+                    __stcs(dst, *src);
+                    src += (32 / OUT_CHUNK) * (OUT_CHUNK + 1);
+                    dst += (size_t)(32 / OUT_CHUNK) * row_stride;
+                }
             }
         }
         else
