@@ -29,7 +29,8 @@ LIB = os.path.join(HERE, "libgrbda_cuda.so")
 # GRBDA_KERNEL_VARIANT=k selects the k-th). KIND: T = TMA-staged tiles, S = software-staged tiles,
 # D = direct global I/O, R = one warp per limb. 'ltl' = forward dynamics as CRBA + bias + sparse LTDL
 # (otherwise the articulated-body sweep); 'park' = long-lived values parked in dead slots of the thread's
-# shared-memory tile row instead of being spilled (T and S only). Measured on B200 (profiles/README.md): T,128,2 is the fastest
+# shared-memory tile row instead of being spilled (T and S only); 'f32aba' = the FP32 kernel of the variant runs the
+# articulated-body sweep. Measured on B200 (profiles/README.md): T,128,2 is the fastest
 # and the most device-independent shape for every entry point.
 DEFAULT_VARIANTS = "id=T,128,2;S,128,2|fd=T,128,2,ltl,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2"
 SYNC_EVERY = int(os.environ.get("GRBDA_SYNC_EVERY", "0"))  # alignment barriers measured useless (profiles/)
@@ -42,10 +43,16 @@ MODELS = {
     "six_bar": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
     "planar_leg_linkage": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
     "mit_humanoid_leg": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
-    "jvrc1_humanoid": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
-    "revolute_rotor_chain": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    "jvrc1_humanoid": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, True),
+    "revolute_rotor_chain": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_2": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_4": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    # depth sweep of the serial cluster chain (BASELINE config 5: deep-tree latency)
+    "revolute_chain_with_rotor_8": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    # FP32: forward dynamics of the 16-link fixed-base chain (cond(H) ~ 2e4) through the articulated-body sweep:
+    # median error 6e-7 instead of 1e-4 with the factorisation (measured, tests/test_gpu_parity.py)
+    "revolute_chain_with_rotor_16": ("id,fd,fk,h,gfa,gfs,gen",
+                                     DEFAULT_VARIANTS.replace("fd=T,128,2,ltl,park;", "fd=T,128,2,ltl,park,f32aba;"), True),
     "revolute_pair_chain_with_rotor_2": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
     "revolute_pair_chain_with_rotor_4": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
 }

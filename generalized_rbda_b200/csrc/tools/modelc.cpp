@@ -27,6 +27,8 @@ namespace
         int block, min_blocks;
         int program = -1; // alternative program of the entry point (-1: the entry's own), e.g. PROGRAM_FD_LTL
         bool park = false; // staged shells: long-lived values are parked in dead slots of the thread's tile row
+        bool f32_aba = false; // FP32 launcher of this variant runs the articulated-body sweep (deep fixed-base
+                              // chains: H^-1 in FP32 loses cond(H) digits, the O(n) recursion does not)
     };
 
     std::vector<std::string> split(const std::string &s, char sep)
@@ -153,10 +155,10 @@ int main(int argc, char **argv)
         for (auto &v : split(spec, ';'))
         {
             auto p = split(v, ',');
-            if (p.size() < 3 || p.size() > 6 || p[0].size() != 1 ||
+            if (p.size() < 3 || p.size() > 7 || p[0].size() != 1 ||
                 std::string("SDRT").find(p[0][0]) == std::string::npos)
                 throw std::runtime_error("bad --variants entry '" + v +
-                                         "' (expected KIND,BLOCK,MINBLOCKS[,SYNC][,ltl][,park])");
+                                         "' (expected KIND,BLOCK,MINBLOCKS[,SYNC][,ltl][,park][,f32aba])");
             Variant var;
             var.kind = p[0][0];
             var.block = std::atoi(p[1].c_str());
@@ -167,6 +169,8 @@ int main(int argc, char **argv)
                     var.program = PROGRAM_FD_LTL;
                 else if (p[t] == "park")
                     var.park = var.kind == 'S' || var.kind == 'T';
+                else if (p[t] == "f32aba")
+                    var.f32_aba = true;
                 else
                     var.sync = std::atoi(p[t].c_str());
             }
@@ -225,6 +229,8 @@ int main(int argc, char **argv)
             // (measured: forward dynamics 0.386 against 0.414 ms): their launchers use the unparked body
             auto f32Variant = [&](Variant v) {
                 v.park = false;
+                if (v.f32_aba)
+                    v.program = -1;
                 return v;
             };
             for (auto &v : variants)

@@ -16,6 +16,8 @@ LTL = 7  # grbda.PROGRAM_FD_LTL
 ROBOTS = {"tello": "tello", "tello_with_arms": "tello_with_arms",
           "revolute_chain_with_rotor_2": "revolute_chain_with_rotor_2",
           "revolute_chain_with_rotor_4": "revolute_chain_with_rotor_4",
+          "revolute_chain_with_rotor_8": "revolute_chain_with_rotor_8",
+          "revolute_chain_with_rotor_16": "revolute_chain_with_rotor_16",
           "revolute_pair_chain_with_rotor_2": "revolute_pair_chain_with_rotor_2",
           "revolute_pair_chain_with_rotor_4": "revolute_pair_chain_with_rotor_4"}
 TOL = 1e-10  # north_star: <= 1e-10 relative in FP64

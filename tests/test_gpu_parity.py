@@ -18,6 +18,8 @@ ROBOTS = {"tello": "tello", "tello_with_arms": "tello_with_arms",
           "mit_humanoid_leg": None, "jvrc1_humanoid": None,
           "revolute_chain_with_rotor_2": "revolute_chain_with_rotor_2",
           "revolute_chain_with_rotor_4": "revolute_chain_with_rotor_4",
+          "revolute_chain_with_rotor_8": "revolute_chain_with_rotor_8",
+          "revolute_chain_with_rotor_16": "revolute_chain_with_rotor_16",
           "revolute_pair_chain_with_rotor_2": "revolute_pair_chain_with_rotor_2",
           "revolute_pair_chain_with_rotor_4": "revolute_pair_chain_with_rotor_4"}
 
@@ -180,7 +182,8 @@ def test_angles_beyond_the_fast_sincos_range(grbda, oracle, torch, dtype_name):
     assert torch.isnan(tau2[130]).any() and not torch.isnan(tau2[131]).any() and not torch.isnan(tau2[0]).any()
 
 
-@pytest.mark.parametrize("robot", ["tello_with_arms", "mini_cheetah", "mit_humanoid", "revolute_chain_with_rotor_2"])
+@pytest.mark.parametrize("robot", ["tello_with_arms", "mini_cheetah", "mit_humanoid", "revolute_chain_with_rotor_2",
+                                   "revolute_chain_with_rotor_16", "revolute_rotor_chain", "jvrc1_humanoid"])
 def test_dynamics_parity_f32(grbda, oracle, torch, robot):
     """FP32 variant against the FP64 oracle on float-rounded states."""
     m = grbda.ClusterTreeModel.from_robot(robot)
