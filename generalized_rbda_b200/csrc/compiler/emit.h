@@ -309,7 +309,10 @@ namespace grbda
                 for (size_t arr = 0; arr < n_arr; arr++)
                 {
                     const int n = (int)p_.outputs[arr].size();
-                    chunked[arr] = out_chunk > 0 && n > 64;
+                    // output 0 is staged as a whole row when it is small (<= 64 values); every other output
+                    // with more than one chunk's worth of values goes through the chunked path (direct
+                    // stores of a thread's own row touch 32 sectors per instruction)
+                    chunked[arr] = out_chunk > 0 && (n > 64 || (arr > 0 && n > out_chunk));
                     ready[arr].assign(n, 0);
                     if (chunked[arr])
                     {

@@ -356,7 +356,7 @@ namespace grbda_kernels
     template <typename Body>
     __host__ __device__ constexpr bool bodyChunked()
     {
-        return Body::N_OUT0 > 64 || Body::N_OUT1 > 64 || Body::N_OUT2 > 64;
+        return Body::N_OUT0 > 64 || Body::N_OUT1 > OUT_CHUNK || Body::N_OUT2 > OUT_CHUNK; // = Emitter's rule
     }
     template <typename Body, typename real, int BLOCK>
     __host__ __device__ constexpr size_t stageBytes()
@@ -583,7 +583,9 @@ namespace grbda_kernels
     // software-staged shell above).
     // ---------------------------------------------------------------------------------------------
     template <typename real>
-    __host__ __device__ constexpr bool tmaRowWise(int n) { return n > 0 && (n * sizeof(real)) % 16 == 0; }
+    // (rows shorter than 12 elements are copied as one dense tile: one bulk copy per thread for 16-64 bytes
+    // costs more than the bank conflicts of an even stride do)
+    __host__ __device__ constexpr bool tmaRowWise(int n) { return n >= 12 && (n * sizeof(real)) % 16 == 0; }
     template <typename real>
     __host__ __device__ constexpr int tmaStride(int n) { return tmaRowWise<real>(n) ? n + 16 / (int)sizeof(real) : n; }
 
