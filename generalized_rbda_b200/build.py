@@ -43,7 +43,8 @@ MODELS = {
     "six_bar": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
     "planar_leg_linkage": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
     "mit_humanoid_leg": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
-    "jvrc1_humanoid": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, True),
+    "jvrc1_humanoid": ("id,fd,fk,h,phi,gfa,gfs,gen",
+                       DEFAULT_VARIANTS.replace("id=T,128,2;S,128,2", "id=T,128,2,park;T,128,2;S,128,2"), True),  # ID spills too: park
     "revolute_rotor_chain": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_2": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_4": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
