@@ -43,8 +43,10 @@ MODELS = {
     "six_bar": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
     "planar_leg_linkage": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
     "mit_humanoid_leg": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    # 58 bodies: the tile rows of a 128-thread CTA take 163 KB (one CTA per SM); 64-thread CTAs fit twice.
+    # Both dynamics kernels spill and are parked (ID 1.01 -> 0.86 ms, FD 3.3-4.2 ms per 2^20 states, L2 dependent)
     "jvrc1_humanoid": ("id,fd,fk,h,phi,gfa,gfs,gen",
-                       DEFAULT_VARIANTS.replace("id=T,128,2;S,128,2", "id=T,128,2,park;T,128,2;S,128,2"), True),  # ID spills too: park
+                       "id=T,64,2,park;T,128,2,park;S,128,2|fd=T,64,2,ltl,park;T,128,2,ltl,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2", True),
     "revolute_rotor_chain": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_2": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_4": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
