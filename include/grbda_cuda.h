@@ -20,6 +20,10 @@
  *   - `_f64` / `_f32` entry points take DEVICE pointers and are asynchronous on `stream`
  *     (a cudaStream_t passed as void*, NULL = default stream); `_host` entry points take HOST
  *     pointers, stage through pinned memory and return when the results are in the host buffers;
+ *   - a batched call enqueues two kernels on `stream` (the straight-line kernel and a normally empty
+ *     pass that recomputes 128-state tiles holding a joint angle beyond 1e12 rad with the library
+ *     sin/cos) and uses a small scratch buffer that the model handle keeps per stream: calls on
+ *     different streams may overlap, calls can be captured in CUDA graphs after one warm-up call;
  *   - there is no CPU implementation behind this API: without a CUDA device (or without compiled
  *     kernels for the model) calls fail with GRBDA_ERR_NO_DEVICE / GRBDA_ERR_NOT_COMPILED.
  */
