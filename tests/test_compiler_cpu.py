@@ -470,3 +470,18 @@ def test_external_force_programs(grbda, oracle, robot, tmp_path):
     tau_eff = run_tape(tapes["gfa"], [q, f_flat, aux])[0]
     ydd_ext = o.dynamics_with_external_forces(q, yd, aux, f_full, forward=True)
     assert rel(o.forward_dynamics(q, yd, tau_eff), ydd_ext) < 1e-9
+
+
+@pytest.mark.parametrize("robot", ["jvrc1_humanoid", "mit_humanoid"])
+def test_emitted_parked_bodies_of_the_large_models(grbda, oracle, robot, tmp_path):
+    """The parked inverse- and forward-dynamics bodies of the two largest URDF models (hundreds of parked
+    values, slot reuse), compiled for the host like test_emitted_cuda_text_on_the_host."""
+    from mirror import mirror_to_oracle
+    m = grbda.ClusterTreeModel.from_robot(robot, device=None)
+    o = oracle.OracleModel(robot) if ROBOTS.get(robot) else mirror_to_oracle(m, oracle)
+    q, yd, aux = o.generate_states(12, seed=37)
+    for program, want in ((0, o.inverse_dynamics(q, yd, aux)), (LTL, o.forward_dynamics(q, yd, aux))):
+        outs, in_range, text = run_emitted_source(m, program, True, [q, yd, aux], tmp_path, "p%d" % program)
+        assert "PARKED = true" in text and in_range == q.shape[0]
+        assert rel(outs[0], want) < 1e-9, program
+
