@@ -53,7 +53,9 @@ _lib.grbda_cuda_cluster_phi.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp]
 _lib.grbda_cuda_dump_program.argtypes = [_vp, C.c_int, C.c_char_p, _vp]
 _lib.grbda_cuda_kernel_counts.argtypes = [_vp, C.c_int, _vp]
 _lib.grbda_cuda_emit_source.argtypes = [_vp, C.c_int, C.c_int, C.c_char_p]
-_lib.grbda_cuda_dump_role_program.argtypes = [_vp, C.c_int, C.c_char_p, _vp]
+_lib.grbda_cuda_model_prepare.argtypes = [_vp, C.c_int, C.c_int]
+_lib.grbda_cuda_kernel_info.argtypes = [_vp, C.c_int, C.c_int, _vp]
+_lib.grbda_cuda_jit_compile.argtypes = [_vp, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
 for _p in ("f64", "f32"):
     getattr(_lib, "grbda_cuda_inverse_dynamics_" + _p).argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp]
     getattr(_lib, "grbda_cuda_forward_dynamics_" + _p).argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp]
@@ -74,7 +76,8 @@ EXPORTED_SYMBOLS = [
     "grbda_cuda_model_create_from_urdf", "grbda_cuda_model_create_from_robot", "grbda_cuda_model_destroy",
     "grbda_cuda_num_positions", "grbda_cuda_num_degrees_of_freedom", "grbda_cuda_num_bodies",
     "grbda_cuda_num_clusters", "grbda_cuda_model_hash", "grbda_cuda_cluster_info", "grbda_cuda_body_info",
-    "grbda_cuda_cluster_G", "grbda_cuda_model_gravity", "grbda_cuda_cluster_phi", "grbda_cuda_dump_program", "grbda_cuda_dump_role_program", "grbda_cuda_kernel_counts", "grbda_cuda_emit_source",
+    "grbda_cuda_cluster_G", "grbda_cuda_model_gravity", "grbda_cuda_cluster_phi", "grbda_cuda_dump_program", "grbda_cuda_kernel_counts", "grbda_cuda_emit_source",
+    "grbda_cuda_model_prepare", "grbda_cuda_kernel_info", "grbda_cuda_jit_compile",
     "grbda_cuda_external_force_bodies", "grbda_cuda_inverse_dynamics_ext_f64", "grbda_cuda_forward_dynamics_ext_f64",
     "grbda_cuda_inverse_dynamics_f64", "grbda_cuda_inverse_dynamics_f32",
     "grbda_cuda_forward_dynamics_f64", "grbda_cuda_forward_dynamics_f32",
@@ -88,6 +91,50 @@ DEFAULT_SEED = 0x6772626461  # "grbda"
 # layout of grbda_phi_op (int32 op, a, b; 4 bytes padding; float64 val)
 PHI_OP_DTYPE = np.dtype({"names": ["op", "a", "b", "val"], "formats": [np.int32, np.int32, np.int32, np.float64],
                          "offsets": [0, 4, 8, 16], "itemsize": 24})
+
+
+class _ScheduleStruct(C.Structure):
+    """ctypes mirror of grbda_schedule (include/grbda_cuda.h)."""
+    _fields_ = [("num_bodies", C.c_int32), ("num_clusters", C.c_int32), ("gravity", C.c_double * 3),
+                ("body_parent", _vp), ("body_joint_axis", _vp), ("body_xtree_E", _vp), ("body_xtree_r", _vp),
+                ("body_inertia", _vp), ("body_independent", _vp),
+                ("cluster_type", _vp), ("cluster_num_bodies", _vp), ("cluster_num_independent", _vp),
+                ("cluster_G_offset", _vp), ("G_values", _vp), ("cluster_phi_offset", _vp),
+                ("cluster_phi_count", _vp), ("cluster_phi_out_offset", _vp), ("cluster_num_constraints", _vp),
+                ("phi_ops", _vp), ("phi_outputs", _vp)]
+
+
+class Schedule:
+    """Flattened structure-of-arrays topology schedule (grbda_schedule) held as numpy arrays: what a
+    binding of the reference fills by walking a grbda::ClusterTreeModel (INTEGRATION.md). Every array
+    may be edited before ClusterTreeModel.from_schedule(schedule)."""
+
+    FIELDS = (("body_parent", np.int32), ("body_joint_axis", np.int32), ("body_xtree_E", np.float64),
+              ("body_xtree_r", np.float64), ("body_inertia", np.float64), ("body_independent", np.uint8),
+              ("cluster_type", np.int32), ("cluster_num_bodies", np.int32), ("cluster_num_independent", np.int32),
+              ("cluster_G_offset", np.int32), ("G_values", np.float64), ("cluster_phi_offset", np.int32),
+              ("cluster_phi_count", np.int32), ("cluster_phi_out_offset", np.int32),
+              ("cluster_num_constraints", np.int32), ("phi_ops", PHI_OP_DTYPE), ("phi_outputs", np.int32))
+
+    def __init__(self, gravity=(0.0, 0.0, -9.81)):
+        self.gravity = np.array(gravity, dtype=np.float64)
+        for name, dt in self.FIELDS:
+            setattr(self, name, np.zeros(0, dtype=dt))
+
+    def struct(self):
+        """(ctypes struct, keep-alive list): arrays are made contiguous copies of the right dtype."""
+        st = _ScheduleStruct()
+        st.num_bodies = len(self.body_parent)
+        st.num_clusters = len(self.cluster_type)
+        st.gravity[:] = [float(x) for x in self.gravity]
+        keep = []
+        for name, dt in self.FIELDS:
+            a = np.ascontiguousarray(getattr(self, name), dtype=dt).reshape(-1)
+            if a.size == 0:
+                a = np.zeros(1, dtype=dt)  # never hand out a NULL array
+            keep.append(a)
+            setattr(st, name, a.ctypes.data)
+        return st, keep
 
 
 class GrbdaError(RuntimeError):
@@ -154,10 +201,60 @@ class ClusterTreeModel:
         return cls(h, device)
 
     @classmethod
-    def from_schedule(cls, schedule_ptr, device=0):
+    def from_schedule(cls, schedule, device=0):
+        """schedule: a Schedule, or the address of a grbda_schedule struct."""
         h = _vp()
-        _check(_lib.grbda_cuda_model_create(schedule_ptr, -1 if device is None else device, C.byref(h)))
+        keep = None
+        if isinstance(schedule, Schedule):
+            st, keep = schedule.struct()
+            schedule = C.addressof(st)
+        _check(_lib.grbda_cuda_model_create(schedule, -1 if device is None else device, C.byref(h)))
+        del keep
         return cls(h, device)
+
+    def to_schedule(self):
+        """The model as a Schedule (numpy arrays), assembled from the introspection entry points."""
+        s = Schedule(self.getGravity())
+        bodies, clusters = self.bodies(), self.clusters()
+        s.body_parent = np.array([b["parent"] for b in bodies], dtype=np.int32)
+        s.body_joint_axis = np.array([b["axis"] for b in bodies], dtype=np.int32)
+        s.body_xtree_E = np.concatenate([b["E"].reshape(-1) for b in bodies])
+        s.body_xtree_r = np.concatenate([b["r"].reshape(-1) for b in bodies])
+        s.body_inertia = np.concatenate([b["inertia"].reshape(-1) for b in bodies])
+        ind = np.ones(len(bodies), dtype=np.uint8)
+        G, ops, outs = [], [], []
+        G_off, phi_off, phi_cnt, phi_out_off, ncons = [], [], [], [], []
+        n_ops = n_outs = n_G = 0
+        for c in clusters:
+            G_off.append(n_G), phi_off.append(n_ops), phi_out_off.append(n_outs)
+            if c["type"] == 2:
+                G.append(c["G"].reshape(-1))
+                n_G += c["G"].size
+                phi_cnt.append(0)
+                ncons.append(c["num_bodies"] - c["num_velocities"])
+            elif c["type"] == 3:
+                ops.append(c["phi_ops"]), outs.append(c["phi_outputs"])
+                n_ops += len(c["phi_ops"])
+                n_outs += len(c["phi_outputs"])
+                phi_cnt.append(len(c["phi_ops"]))
+                ncons.append(len(c["phi_outputs"]))
+                ind[c["first_body"]:c["first_body"] + c["num_bodies"]] = c["independent"]
+            else:
+                phi_cnt.append(0)
+                ncons.append(0)
+        s.body_independent = ind
+        s.cluster_type = np.array([c["type"] for c in clusters], dtype=np.int32)
+        s.cluster_num_bodies = np.array([c["num_bodies"] for c in clusters], dtype=np.int32)
+        s.cluster_num_independent = np.array([c["num_velocities"] for c in clusters], dtype=np.int32)
+        s.cluster_G_offset = np.array(G_off, dtype=np.int32)
+        s.G_values = np.concatenate(G) if G else np.zeros(0)
+        s.cluster_phi_offset = np.array(phi_off, dtype=np.int32)
+        s.cluster_phi_count = np.array(phi_cnt, dtype=np.int32)
+        s.cluster_phi_out_offset = np.array(phi_out_off, dtype=np.int32)
+        s.cluster_num_constraints = np.array(ncons, dtype=np.int32)
+        s.phi_ops = np.concatenate(ops) if ops else np.zeros(0, dtype=PHI_OP_DTYPE)
+        s.phi_outputs = np.concatenate(outs) if outs else np.zeros(0, dtype=np.int32)
+        return s
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:
@@ -272,16 +369,32 @@ class ClusterTreeModel:
         d["flops"] = d["add"] + d["mul"] + d["div"] + d["sqrt"]
         return d
 
-    def dump_role_program(self, algo, path=None):
-        info = (C.c_int64 * 4)()
-        _check(_lib.grbda_cuda_dump_role_program(self._h, algo, path.encode() if path else None, info))
-        return dict(W=int(info[0]), slots=int(info[1]), max_role_flops=int(info[2]), sum_role_flops=int(info[3]))
+    # ---- kernel provenance / run-time compilation ------------------------------------------------
+    def prepare(self, algo, f32=False):
+        """Compile / load the kernels of one entry point now instead of on first use."""
+        _check(_lib.grbda_cuda_model_prepare(self._h, algo, int(bool(f32))))
+
+    def kernel_info(self, algo, f32=False):
+        info = (C.c_int64 * 8)()
+        _check(_lib.grbda_cuda_kernel_info(self._h, algo, int(bool(f32)), info))
+        v = [int(x) for x in info]
+        return dict(source="jit" if v[0] else "aot", block=v[1], min_blocks=v[2], smem=v[3], program=v[4],
+                    parked=bool(v[5] & 1), tma=bool(v[5] & 2), direct=bool(v[5] & 4), from_cache=bool(v[5] & 8),
+                    compile_ms=v[6], ready=bool(v[7]))
+
+    def jit_compile(self, algo, f32=False, source_path=None, cubin_path=None):
+        """Run-time compiler without a device: CUDA text and / or NVRTC cubin of one entry point (algo -1: generator)."""
+        _check(_lib.grbda_cuda_jit_compile(self._h, algo, int(bool(f32)),
+                                           source_path.encode() if source_path else None,
+                                           cubin_path.encode() if cubin_path else None))
 
     # ---- batched hot path (device tensors) ----------------------------------------------------
     def _prep(self, t, n, dtype=None):
         import torch
         if not t.is_cuda:
             raise ValueError("expected a CUDA tensor")
+        if self.device is not None and t.device.index != self.device:
+            raise ValueError("tensor lives on cuda:%d but the model was created on cuda:%d" % (t.device.index, self.device))
         if dtype is not None and t.dtype != dtype:
             raise ValueError("dtype mismatch: %s vs %s" % (t.dtype, dtype))
         if t.dtype not in (torch.float64, torch.float32):
@@ -359,21 +472,36 @@ class ClusterTreeModel:
         return p, R, v
 
     # ---- host buffers (end-to-end path) ---------------------------------------------------------
+    @staticmethod
+    def _host_ptr(a, rows, cols, what):
+        """Address of a float64, C-contiguous [rows, cols] host array (numpy or CPU torch tensor)."""
+        if isinstance(a, np.ndarray):
+            ok = a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+            ptr = a.ctypes.data
+        else:
+            import torch
+            ok = isinstance(a, torch.Tensor) and not a.is_cuda and a.dtype == torch.float64 and a.is_contiguous()
+            ptr = a.data_ptr() if ok else 0
+        if not ok or tuple(a.shape) != (rows, cols):
+            raise ValueError("%s: expected a float64, C-contiguous host array of shape (%d, %d)" % (what, rows, cols))
+        return _vp(ptr)
+
     def dynamics_host(self, algo, q, yd, in3, out):
-        """ID (algo=0) / FD (algo=1) on HOST arrays (numpy float64 or CPU torch tensors, ideally
-        pinned): H2D copy, kernel and D2H copy are pipelined inside the call."""
-        def hp(a):
-            return _vp(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
-        batch = q.shape[0]
-        _check(_lib.grbda_cuda_dynamics_host_f64(self._h, algo, hp(q), hp(yd), hp(in3), hp(out), batch))
+        """ID (algo=0) / FD (algo=1) on HOST arrays (numpy float64 or CPU torch tensors): H2D copy, kernel and
+        D2H copy are pipelined inside the call. Page-locked arrays are used in place, pageable ones are staged."""
+        B = q.shape[0]
+        hp = self._host_ptr
+        _check(_lib.grbda_cuda_dynamics_host_f64(self._h, algo, hp(q, B, self.nq, "q"), hp(yd, B, self.nv, "yd"),
+                                                 hp(in3, B, self.nv, "in3"), hp(out, B, self.nv, "out"), B))
         return out
 
     def forward_inverse_host(self, q, yd, tau, ydd, tau_back):
         """One benchmark step on HOST arrays: ydd = FD(q, yd, tau), tau_back = ID(q, yd, ydd)."""
-        def hp(a):
-            return _vp(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
-        _check(_lib.grbda_cuda_forward_inverse_host_f64(self._h, hp(q), hp(yd), hp(tau), hp(ydd), hp(tau_back),
-                                                        q.shape[0]))
+        B = q.shape[0]
+        hp = self._host_ptr
+        _check(_lib.grbda_cuda_forward_inverse_host_f64(self._h, hp(q, B, self.nq, "q"), hp(yd, B, self.nv, "yd"),
+                                                        hp(tau, B, self.nv, "tau"), hp(ydd, B, self.nv, "ydd"),
+                                                        hp(tau_back, B, self.nv, "tau_back"), B))
         return ydd, tau_back
 
     # ---- synthetic states / checks --------------------------------------------------------------

@@ -136,6 +136,23 @@ def build(verbose=True, jobs=None, models=None):
             if os.path.exists(p):
                 gen_sources.append(p)
 
+    # 2b. the kernel headers as string literals for the run-time compiler (runtime/jit.cpp hands them to NVRTC)
+    inc = []
+    for var, rel in (("shapes", "kernels/shapes.h"), ("batched", "kernels/batched_kernel.cuh"),
+                     ("stategen", "kernels/stategen.cuh")):
+        with open(os.path.join(CSRC, rel)) as f:
+            text = f.read()
+        assert ')GRBDAHDR"' not in text
+        # string literals are limited to 64 KB by some compilers: concatenate pieces
+        pieces = [text[i:i + 12000] for i in range(0, len(text), 12000)]
+        inc.append("static const char k_jit_header_%s[] =\n%s;\n" % (
+            var, "\n".join('R"GRBDAHDR(%s)GRBDAHDR"' % piece for piece in pieces)))
+    inc_path = os.path.join(BUILD, "jit_headers.inc")
+    inc_text = "// generated by build.py from csrc/kernels — do not edit\n" + "\n".join(inc)
+    if not os.path.exists(inc_path) or open(inc_path).read() != inc_text:
+        with open(inc_path, "w") as f:
+            f.write(inc_text)
+
     # 3. nvcc (parallel)
     cuda_sources = gen_sources + [os.path.join(CSRC, "runtime/capi.cu")]
     with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
@@ -143,12 +160,14 @@ def build(verbose=True, jobs=None, models=None):
         cuda_objs = [f.result() for f in futs]
     reg_obj = _compile_cached(os.path.join(CSRC, "runtime/registry.cpp"), BUILD,
                               [NVCC] + NVCCFLAGS + ["-x", "cu"], hdr_digest, log)
+    jit_obj = _compile_cached(os.path.join(CSRC, "runtime/jit.cpp"), BUILD,
+                              [NVCC] + NVCCFLAGS + ["-x", "cu", "-I", BUILD], hdr_digest, log)
 
     # 4. link
     _run([NVCC, "-shared", "-o", LIB, "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", CXX]
-         + cuda_objs + [reg_obj] + host_objs + ["-lcudart"])
+         + cuda_objs + [reg_obj, jit_obj] + host_objs + ["-lcudart", "-ldl"])
     # drop stale cached objects so that _build does not grow without bound
-    keep = set(cuda_objs + [reg_obj, modelc_obj, modelc] + host_objs)
+    keep = set(cuda_objs + [reg_obj, jit_obj, modelc_obj, modelc] + host_objs)
     for f in os.listdir(BUILD):
         p = os.path.join(BUILD, f)
         if p not in keep and f.endswith(".o"):

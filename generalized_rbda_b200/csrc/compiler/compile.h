@@ -5,7 +5,6 @@
 #include <sstream>
 #include "algorithms.h"
 #include "emit.h"
-#include "partition.h"
 
 namespace grbda
 {
@@ -48,6 +47,42 @@ namespace grbda
             ProgramStats stats;
             Tape tape;
         };
+
+        // Input / output sizes of one program without building it (launch-shape decisions need them first).
+        inline void algoSizes(const ClusterTreeModel &model, int program, int n_in[3], int n_out[3])
+        {
+            const int nq = model.getNumPositions(), nv = model.getNumDegreesOfFreedom(), nb = model.getNumBodies();
+            n_in[0] = nq, n_in[1] = n_in[2] = 0;
+            n_out[0] = n_out[1] = n_out[2] = 0;
+            switch (program)
+            {
+            case ALGO_ID:
+            case ALGO_FD:
+            case PROGRAM_FD_LTL:
+                n_in[1] = n_in[2] = nv, n_out[0] = nv;
+                break;
+            case ALGO_GFA:
+            case ALGO_GFS:
+                n_in[1] = 6 * (int)ModelCompiler::externalForceBodies(model).size(), n_in[2] = nv, n_out[0] = nv;
+                break;
+            case ALGO_FK:
+                n_in[1] = nv, n_out[0] = 3 * nb, n_out[1] = 9 * nb, n_out[2] = 6 * nb;
+                break;
+            case ALGO_H:
+                n_out[0] = nv * nv;
+                break;
+            case ALGO_PHI:
+                for (const ClusterTreeNode &c : model.clusters())
+                    if (c.joint_.type == ClusterType::Implicit)
+                    {
+                        n_out[0] += c.joint_.num_constraints;
+                        n_out[1] += c.joint_.num_constraints * (c.joint_.num_bodies - c.joint_.num_velocities);
+                    }
+                break;
+            default:
+                throw std::runtime_error("algoSizes: unknown program");
+            }
+        }
 
         // Build the symbolic program of one algorithm in the CURRENT graph scope.
         inline Program buildProgram(const ClusterTreeModel &model, int algo)
@@ -153,7 +188,7 @@ namespace grbda
 
         // The generated `struct Body` of one program: sizes, range check, run<real, FAST>(). Shared by the
         // build-time tool (tools/modelc.cpp) and grbda_cuda_emit_source (host-compiled emitter self test).
-            inline void emitBodyStruct(std::ostream &os, const std::string &struct_name, const CompiledAlgo &c)
+        inline void emitBodyStruct(std::ostream &os, const std::string &struct_name, const CompiledAlgo &c)
         {
             os << "struct " << struct_name << "\n{\n";
             os << "    static constexpr int N_IN0 = " << c.n_in[0] << ", N_IN1 = " << c.n_in[1]
@@ -203,134 +238,75 @@ namespace grbda
         }
 
 
-        // ---- limb-parallel (one warp per limb) version of the same program ---------------------------
-        struct CompiledRoles
+        // State generator of one model (kernels/stategen.cuh): one (phi, K_d) evaluator per implicit cluster and
+        // `struct Gen` that fills one random valid state. Shared by tools/modelc.cpp and the run-time compiler.
+        inline void emitGenerator(std::ostream &os, const ClusterTreeModel &model)
         {
-            std::string name;
-            int W = 1, num_slots = 0;
-            bool has_barrier = false;
-            int n_in[3] = {0, 0, 0};
-            int n_out[3] = {0, 0, 0};
-            std::vector<std::string> bodies;  // per role
-            std::vector<ProgramStats> stats;  // per role
-            // for the CPU-side self test (tests/tape.py): the whole graph + the role instruction lists
-            sym::Graph graph;
-            RolePrograms programs;
-            std::vector<std::vector<RolePartitioner::Out>> role_outputs;
-        };
-
-        inline CompiledRoles compileAlgoRoles(const ClusterTreeModel &model, int algo, bool want_body = true,
-                                              ConstTable *consts = nullptr)
-        {
-            CompiledRoles out;
-            const RolePlan plan = planRoles(model);
-            sym::GraphScope scope(out.graph);
-            const Program p = buildProgram(model, algo);
-            out.name = p.name;
-            out.W = algo == ALGO_PHI ? 1 : plan.W;
-            for (int i = 0; i < 3; i++)
-                out.n_in[i] = p.n_in[i];
-            for (size_t i = 0; i < p.outputs.size(); i++)
-                out.n_out[i] = (int)p.outputs[i].size();
-            const int nv = model.getNumDegreesOfFreedom();
-
-            // cluster of a position / velocity / body index
-            std::vector<int> pos_cluster(model.getNumPositions()), vel_cluster(nv), body_cluster(model.getNumBodies());
-            std::vector<int> weight(std::max(1, plan.W), 0);
+            const int nq = model.getNumPositions(), nv = model.getNumDegreesOfFreedom();
+            // one (phi, Kd) evaluator per implicit cluster
             for (const ClusterTreeNode &c : model.clusters())
             {
-                for (int i = 0; i < c.num_positions_; i++)
-                    pos_cluster[c.position_index_ + i] = c.index_;
-                for (int i = 0; i < c.num_velocities_; i++)
-                    vel_cluster[c.velocity_index_ + i] = c.index_;
-                for (int i = 0; i < c.joint_.num_bodies; i++)
-                    body_cluster[c.first_body_ + i] = c.index_;
-                if (plan.cluster_role[c.index_] >= 0)
-                    weight[plan.cluster_role[c.index_]] += c.joint_.num_bodies * (c.joint_.type == ClusterType::Implicit ? 3 : 1);
+                if (c.joint_.type != ClusterType::Implicit)
+                    continue;
+                const ClusterDesc &d = c.joint_;
+                sym::Graph graph;
+                sym::GraphScope scope(graph);
+                ModelCompiler mc(model);
+                std::vector<sym::Sym> q(d.num_bodies), phi, K, Kd;
+                for (int i = 0; i < d.num_bodies; i++)
+                    q[i] = sym::Sym::input(0, i);
+                mc.implicitJacobian(d, q, nullptr, phi, K, nullptr);
+                std::vector<int> ind, dep;
+                for (int i = 0; i < d.num_bodies; i++)
+                    (d.independent[i] ? ind : dep).push_back(i);
+                for (int i = 0; i < d.num_constraints; i++)
+                    for (int j : dep)
+                        Kd.push_back(K[i * d.num_bodies + j]);
+                Program p;
+                p.outputs = {phi, Kd};
+                Emitter em(graph, p);
+                os << "struct Cluster" << c.index_ << "\n{\n    static constexpr int N = " << d.num_bodies
+                   << ", NC = " << d.num_constraints << ";\n";
+                os << "    static __device__ __forceinline__ int ind(int i) { const int t[] = {";
+                for (size_t i = 0; i < ind.size(); i++)
+                    os << ind[i] << (i + 1 < ind.size() ? ", " : "");
+                os << "}; return t[i]; }\n";
+                os << "    static __device__ __forceinline__ int dep(int i) { const int t[] = {";
+                for (size_t i = 0; i < dep.size(); i++)
+                    os << dep[i] << (i + 1 < dep.size() ? ", " : "");
+                os << "}; return t[i]; }\n";
+                os << "    static __device__ __noinline__ void eval(const double *q, double *phi, double *Kd)\n    {\n"
+                      "        typedef double real;\n        constexpr bool FAST = false;\n"
+                      "#define KC(x) ((real)(x))\n#define GRBDA_PIN(x, late) (x)\n#define GRBDA_DIV(a, b) ((a) / (b))\n#define IN0(i) q[i]\n#define OUT0(i, x) phi[i] = (x)\n"
+                      "#define OUT1(i, x) Kd[i] = (x)\n";
+                os << em.cudaBody();
+                os << "#undef KC\n#undef KT\n#undef GRBDA_PIN\n#undef GRBDA_DIV\n#undef IN0\n#undef OUT0\n#undef OUT1\n    }\n};\n\n";
             }
-            // trunk outputs go to the lightest limb
-            const int trunk_role = (int)(std::min_element(weight.begin(), weight.end()) - weight.begin());
-            auto roleOfCluster = [&](int c) { return out.W > 1 ? plan.cluster_role[c] : 0; };
-            auto input_role = [&](int array, int element) {
-                return roleOfCluster(array == IN_Q ? pos_cluster[element] : vel_cluster[element]);
-            };
-            auto output_role = [&](int array, int element) {
-                int r = -1;
-                switch (algoOfProgram(algo))
-                {
-                case ALGO_ID:
-                case ALGO_FD: r = roleOfCluster(vel_cluster[element]); break;
-                case ALGO_FK:
-                    r = roleOfCluster(body_cluster[element / (array == 0 ? 3 : (array == 1 ? 9 : 6))]);
-                    break;
-                case ALGO_H:
-                {
-                    const int ra = roleOfCluster(vel_cluster[element / nv]), rb = roleOfCluster(vel_cluster[element % nv]);
-                    r = ra >= 0 ? ra : rb;
-                    break;
-                }
-                default: r = 0;
-                }
-                return r >= 0 ? r : trunk_role;
-            };
-            RolePartitioner part(out.graph, p, out.W, input_role, output_role);
-            out.programs = part.build();
-            out.num_slots = out.programs.num_slots;
-            out.has_barrier = out.programs.has_barrier;
-            out.role_outputs = part.roleOutputs();
-            RoleEmitter em(out.graph, part, out.programs, consts);
-            for (int r = 0; r < out.W; r++)
+            os << "struct Gen\n{\n    static constexpr int NQ = " << nq << ", NV = " << nv << ";\n";
+            os << "    static __device__ bool run(Philox &rng, double *q, double *yd, double *aux)\n    {\n"
+                  "        bool ok = true;\n";
+            for (const ClusterTreeNode &c : model.clusters())
             {
-                out.stats.push_back(em.roleStats(r));
-                if (want_body)
-                    out.bodies.push_back(em.roleBody(r));
-            }
-            return out;
-        }
-
-        // Role tape (tests/tape.py run_role_tape): int32 header {magic 0x47524245, n_nodes, W, num_slots,
-        // n_in0, n_in1, n_in2, n_out0, n_out1, n_out2}; node table op,a,b,c,e (int32) + val (float64);
-        // per role: int32 n_ops, then (kind, id, slot) int32 triples; int32 n_outputs, then
-        // (id, array, element) int32 triples.
-        inline void writeRoleTape(const CompiledRoles &c, const std::string &path)
-        {
-            std::ofstream f(path, std::ios::binary);
-            if (!f)
-                throw std::runtime_error("cannot write " + path);
-            const int32_t n = (int32_t)c.graph.nodes.size();
-            const int32_t hdr[10] = {0x47524245, n, c.W, c.num_slots, c.n_in[0], c.n_in[1], c.n_in[2],
-                                     c.n_out[0], c.n_out[1], c.n_out[2]};
-            f.write((const char *)hdr, sizeof(hdr));
-            std::vector<int32_t> col(n);
-            auto dump = [&](auto get) {
-                for (int32_t i = 0; i < n; i++)
-                    col[i] = get(c.graph.nodes[i]);
-                f.write((const char *)col.data(), (size_t)n * 4);
-            };
-            dump([](const sym::Node &x) { return (int32_t)x.op; });
-            dump([](const sym::Node &x) { return x.a; });
-            dump([](const sym::Node &x) { return x.b; });
-            dump([](const sym::Node &x) { return x.c; });
-            dump([](const sym::Node &x) { return x.e; });
-            for (int32_t i = 0; i < n; i++)
-                f.write((const char *)&c.graph.nodes[i].val, 8);
-            for (int r = 0; r < c.W; r++)
-            {
-                const int32_t no = (int32_t)c.programs.ops[r].size();
-                f.write((const char *)&no, 4);
-                for (const RoleOp &op : c.programs.ops[r])
+                const ClusterDesc &d = c.joint_;
+                const int pi = c.position_index_;
+                if (d.type == ClusterType::FreeQuaternion || d.type == ClusterType::FreeRollPitchYaw)
                 {
-                    const int32_t t[3] = {op.kind, op.id, op.slot};
-                    f.write((const char *)t, 12);
+                    os << "        for (int i = 0; i < 3; i++) q[" << pi << " + i] = rng.uniform();\n";
+                    os << "        { double rpy[3]; for (int i = 0; i < 3; i++) rpy[i] = rng.uniform();\n";
+                    if (d.type == ClusterType::FreeQuaternion)
+                        os << "          rpyToQuat(rpy, q + " << pi + 3 << "); }\n";
+                    else
+                        os << "          for (int i = 0; i < 3; i++) q[" << pi + 3 << " + i] = rpy[i]; }\n";
                 }
-                const int32_t nout = (int32_t)c.role_outputs[r].size();
-                f.write((const char *)&nout, 4);
-                for (auto &o : c.role_outputs[r])
-                {
-                    const int32_t t[3] = {o.id, o.array, o.element};
-                    f.write((const char *)t, 12);
-                }
+                else if (d.type == ClusterType::Explicit)
+                    os << "        for (int i = 0; i < " << d.num_positions << "; i++) q[" << pi
+                       << " + i] = rng.uniform();\n";
+                else
+                    os << "        ok = randomImplicitPosition<Cluster" << c.index_ << ">(rng, q + " << pi
+                       << ") && ok;\n";
             }
+            os << "        for (int i = 0; i < NV; i++) yd[i] = rng.uniform();\n"
+                  "        for (int i = 0; i < NV; i++) aux[i] = rng.uniform();\n        return ok;\n    }\n};\n";
         }
 
         // Binary tape: int32 header {magic, n_ops, n_arrays, n_in0, n_in1, n_in2}, then op,a,b,c,e

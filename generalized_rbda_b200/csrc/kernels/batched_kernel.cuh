@@ -12,14 +12,38 @@
 // The CTA's tile of every input array is streamed from HBM with coalesced 128-bit loads into
 // shared memory (stage_in), the threads then read their own state from shared memory with an odd
 // stride (bank-conflict free), and results go back the same way (stage_out).
-#pragma once
+#ifndef GRBDA_KERNELS_BATCHED_KERNEL_CUH // (NVRTC sees this header under two include names: #pragma once is not enough)
+#define GRBDA_KERNELS_BATCHED_KERNEL_CUH
+// The device part of this header is also compiled at run time by NVRTC (runtime/jit.cpp: models that were
+// not compiled ahead of time), which has no host or standard-library headers: everything outside the
+// `#ifndef __CUDACC_RTC__` blocks must stay free of them.
+#ifdef __CUDACC_RTC__
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uintptr_t;
+namespace grbda_std
+{
+    template <bool B, class T, class F> struct conditional { typedef T type; };
+    template <class T, class F> struct conditional<false, T, F> { typedef F type; };
+}
+#else
 #include <algorithm>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <type_traits>
+namespace grbda_std
+{
+    using std::conditional;
+}
+#endif
+
+#include "shapes.h"
 
 namespace grbda_kernels
 {
+#ifndef __CUDACC_RTC__
     struct LaunchArgs
     {
         const void *in[3];
@@ -32,6 +56,7 @@ namespace grbda_kernels
         unsigned char *flags = nullptr;
         size_t flags_bytes = 0;
     };
+#endif
 
     // ---- scalar math of the generated bodies -------------------------------------------------------
     // The generated per-state program is ONE basic block of several thousand FP64 instructions. Any
@@ -200,10 +225,6 @@ namespace grbda_kernels
         return fmaf(fmaf(-b, q, a), r, q);
     }
 
-    // Row stride (in elements) of a staged tile: odd, so that thread t reading element i of its
-    // own state (address t * stride + i) hits 32 distinct banks for 4-byte and 16 distinct bank
-    // pairs per half warp for 8-byte elements.
-    __host__ __device__ constexpr int oddStride(int n) { return n | 1; }
 
     // Cooperative, coalesced copy of the CTA's [rows x N] tile (global, dense) into shared memory
     // rows of stride oddStride(N). 128-bit loads when the tile base is 16-byte aligned.
@@ -215,7 +236,7 @@ namespace grbda_kernels
         const int total = rows * N;
         if ((reinterpret_cast<uintptr_t>(g) & 15) == 0)
         {
-            using vec_t = typename std::conditional<sizeof(real) == 8, double2, float4>::type;
+            using vec_t = typename grbda_std::conditional<sizeof(real) == 8, double2, float4>::type;
             const vec_t *gv = reinterpret_cast<const vec_t *>(g);
             const int nvec = total / VEC;
 #pragma unroll 4
@@ -250,7 +271,7 @@ namespace grbda_kernels
         const int total = rows * N;
         if ((reinterpret_cast<uintptr_t>(g) & 15) == 0)
         {
-            using vec_t = typename std::conditional<sizeof(real) == 8, double2, float4>::type;
+            using vec_t = typename grbda_std::conditional<sizeof(real) == 8, double2, float4>::type;
             vec_t *gv = reinterpret_cast<vec_t *>(g);
             const int nvec = total / VEC;
 #pragma unroll 4
@@ -281,7 +302,6 @@ namespace grbda_kernels
     // The generated body hands over `COUNT` consecutive elements of one output array for the 32
     // states of the warp through the warp's staging buffer; this writes them with coalesced stores
     // (for COUNT = 16 doubles every instruction covers two states x 128 contiguous bytes).
-    constexpr int OUT_CHUNK = 16;
     template <typename real>
     struct OutStage
     {
@@ -501,6 +521,7 @@ namespace grbda_kernels
         } while (!FAST && tile < tile_end);
     }
 
+#ifndef __CUDACC_RTC__
     template <typename Body>
     cudaError_t acquireFlags(const LaunchArgs &a, int64_t tiles, unsigned char **flags)
     {
@@ -522,7 +543,8 @@ namespace grbda_kernels
             return cudaSuccess;
         using L = TileLayout<Body, real, BLOCK>;
         // staged tiles unless the rows of this program do not fit into shared memory (then direct I/O)
-        constexpr bool STAGED = L::BYTES <= 200 * 1024;
+        constexpr bool STAGED = L::BYTES <= SLOW_PASS_STAGED_LIMIT;
+        static_assert(!Body::PARKED || STAGED, "a parked body writes into its tile rows: it cannot run on caller memory");
         constexpr size_t SMEM = STAGED ? L::BYTES : stageBytes<Body, real, BLOCK>();
         auto kernel = grbda_batched_kernel<real, Body, BLOCK, MIN_BLOCKS, STAGED, false>;
         if (SMEM > 48 * 1024)
@@ -543,6 +565,7 @@ namespace grbda_kernels
     template <typename real, typename Body, int BLOCK, int MIN_BLOCKS, bool STAGED>
     cudaError_t launchBatched(const LaunchArgs &a)
     {
+        static_assert(!Body::PARKED || STAGED, "a parked body writes into its tile rows: it cannot run on caller memory");
         using L = TileLayout<Body, real, BLOCK>;
         auto kernel = grbda_batched_kernel<real, Body, BLOCK, MIN_BLOCKS, STAGED, true>;
         const size_t smem = STAGED ? L::BYTES : stageBytes<Body, real, BLOCK>();
@@ -568,6 +591,8 @@ namespace grbda_kernels
         const cudaError_t e2 = launchSlowPass<real, Body, BLOCK, MIN_BLOCKS>(a, grid, flags);
         return e != cudaSuccess ? e : e2;
     }
+
+#endif // !__CUDACC_RTC__
 
     // ---------------------------------------------------------------------------------------------
     // TMA-staged shell (variant 'T'): the CTA's input tiles are brought into shared memory by the
@@ -675,6 +700,14 @@ namespace grbda_kernels
         static constexpr size_t BYTES = TILE_BYTES + stageBytes<Body, real, BLOCK>();
     };
 
+    template <typename Body, typename real, int BLOCK>
+    __host__ __device__ constexpr bool shapeMirrorsAgree()
+    {
+        const int n_in[3] = {Body::N_IN0, Body::N_IN1, Body::N_IN2}, n_out[3] = {Body::N_OUT0, Body::N_OUT1, Body::N_OUT2};
+        return shapeTileBytes(n_in, n_out, Body::STAGE_BUFFERS, BLOCK, (int)sizeof(real)) == TileLayout<Body, real, BLOCK>::BYTES &&
+               shapeTmaBytes(n_in, n_out, Body::STAGE_BUFFERS, BLOCK, (int)sizeof(real)) == TmaLayout<Body, real, BLOCK>::BYTES;
+    }
+
     template <typename real, typename Body, int BLOCK, int MIN_BLOCKS>
     __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
         grbda_batched_kernel_tma(const real *__restrict__ in0, const real *__restrict__ in1,
@@ -683,6 +716,7 @@ namespace grbda_kernels
                                  unsigned char *__restrict__ flags)
     {
         using L = TmaLayout<Body, real, BLOCK>;
+        static_assert(shapeMirrorsAgree<Body, real, BLOCK>(), "shape* functions out of step with the tile layouts");
         extern __shared__ __align__(128) unsigned char smem_raw[];
         uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
         real *s0 = reinterpret_cast<real *>(smem_raw + L::OFF0);
@@ -754,6 +788,7 @@ namespace grbda_kernels
         }
     }
 
+#ifndef __CUDACC_RTC__
     template <typename real, typename Body, int BLOCK, int MIN_BLOCKS>
     cudaError_t launchBatchedTma(const LaunchArgs &a)
     {
@@ -788,100 +823,7 @@ namespace grbda_kernels
         const cudaError_t e2 = launchSlowPass<real, Body, BLOCK, MIN_BLOCKS>(a, grid, flags);
         return e != cudaSuccess ? e : e2;
     }
-
-    // ---------------------------------------------------------------------------------------------
-    // Limb-parallel shell: ONE STATE PER LANE, ONE LIMB PER WARP (compiler/partition.h).
-    // A CTA of W warps evaluates 32 states; warp w runs the straight-line program of limb
-    // (w + blockIdx.x) % W (rotated so that heavy and light limbs spread over the four schedulers of
-    // an SM), publishes what the trunk needs from its limb in shared memory (COMM_ST), meets the
-    // other warps at ONE named barrier and continues with the values of the other limbs (COMM_LD).
-    //   Body::W, Body::NUM_SLOTS, Body::N_INk / N_OUTk
-    //   Body::run<real>(role, in0, in1, in2, out0, out1, out2, comm)
-    // ---------------------------------------------------------------------------------------------
-    template <typename Body, typename real>
-    struct RoleLayout
-    {
-        static constexpr int TILE = 32;
-        static constexpr int S0 = Body::N_IN0 ? oddStride(Body::N_IN0) : 0;
-        static constexpr int S1 = Body::N_IN1 ? oddStride(Body::N_IN1) : 0;
-        static constexpr int S2 = Body::N_IN2 ? oddStride(Body::N_IN2) : 0;
-        static constexpr bool STAGE_OUT0 = Body::N_OUT0 <= 64;
-        static constexpr int SO = STAGE_OUT0 ? oddStride(Body::N_OUT0) : 0;
-        static constexpr int OFF1 = S0 * TILE;
-        static constexpr int OFF2 = OFF1 + S1 * TILE;
-        static constexpr int OFFO = OFF2 + S2 * TILE;
-        static constexpr int OFFC = OFFO + SO * TILE;
-        static constexpr int ELEMS = OFFC + Body::NUM_SLOTS * TILE;
-        static constexpr size_t BYTES = (size_t)ELEMS * sizeof(real);
-    };
-
-    template <int NTHREADS>
-    __device__ __forceinline__ void roleBarrier()
-    {
-        // named barrier 1: every warp of the CTA arrives exactly once, from its own role program
-        asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
-    }
-
-    template <typename real, typename Body, int MIN_BLOCKS>
-    __global__ void __launch_bounds__(Body::W * 32, MIN_BLOCKS)
-        grbda_role_kernel(const real *__restrict__ in0, const real *__restrict__ in1,
-                          const real *__restrict__ in2, real *__restrict__ out0, real *__restrict__ out1,
-                          real *__restrict__ out2, int64_t batch)
-    {
-        using L = RoleLayout<Body, real>;
-        constexpr int BLOCK = Body::W * 32;
-        extern __shared__ __align__(16) unsigned char smem_raw[];
-        real *smem = reinterpret_cast<real *>(smem_raw);
-
-        const int64_t first = (int64_t)blockIdx.x * L::TILE;
-        const int64_t remaining = batch - first;
-        const int rows = remaining < L::TILE ? (int)remaining : L::TILE;
-
-        if (Body::N_IN0)
-            stage_in<real, Body::N_IN0 ? Body::N_IN0 : 1, BLOCK>(in0 + first * Body::N_IN0, smem, rows);
-        if (Body::N_IN1)
-            stage_in<real, Body::N_IN1 ? Body::N_IN1 : 1, BLOCK>(in1 + first * Body::N_IN1, smem + L::OFF1, rows);
-        if (Body::N_IN2)
-            stage_in<real, Body::N_IN2 ? Body::N_IN2 : 1, BLOCK>(in2 + first * Body::N_IN2, smem + L::OFF2, rows);
-        __syncthreads();
-
-        const int warp = threadIdx.x >> 5;
-        const int role = (warp + (int)(blockIdx.x % Body::W)) % Body::W;
-        // lanes past the end of the batch recompute the last valid state (identical values, so the
-        // duplicate stores are benign) and thereby still take part in the barrier
-        const int lane = min((int)(threadIdx.x & 31), rows - 1);
-        const int64_t state = first + lane;
-        real *o0 = L::STAGE_OUT0 ? smem + L::OFFO + lane * L::SO : out0 + state * Body::N_OUT0;
-        real *o1 = Body::N_OUT1 ? out1 + state * Body::N_OUT1 : nullptr;
-        real *o2 = Body::N_OUT2 ? out2 + state * Body::N_OUT2 : nullptr;
-        Body::template run<real>(role, smem + lane * L::S0, smem + L::OFF1 + lane * L::S1,
-                                 smem + L::OFF2 + lane * L::S2, o0, o1, o2, smem + L::OFFC + lane);
-        if (L::STAGE_OUT0)
-        {
-            __syncthreads();
-            stage_out<real, Body::N_OUT0 ? Body::N_OUT0 : 1, BLOCK>(out0 + first * Body::N_OUT0,
-                                                                   smem + L::OFFO, rows);
-        }
-    }
-
-    template <typename real, typename Body, int MIN_BLOCKS>
-    cudaError_t launchRoles(const LaunchArgs &a)
-    {
-        using L = RoleLayout<Body, real>;
-        auto kernel = grbda_role_kernel<real, Body, MIN_BLOCKS>;
-        if (L::BYTES > 48 * 1024)
-        {
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES);
-            if (e != cudaSuccess)
-                return e;
-        }
-        if (a.batch <= 0)
-            return cudaSuccess;
-        const int64_t grid = (a.batch + L::TILE - 1) / L::TILE;
-        kernel<<<(unsigned)grid, Body::W * 32, L::BYTES, a.stream>>>(
-            (const real *)a.in[0], (const real *)a.in[1], (const real *)a.in[2], (real *)a.out[0],
-            (real *)a.out[1], (real *)a.out[2], a.batch);
-        return cudaGetLastError();
-    }
+#endif // !__CUDACC_RTC__
 
 } // namespace grbda_kernels
+#endif // GRBDA_KERNELS_BATCHED_KERNEL_CUH

@@ -1,0 +1,59 @@
+// Shared-memory layouts of the kernel shells as functions of plain sizes. Plain C++ (no CUDA constructs)
+// so that the device code (kernels/batched_kernel.cuh, also under NVRTC), the ahead-of-time tool
+// (tools/modelc.cpp) and the run-time compiler (runtime/jit.cpp) size tiles with the same code.
+#ifndef GRBDA_KERNELS_SHAPES_H // (NVRTC sees this header under two include names: #pragma once is not enough)
+#define GRBDA_KERNELS_SHAPES_H
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+#define GRBDA_HD __host__ __device__
+#else
+#include <stddef.h>
+#define GRBDA_HD
+#endif
+
+namespace grbda_kernels
+{
+    // values per chunk of the chunked output staging (kernels with large outputs: FK, H)
+    constexpr int OUT_CHUNK = 16;
+    // largest software-staged tile set the flagged-tile pass keeps in shared memory; beyond it the pass uses
+    // direct global I/O, and a body of such a program is never parked (it would write into caller memory)
+    constexpr size_t SLOW_PASS_STAGED_LIMIT = 200 * 1024;
+    // shared memory one SM can give to resident CTAs (227 KB opt-in per CTA, 1 KB reserved per CTA)
+    constexpr size_t SM_SHARED_BYTES = 228 * 1024;
+
+    // Row stride (in elements) of a staged tile: odd, so that thread t reading element i of its
+    // own state (address t * stride + i) hits 32 distinct banks for 4-byte and 16 distinct bank
+    // pairs per half warp for 8-byte elements.
+    GRBDA_HD constexpr int oddStride(int n) { return n | 1; }
+
+    // elem = sizeof(real); the static_asserts in the kernels keep these in step with TileLayout / TmaLayout
+    GRBDA_HD constexpr size_t shapeAlign16(size_t x) { return (x + 15) & ~(size_t)15; }
+    GRBDA_HD constexpr size_t shapeStageBytes(const int *n_out, int stage_buffers, int block, int elem)
+    {
+        return (n_out[0] > 64 || n_out[1] > OUT_CHUNK || n_out[2] > OUT_CHUNK)
+                   ? (size_t)stage_buffers * block * (OUT_CHUNK + 1) * elem
+                   : 0;
+    }
+    GRBDA_HD constexpr size_t shapeTileBytes(const int *n_in, const int *n_out, int stage_buffers, int block,
+                                                        int elem)
+    {
+        size_t elems = 0;
+        for (int i = 0; i < 3; i++)
+            elems += n_in[i] ? (size_t)oddStride(n_in[i]) * block : 0;
+        elems += n_out[0] <= 64 ? (size_t)oddStride(n_out[0]) * block : 0;
+        return shapeAlign16(elems * elem) + shapeStageBytes(n_out, stage_buffers, block, elem);
+    }
+    GRBDA_HD constexpr int shapeTmaStride(int n, int elem)
+    {
+        return (n >= 12 && (n * elem) % 16 == 0) ? n + 16 / elem : n;
+    }
+    GRBDA_HD constexpr size_t shapeTmaBytes(const int *n_in, const int *n_out, int stage_buffers, int block,
+                                                       int elem)
+    {
+        size_t off = 16;
+        for (int i = 0; i < 3; i++)
+            off = shapeAlign16(off + (size_t)shapeTmaStride(n_in[i], elem) * block * elem);
+        off = shapeAlign16(off + (n_out[0] <= 64 ? (size_t)shapeTmaStride(n_out[0], elem) * block * elem : 0));
+        return off + shapeStageBytes(n_out, stage_buffers, block, elem);
+    }
+} // namespace grbda_kernels
+#endif // GRBDA_KERNELS_SHAPES_H

@@ -9,9 +9,9 @@
 //                                                uniform, dependent ones by Newton on phi from a
 //                                                guess in [-0.1, 0.1], up to 45 restarts)
 // The per-cluster constraint function (phi, K_d) is generated code (struct C below).
-#pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
+#ifndef GRBDA_KERNELS_STATEGEN_CUH // (NVRTC sees this header under two include names: #pragma once is not enough)
+#define GRBDA_KERNELS_STATEGEN_CUH
+#include "batched_kernel.cuh" // integer typedefs that also work under NVRTC
 
 namespace grbda_kernels
 {
@@ -265,3 +265,4 @@ namespace grbda_kernels
     }
 
 } // namespace grbda_kernels
+#endif // GRBDA_KERNELS_STATEGEN_CUH

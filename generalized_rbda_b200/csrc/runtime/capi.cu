@@ -9,12 +9,14 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include "../../../include/grbda_cuda.h"
 #include "../compiler/compile.h"
 #include "../host/robots.h"
 #include "../host/schedule.h"
+#include "jit.h"
 #include "registry.h"
 #include "support_kernels.cuh"
 
@@ -26,12 +28,15 @@ struct grbda_model
     ClusterTreeModel model;
     uint64_t hash = 0;
     int device = -1;
-    const ModelKernels *kernels = nullptr;
+    const ModelKernels *kernels = nullptr;         // ahead-of-time kernels (build.py MODELS), or
+    std::unique_ptr<grbda_runtime::JitModel> jit;  // kernels compiled at run time (runtime/jit.h)
+    bool hasKernels() const { return kernels || jit; }
     // host-buffer pipeline (grbda_cuda_dynamics_host_f64)
     std::mutex host_mutex;
     static constexpr int NSTREAM = 3;
     cudaStream_t streams[NSTREAM] = {nullptr, nullptr, nullptr};
     double *dev_buf[NSTREAM] = {nullptr, nullptr, nullptr};
+    double *pin_buf[NSTREAM] = {nullptr, nullptr, nullptr}; // pinned staging for pageable caller buffers
     int64_t dev_capacity = 0; // states per stream buffer
     // per-stream scratch of the kernels (tile flags of the sin/cos range decision). Launches on one
     // stream are ordered, so they can share a buffer; different streams get different buffers.
@@ -111,7 +116,8 @@ namespace
         h->model = std::move(m);
         h->hash = modelHash(h->model);
         h->device = device;
-        h->kernels = grbda_runtime::findModelKernels(h->hash);
+        const int jit_mode = grbda_runtime::jitMode();
+        h->kernels = jit_mode == 2 ? nullptr : grbda_runtime::findModelKernels(h->hash);
         if (device >= 0)
         {
             int count = 0;
@@ -124,13 +130,18 @@ namespace
             }
             if (!h->kernels)
             {
-                char buf[256];
-                std::snprintf(buf, sizeof(buf),
-                              "no sm_100a kernels were compiled for this model (hash %016llx); add it to "
-                              "generalized_rbda_b200/build.py and rebuild",
-                              (unsigned long long)h->hash);
-                delete h;
-                return fail(GRBDA_ERR_NOT_COMPILED, buf);
+                if (jit_mode == 0)
+                {
+                    char buf[256];
+                    std::snprintf(buf, sizeof(buf),
+                                  "no sm_100a kernels were compiled ahead of time for this model (hash %016llx) and "
+                                  "run-time compilation is disabled (GRBDA_JIT=0)",
+                                  (unsigned long long)h->hash);
+                    delete h;
+                    return fail(GRBDA_ERR_NOT_COMPILED, buf);
+                }
+                // kernels are compiled by NVRTC when an entry point is first used (or grbda_cuda_model_prepare)
+                h->jit.reset(new grbda_runtime::JitModel());
             }
         }
         *out = h;
@@ -150,33 +161,87 @@ namespace
         }
     }
 
+    // RAII: make the model's device current for the duration of a call, restore the caller's afterwards
+    struct DeviceScope
+    {
+        int previous = -1;
+        cudaError_t error = cudaSuccess;
+        explicit DeviceScope(int device)
+        {
+            error = cudaGetDevice(&previous);
+            if (error == cudaSuccess && previous != device)
+                error = cudaSetDevice(device);
+            else
+                previous = -1;
+        }
+        ~DeviceScope()
+        {
+            if (previous >= 0)
+                cudaSetDevice(previous);
+        }
+    };
+
+    // sizes of an entry point whatever the kernel source; false: the entry point does not exist for this model
+    bool entrySizes(const grbda_model *m, int algo, bool f32, int n_in[3], int n_out[3])
+    {
+        if (m->kernels)
+        {
+            const grbda_runtime::AlgoKernels &ak = m->kernels->algo[algo];
+            std::memcpy(n_in, ak.n_in, sizeof(ak.n_in));
+            std::memcpy(n_out, ak.n_out, sizeof(ak.n_out));
+            return (f32 ? ak.f32[0] : ak.f64[0]) != nullptr;
+        }
+        compiler::algoSizes(m->model, algo, n_in, n_out);
+        return n_out[0] > 0;
+    }
+
     grbda_status launchAlgo(const grbda_model *m, int algo, bool f32, const void *in0, const void *in1,
                             const void *in2, void *out0, void *out1, void *out2, int64_t batch, void *stream)
     {
         if (!m)
             return fail(GRBDA_ERR_INVALID_ARGUMENT, "null model");
-        if (m->device < 0 || !m->kernels)
+        if (m->device < 0 || !m->hasKernels())
             return fail(GRBDA_ERR_NO_DEVICE, "model was created without a CUDA device (host-only handle)");
         if (batch < 0)
             return fail(GRBDA_ERR_INVALID_ARGUMENT, "negative batch");
-        const grbda_runtime::AlgoKernels &ak = m->kernels->algo[algo];
-        int v = kernelVariant();
-        grbda_runtime::LaunchFn fn = f32 ? ak.f32[v] : ak.f64[v];
-        if (!fn)
-            fn = f32 ? ak.f32[0] : ak.f64[0];
-        if (!fn)
-            return fail(GRBDA_ERR_NOT_COMPILED, std::string("kernel '") + compiler::algoName(algo) +
-                                                    (f32 ? "' (f32)" : "' (f64)") +
-                                                    " was not compiled for this model");
+        DeviceScope scope(m->device);
+        if (scope.error != cudaSuccess)
+            return cudaFail(scope.error, "cudaSetDevice");
+        int n_in[3], n_out[3];
+        grbda_runtime::LaunchFn fn = nullptr;
+        const grbda_runtime::JitKernel *jk = nullptr;
+        if (m->kernels)
+        {
+            const grbda_runtime::AlgoKernels &ak = m->kernels->algo[algo];
+            entrySizes(m, algo, f32, n_in, n_out);
+            const char *vs = std::getenv("GRBDA_KERNEL_VARIANT");
+            const int v = kernelVariant();
+            fn = f32 ? ak.f32[v] : ak.f64[v];
+            if (!fn && !vs)
+                fn = f32 ? ak.f32[0] : ak.f64[0];
+            if (!fn)
+                return fail(GRBDA_ERR_NOT_COMPILED, std::string("kernel '") + compiler::algoName(algo) +
+                                                        (f32 ? "' (f32)" : "' (f64)") + (vs ? " variant " + std::string(vs) : std::string()) +
+                                                        " was not compiled for this model");
+        }
+        else
+        {
+            std::string err;
+            if (!grbda_runtime::jitPrepare(*m->jit, m->model, m->hash, m->device, algo, f32, err))
+                return fail(GRBDA_ERR_NOT_COMPILED, std::string("kernel '") + compiler::algoName(algo) + "': " + err);
+            jk = &m->jit->algo[algo][f32 ? 1 : 0];
+            std::memcpy(n_in, jk->n_in, sizeof(jk->n_in));
+            std::memcpy(n_out, jk->n_out, sizeof(jk->n_out));
+        }
         if (batch == 0)
             return GRBDA_OK;
         const void *ins[3] = {in0, in1, in2};
         void *outs[3] = {out0, out1, out2};
         for (int i = 0; i < 3; i++)
         {
-            if (ak.n_in[i] && !ins[i])
+            if (n_in[i] && !ins[i])
                 return fail(GRBDA_ERR_INVALID_ARGUMENT, "null input pointer");
-            if (ak.n_out[i] && !outs[i])
+            if (n_out[i] && !outs[i])
                 return fail(GRBDA_ERR_INVALID_ARGUMENT, "null output pointer");
         }
         grbda_kernels::LaunchArgs a;
@@ -193,7 +258,7 @@ namespace
             return fail(GRBDA_ERR_CUDA, "cannot allocate the kernel scratch buffer: " + m->scratch_error);
         int launched = 0;
         a.launched = &launched;
-        cudaError_t e = fn(a);
+        cudaError_t e = jk ? grbda_runtime::jitLaunch(*jk, f32, a) : fn(a);
         if (e != cudaSuccess)
             return cudaFail(e, "kernel launch");
         g_launches += launched ? launched : 1;
@@ -232,12 +297,16 @@ extern "C"
         {
             if (m->dev_buf[i])
                 cudaFree(m->dev_buf[i]);
+            if (m->pin_buf[i])
+                cudaFreeHost(m->pin_buf[i]);
             if (m->streams[i])
                 cudaStreamDestroy(m->streams[i]);
         }
         for (auto &kv : m->scratch)
             if (kv.second.ptr)
                 cudaFree(kv.second.ptr);
+        if (m->jit)
+            grbda_runtime::jitRelease(*m->jit);
         delete m;
         return GRBDA_OK;
     }
@@ -366,32 +435,18 @@ extern "C"
     {
         if (!m || !counts8 || algo < 0 || algo >= compiler::ALGO_COUNT)
             return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        if (m->jit)
+        {
+            std::string err;
+            if (!grbda_runtime::jitPrepare(*m->jit, m->model, m->hash, m->device, algo, false, err))
+                return fail(GRBDA_ERR_NOT_COMPILED, err);
+            std::memcpy(counts8, m->jit->algo[algo][0].counts, 8 * sizeof(int64_t));
+            return GRBDA_OK;
+        }
         if (!m->kernels || !m->kernels->algo[algo].f64[0])
             return fail(GRBDA_ERR_NOT_COMPILED, "no compiled kernel for this model / algorithm");
         std::memcpy(counts8, m->kernels->algo[algo].counts, 8 * sizeof(int64_t));
         return GRBDA_OK;
-    }
-
-    grbda_status grbda_cuda_dump_role_program(const grbda_model *m, int algo, const char *path, int64_t *info4)
-    {
-        if (!m || algo < 0 || algo >= compiler::PROGRAM_COUNT || algo == compiler::ALGO_GFA || algo == compiler::ALGO_GFS)
-            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
-        return guarded([&]
-                       {
-            const compiler::CompiledRoles c = compiler::compileAlgoRoles(m->model, algo, false);
-            if (path)
-                compiler::writeRoleTape(c, path);
-            if (info4)
-            {
-                int64_t mx = 0, sum = 0;
-                for (auto &s : c.stats)
-                {
-                    mx = std::max<int64_t>(mx, s.flops());
-                    sum += s.flops();
-                }
-                info4[0] = c.W, info4[1] = c.num_slots, info4[2] = mx, info4[3] = sum;
-            }
-            return (grbda_status)GRBDA_OK; });
     }
 
     // ---- device-pointer hot path -------------------------------------------------------------------
@@ -490,67 +545,144 @@ extern "C"
     }
 
     // ---- host-pointer path: chunks pipelined over three streams --------------------------------------
-    // mode 0: ID, 1: FD, 2: FD followed by ID of the result (out2 = tau_back)
+    // mode 0: ID, 1: FD, 2: FD followed by ID of the result (out2 = tau_back).
+    // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used in place:
+    // the copies of one chunk overlap the kernels and copies of the others. Pageable buffers are staged
+    // through the handle's own pinned buffers, chunk by chunk, so that the overlap survives (an async copy
+    // from pageable memory is synchronous).
+    static bool isPinned(const void *p)
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess)
+        {
+            (void)cudaGetLastError();
+            return false;
+        }
+        return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+    }
+
     static grbda_status hostPipeline(grbda_model *m, int mode, const double *q, const double *yd,
                                      const double *in3, double *out, double *out2, int64_t batch)
     {
-        if (m->device < 0 || !m->kernels)
+        if (m->device < 0 || !m->hasKernels())
             return fail(GRBDA_ERR_NO_DEVICE, "model was created without a CUDA device (host-only handle)");
+        if (batch < 0)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "negative batch");
         std::lock_guard<std::mutex> lock(m->host_mutex);
-        cudaError_t e = cudaSetDevice(m->device);
+        DeviceScope scope(m->device);
+        cudaError_t e = scope.error;
         if (e != cudaSuccess)
             return cudaFail(e, "cudaSetDevice");
         const int nq = m->model.getNumPositions(), nv = m->model.getNumDegreesOfFreedom();
         const int64_t per_state = nq + 4 * (int64_t)nv; // q, yd, in3, out, out2 (doubles)
+        const bool staged = !(isPinned(q) && isPinned(yd) && isPinned(in3) && isPinned(out) && (mode != 2 || isPinned(out2)));
         // measured (tools/e2e_sweep.py, 2^20 Tello states): 16 k -> 57.6, 32 k -> 67.0, 64 k -> 70.7, 128 k -> 72.3,
         // 256 k -> 68.6 M fwd+inv/s; the call is bound by the host link (47 GB/s in, 28 GB/s out, concurrently)
-        int64_t chunk = 1 << 17;
+        int64_t chunk = staged ? 1 << 15 : 1 << 17;
         if (const char *c = std::getenv("GRBDA_HOST_CHUNK")) // tuning knob (states per pipelined chunk)
             chunk = std::max<int64_t>(1024, std::atoll(c));
-        if (m->dev_capacity != chunk)
+        if (m->dev_capacity != chunk || (staged && !m->pin_buf[0]))
         {
             for (int i = 0; i < grbda_model::NSTREAM; i++)
             {
                 if (!m->streams[i] && (e = cudaStreamCreateWithFlags(&m->streams[i], cudaStreamNonBlocking)) != cudaSuccess)
                     return cudaFail(e, "cudaStreamCreate");
-                if (m->dev_buf[i])
-                    cudaFree(m->dev_buf[i]);
-                if ((e = cudaMalloc(&m->dev_buf[i], chunk * per_state * sizeof(double))) != cudaSuccess)
-                    return cudaFail(e, "cudaMalloc");
+                if (m->dev_capacity != chunk)
+                {
+                    if (m->dev_buf[i])
+                        cudaFree(m->dev_buf[i]);
+                    m->dev_buf[i] = nullptr;
+                    if (m->pin_buf[i])
+                        cudaFreeHost(m->pin_buf[i]);
+                    m->pin_buf[i] = nullptr;
+                    if ((e = cudaMalloc(&m->dev_buf[i], chunk * per_state * sizeof(double))) != cudaSuccess)
+                        return cudaFail(e, "cudaMalloc");
+                }
+                if (staged && !m->pin_buf[i] &&
+                    (e = cudaHostAlloc((void **)&m->pin_buf[i], chunk * per_state * sizeof(double), cudaHostAllocDefault)) != cudaSuccess)
+                    return cudaFail(e, "cudaHostAlloc");
             }
             m->dev_capacity = chunk;
         }
+        // staged mode: results of the chunk a stream worked on last, still to be copied to the caller
+        struct Pending
+        {
+            int64_t b0 = 0, nb = 0;
+        } pending[grbda_model::NSTREAM];
+        grbda_status rs = GRBDA_OK;
+        auto drain = [&](int s) -> cudaError_t
+        {
+            cudaError_t de = cudaStreamSynchronize(m->streams[s]);
+            if (de == cudaSuccess && staged && pending[s].nb)
+            {
+                const double *pout = m->pin_buf[s] + chunk * (nq + 2 * (int64_t)nv);
+                std::memcpy(out + pending[s].b0 * nv, pout, pending[s].nb * nv * 8);
+                if (mode == 2)
+                    std::memcpy(out2 + pending[s].b0 * nv, pout + chunk * nv, pending[s].nb * nv * 8);
+            }
+            pending[s].nb = 0;
+            return de;
+        };
         int k = 0;
-        for (int64_t b0 = 0; b0 < batch; b0 += chunk, k++)
+        for (int64_t b0 = 0; b0 < batch && rs == GRBDA_OK; b0 += chunk, k++)
         {
             const int64_t nb = std::min(chunk, batch - b0);
             const int s = k % grbda_model::NSTREAM;
             cudaStream_t st = m->streams[s];
             double *dq = m->dev_buf[s], *dyd = dq + chunk * nq, *din = dyd + chunk * nv, *dout = din + chunk * nv,
                    *dout2 = dout + chunk * nv;
-            if ((e = cudaMemcpyAsync(dq, q + b0 * nq, nb * nq * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
-                (e = cudaMemcpyAsync(dyd, yd + b0 * nv, nb * nv * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
-                (e = cudaMemcpyAsync(din, in3 + b0 * nv, nb * nv * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-                return cudaFail(e, "cudaMemcpyAsync H2D");
-            grbda_status rs = launchAlgo(m, mode == 0 ? compiler::ALGO_ID : compiler::ALGO_FD, false, dq, dyd, din,
-                                         dout, nullptr, nullptr, nb, st);
+            const double *hq = q + b0 * nq, *hyd = yd + b0 * nv, *hin = in3 + b0 * nv;
+            double *hout = out + b0 * nv, *hout2 = out2 ? out2 + b0 * nv : nullptr;
+            if (staged)
+            {
+                if ((e = drain(s)) != cudaSuccess) // the stream's pinned buffer is free again
+                {
+                    rs = cudaFail(e, "cudaStreamSynchronize");
+                    break;
+                }
+                double *pq = m->pin_buf[s], *pyd = pq + chunk * nq, *pin = pyd + chunk * nv, *pout = pin + chunk * nv;
+                std::memcpy(pq, hq, nb * nq * 8);
+                std::memcpy(pyd, hyd, nb * nv * 8);
+                std::memcpy(pin, hin, nb * nv * 8);
+                hq = pq, hyd = pyd, hin = pin, hout = pout, hout2 = pout + chunk * nv;
+                pending[s].b0 = b0, pending[s].nb = nb;
+            }
+            if ((e = cudaMemcpyAsync(dq, hq, nb * nq * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(dyd, hyd, nb * nv * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(din, hin, nb * nv * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+            {
+                rs = cudaFail(e, "cudaMemcpyAsync H2D");
+                break;
+            }
+            rs = launchAlgo(m, mode == 0 ? compiler::ALGO_ID : compiler::ALGO_FD, false, dq, dyd, din, dout, nullptr,
+                            nullptr, nb, st);
             if (rs != GRBDA_OK)
-                return rs;
-            if ((e = cudaMemcpyAsync(out + b0 * nv, dout, nb * nv * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
-                return cudaFail(e, "cudaMemcpyAsync D2H");
+                break;
+            if ((e = cudaMemcpyAsync(hout, dout, nb * nv * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+            {
+                rs = cudaFail(e, "cudaMemcpyAsync D2H");
+                break;
+            }
             if (mode == 2)
             {
                 rs = launchAlgo(m, compiler::ALGO_ID, false, dq, dyd, dout, dout2, nullptr, nullptr, nb, st);
                 if (rs != GRBDA_OK)
-                    return rs;
-                if ((e = cudaMemcpyAsync(out2 + b0 * nv, dout2, nb * nv * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
-                    return cudaFail(e, "cudaMemcpyAsync D2H");
+                    break;
+                if ((e = cudaMemcpyAsync(hout2, dout2, nb * nv * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+                {
+                    rs = cudaFail(e, "cudaMemcpyAsync D2H");
+                    break;
+                }
             }
         }
+        // also on the error paths: no copy on a caller buffer may still be in flight when the call returns
+        const std::string first_error = g_error;
         for (int i = 0; i < grbda_model::NSTREAM; i++)
-            if ((e = cudaStreamSynchronize(m->streams[i])) != cudaSuccess)
-                return cudaFail(e, "cudaStreamSynchronize");
-        return GRBDA_OK;
+            if (m->streams[i] && (e = drain(i)) != cudaSuccess && rs == GRBDA_OK)
+                rs = cudaFail(e, "cudaStreamSynchronize");
+        if (rs != GRBDA_OK && !first_error.empty())
+            g_error = first_error;
+        return rs;
     }
 
     grbda_status grbda_cuda_dynamics_host_f64(const grbda_model *cm, int algo, const double *q, const double *yd,
@@ -571,6 +703,89 @@ extern "C"
         return hostPipeline(m, 2, q, yd, tau, ydd, tau_back, batch);
     }
 
+    // ---- kernel provenance / run-time compilation ------------------------------------------------------
+    grbda_status grbda_cuda_model_prepare(const grbda_model *m, int algo, int f32)
+    {
+        if (!m || algo < 0 || algo >= compiler::ALGO_COUNT)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        if (m->device < 0 || !m->hasKernels())
+            return fail(GRBDA_ERR_NO_DEVICE, "model was created without a CUDA device (host-only handle)");
+        if (m->kernels)
+            return (f32 ? m->kernels->algo[algo].f32[0] : m->kernels->algo[algo].f64[0])
+                       ? GRBDA_OK
+                       : fail(GRBDA_ERR_NOT_COMPILED, "entry point was not compiled ahead of time for this model");
+        std::string err;
+        if (!grbda_runtime::jitPrepare(*m->jit, m->model, m->hash, m->device, algo, f32 != 0, err))
+            return fail(GRBDA_ERR_NOT_COMPILED, err);
+        return GRBDA_OK;
+    }
+
+    grbda_status grbda_cuda_kernel_info(const grbda_model *m, int algo, int f32, int64_t *info8)
+    {
+        if (!m || !info8 || algo < 0 || algo >= compiler::ALGO_COUNT)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        std::memset(info8, 0, 8 * sizeof(int64_t));
+        if (m->kernels)
+        {
+            info8[0] = 0;
+            info8[7] = (f32 ? m->kernels->algo[algo].f32[0] : m->kernels->algo[algo].f64[0]) ? 1 : 0;
+            return GRBDA_OK;
+        }
+        return guarded([&]
+                       {
+            grbda_runtime::JitKernel local;
+            const grbda_runtime::JitKernel *k = &local;
+            std::string err;
+            if (m->jit && m->jit->algo[algo][f32 ? 1 : 0].ready)
+                k = &m->jit->algo[algo][f32 ? 1 : 0];
+            else if (!grbda_runtime::jitDescribe(m->model, algo, f32 != 0, local, err))
+                return fail(GRBDA_ERR_NOT_COMPILED, err);
+            info8[0] = 1;
+            info8[1] = k->shape.block;
+            info8[2] = k->shape.min_blocks;
+            info8[3] = (int64_t)k->shape.smem_fast;
+            info8[4] = k->shape.program;
+            info8[5] = (k->shape.park ? 1 : 0) | (k->shape.kind == 'T' ? 2 : 0) | (k->shape.kind == 'D' ? 4 : 0) |
+                       (k->from_cache ? 8 : 0);
+            info8[6] = (int64_t)(k->compile_seconds * 1000.0);
+            info8[7] = k->ready ? 1 : 0;
+            return (grbda_status)GRBDA_OK; });
+    }
+
+    grbda_status grbda_cuda_jit_compile(const grbda_model *m, int algo, int f32, const char *source_path,
+                                        const char *cubin_path)
+    {
+        if (!m || algo < -1 || algo >= compiler::ALGO_COUNT)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        return guarded([&]
+                       {
+            grbda_runtime::JitKernel k;
+            std::vector<std::string> names, lowered;
+            const std::string src = algo < 0 ? grbda_runtime::jitGenerateSource(m->model, names)
+                                             : grbda_runtime::jitSource(m->model, algo, f32 != 0, k, names);
+            if (source_path)
+            {
+                std::ofstream f(source_path);
+                if (!f)
+                    return fail(GRBDA_ERR_IO, std::string("cannot write ") + source_path);
+                f << src;
+                for (auto &n : names)
+                    f << "// kernel: " << n << "\n";
+            }
+            if (cubin_path)
+            {
+                std::vector<char> cubin;
+                std::string log;
+                if (!grbda_runtime::jitCompile(src, names, cubin, lowered, log))
+                    return fail(GRBDA_ERR_NOT_COMPILED, log);
+                std::ofstream f(cubin_path, std::ios::binary);
+                if (!f)
+                    return fail(GRBDA_ERR_IO, std::string("cannot write ") + cubin_path);
+                f.write(cubin.data(), (std::streamsize)cubin.size());
+            }
+            return (grbda_status)GRBDA_OK; });
+    }
+
     // ---- states, checks, measurement -----------------------------------------------------------------
     grbda_status grbda_cuda_generate_states(const grbda_model *m, uint64_t seed, int64_t first_index,
                                             int64_t count, double *q, double *yd, double *aux, int32_t *flags,
@@ -578,12 +793,21 @@ extern "C"
     {
         if (!m || !q || !yd || !aux || count < 0)
             return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
-        if (m->device < 0 || !m->kernels)
+        if (m->device < 0 || !m->hasKernels())
             return fail(GRBDA_ERR_NO_DEVICE, "model was created without a CUDA device (host-only handle)");
-        if (!m->kernels->generate)
+        if (m->kernels && !m->kernels->generate)
             return fail(GRBDA_ERR_NOT_COMPILED, "state generator was not compiled for this model");
+        DeviceScope scope(m->device);
+        if (scope.error != cudaSuccess)
+            return cudaFail(scope.error, "cudaSetDevice");
         grbda_runtime::GenArgs a{seed, first_index, count, q, yd, aux, flags, (cudaStream_t)stream};
-        cudaError_t e = m->kernels->generate(a);
+        if (m->jit)
+        {
+            std::string err;
+            if (!grbda_runtime::jitPrepareGenerate(*m->jit, m->model, m->hash, m->device, err))
+                return fail(GRBDA_ERR_NOT_COMPILED, "state generator: " + err);
+        }
+        cudaError_t e = m->jit ? grbda_runtime::jitLaunchGenerate(m->jit->generate, a) : m->kernels->generate(a);
         if (e != cudaSuccess)
             return cudaFail(e, "generate launch");
         g_launches++;
@@ -595,11 +819,17 @@ extern "C"
     {
         if (!m || !q || !max_abs_phi)
             return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
-        if (m->device < 0 || !m->kernels)
+        if (m->device < 0 || !m->hasKernels())
             return fail(GRBDA_ERR_NO_DEVICE, "model was created without a CUDA device (host-only handle)");
+        DeviceScope scope(m->device);
+        if (scope.error != cudaSuccess)
+            return cudaFail(scope.error, "cudaSetDevice");
         cudaStream_t st = (cudaStream_t)stream;
-        const grbda_runtime::AlgoKernels &ak = m->kernels->algo[compiler::ALGO_PHI];
-        if (!ak.f64[0])
+        struct
+        {
+            int n_in[3], n_out[3];
+        } ak;
+        if (!entrySizes(m, compiler::ALGO_PHI, false, ak.n_in, ak.n_out))
         {
             // no implicit cluster: violation is zero by definition
             cudaError_t e = cudaMemsetAsync(max_abs_phi, 0, batch * 8, st);

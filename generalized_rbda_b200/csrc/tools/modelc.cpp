@@ -13,6 +13,7 @@
 #include "../compiler/compile.h"
 #include "../host/robots.h"
 #include "../host/schedule.h"
+#include "../kernels/shapes.h"
 
 using namespace grbda;
 using namespace grbda::compiler;
@@ -23,7 +24,7 @@ namespace
     {
         int sync = -1; // alignment barrier period in statements (-1: the --sync-every default)
         char kind; // 'S' one state per thread, software-staged I/O; 'T' the same with TMA bulk-copy staging;
-                   // 'D' direct global I/O; 'R' one limb per warp
+                   // 'D' direct global I/O
         int block, min_blocks;
         int program = -1; // alternative program of the entry point (-1: the entry's own), e.g. PROGRAM_FD_LTL
         bool park = false; // staged shells: long-lived values are parked in dead slots of the thread's tile row
@@ -49,35 +50,6 @@ namespace
             if (!isalnum((unsigned char)c))
                 c = '_';
         return s;
-    }
-
-    void emitRoleStruct(std::ostream &os, const std::string &struct_name, const CompiledRoles &c)
-    {
-        os << "struct " << struct_name << "\n{\n";
-        os << "    static constexpr int W = " << c.W << ", NUM_SLOTS = " << c.num_slots << ";\n";
-        os << "    static constexpr int N_IN0 = " << c.n_in[0] << ", N_IN1 = " << c.n_in[1]
-           << ", N_IN2 = " << c.n_in[2] << ";\n";
-        os << "    static constexpr int N_OUT0 = " << c.n_out[0] << ", N_OUT1 = " << c.n_out[1]
-           << ", N_OUT2 = " << c.n_out[2] << ";\n";
-        os << "    template <typename real>\n";
-        os << "    static __device__ __forceinline__ void run(const int role, const real *__restrict__ in0,\n"
-              "        const real *__restrict__ in1, const real *__restrict__ in2, real *__restrict__ out0,\n"
-              "        real *__restrict__ out1, real *__restrict__ out2, real *__restrict__ comm)\n    {\n";
-        os << "#define KC(x) ((real)(x))\n#define KT(i) kc_table<real>(i)\n#define IN0(i) in0[i]\n#define IN1(i) in1[i]\n#define IN2(i) in2[i]\n"
-              "#define OUT0(i, x) out0[i] = (x)\n#define OUT1(i, x) out1[i] = (x)\n#define OUT2(i, x) out2[i] = (x)\n"
-              "#define COMM_ST(s, x) comm[(s) * 32] = (x)\n#define COMM_LD(s) comm[(s) * 32]\n"
-              "#define ROLE_BARRIER() roleBarrier<W * 32>()\n";
-        os << "        switch (role)\n        {\n";
-        for (int r = 0; r < c.W; r++)
-        {
-            os << "        case " << r << ":\n        {\n";
-            os << c.bodies[r];
-            os << "        }\n        break;\n";
-        }
-        os << "        default: break;\n        }\n";
-        os << "#undef KC\n#undef KT\n#undef IN0\n#undef IN1\n#undef IN2\n#undef OUT0\n#undef OUT1\n#undef OUT2\n"
-              "#undef COMM_ST\n#undef COMM_LD\n#undef ROLE_BARRIER\n";
-        os << "    }\n};\n";
     }
 
     void writeIfChanged(const std::string &path, const std::string &text)
@@ -156,7 +128,7 @@ int main(int argc, char **argv)
         {
             auto p = split(v, ',');
             if (p.size() < 3 || p.size() > 7 || p[0].size() != 1 ||
-                std::string("SDRT").find(p[0][0]) == std::string::npos)
+                std::string("SDT").find(p[0][0]) == std::string::npos)
                 throw std::runtime_error("bad --variants entry '" + v +
                                          "' (expected KIND,BLOCK,MINBLOCKS[,SYNC][,ltl][,park][,f32aba])");
             Variant var;
@@ -216,10 +188,18 @@ int main(int argc, char **argv)
             for (auto &v : variants)
                 if (v.sync < 0)
                     v.sync = sync_every;
-            const int out_chunk = 16; // = grbda_kernels::OUT_CHUNK; only arrays with more than 64 values use it
+            const int out_chunk = grbda_kernels::OUT_CHUNK; // only arrays with more than 64 values use it
             for (auto &v : variants)
                 if (v.program >= 0 && algoOfProgram(v.program) != a)
                     v.program = -1; // "ltl" only applies to fd
+            {
+                // a parked body writes into its tile rows: only where the flagged-tile pass stages them too
+                int n_in[3], n_out[3];
+                algoSizes(model, a, n_in, n_out);
+                for (auto &v : variants)
+                    if (v.park && grbda_kernels::shapeTileBytes(n_in, n_out, 3, v.block, 8) > grbda_kernels::SLOW_PASS_STAGED_LIMIT)
+                        v.park = false;
+            }
             auto programOf = [&](const Variant &v) { return v.program >= 0 ? v.program : a; };
             auto bodyKey = [&](const Variant &v) { return (v.sync * 2 + (v.park ? 1 : 0)) * 16 + programOf(v); };
             const CompiledAlgo c = compileAlgo(model, programOf(variants[0]), true, variants[0].sync, &consts, out_chunk,
@@ -235,26 +215,14 @@ int main(int argc, char **argv)
             };
             for (auto &v : variants)
             {
-                if (v.kind != 'R' && !by_sync.count(bodyKey(v)))
+                if (!by_sync.count(bodyKey(v)))
                     by_sync[bodyKey(v)] = compileAlgo(model, programOf(v), true, v.sync, &consts, out_chunk, v.park);
                 const Variant u = f32Variant(v);
-                if (v.kind != 'R' && !by_sync.count(bodyKey(u))) // also the body of the direct-I/O fallback
+                if (!by_sync.count(bodyKey(u))) // also the body of the direct-I/O fallback
                     by_sync[bodyKey(u)] = compileAlgo(model, programOf(u), true, u.sync, &consts, out_chunk, false);
             }
             if (a == ALGO_PHI && c.n_out[0] == 0)
                 continue; // no implicit clusters
-            bool want_roles = false, want_single = false;
-            for (auto &v : variants)
-                (v.kind == 'R' ? want_roles : want_single) = true;
-            CompiledRoles roles;
-            if (want_roles && a != ALGO_PHI)
-                for (auto &v : variants)
-                    if (v.kind == 'R')
-                    {
-                        roles = compileAlgoRoles(model, programOf(v), true, &consts);
-                        break;
-                    }
-            const bool have_roles = want_roles && a != ALGO_PHI && roles.W > 1;
             std::ostringstream os;
             os << header_common;
             os << consts.definition("kc_table");
@@ -262,8 +230,6 @@ int main(int argc, char **argv)
                 by_sync[bodyKey(variants[0])] = c;
             for (auto &kv : by_sync)
                 emitBodyStruct(os, "Body" + std::to_string(kv.first), kv.second);
-            if (have_roles)
-                emitRoleStruct(os, "RoleBody", roles);
             os << "} // namespace\n\n";
             auto launcher = [&](const Variant &v0, const char *real) {
                 Variant v = std::string(real) == "float" ? f32Variant(v0) : v0;
@@ -271,9 +237,10 @@ int main(int argc, char **argv)
                 // a program whose rows do not fit into an SM at all falls back to direct global I/O
                 if (v.kind == 'T' || v.kind == 'S')
                 {
-                    const size_t elem = std::string(real) == "float" ? 4 : 8;
-                    const size_t rows = (size_t)c.n_in[0] + c.n_in[1] + c.n_in[2] + 6 + (c.n_out[0] <= 64 ? c.n_out[0] + 2 : 0);
-                    if (rows * elem * v.block > 220 * 1024) // not even one CTA per SM
+                    const int elem = std::string(real) == "float" ? 4 : 8;
+                    const size_t bytes = v.kind == 'T' ? grbda_kernels::shapeTmaBytes(c.n_in, c.n_out, c.stage_buffers, v.block, elem)
+                                                       : grbda_kernels::shapeTileBytes(c.n_in, c.n_out, c.stage_buffers, v.block, elem);
+                    if (bytes + 1024 > grbda_kernels::SM_SHARED_BYTES) // not even one CTA per SM
                     {
                         v.kind = 'D';
                         v.park = false;
@@ -282,13 +249,10 @@ int main(int argc, char **argv)
                     }
                 }
                 std::ostringstream l;
-                if (v.kind == 'R' && have_roles)
-                    l << "&launchRoles<" << real << ", RoleBody, " << v.min_blocks << ">";
-                else if (v.kind == 'T')
+                if (v.kind == 'T')
                     l << "&launchBatchedTma<" << real << ", Body" << bodyKey(v) << ", " << v.block << ", " << v.min_blocks << ">";
                 else
-                    l << "&launchBatched<" << real << ", Body" << (v.kind == 'R' ? by_sync.begin()->first : bodyKey(v)) << ", "
-                      << (v.kind == 'R' ? 128 : v.block) << ", " << (v.kind == 'R' ? 2 : v.min_blocks) << ", "
+                    l << "&launchBatched<" << real << ", Body" << bodyKey(v) << ", " << v.block << ", " << v.min_blocks << ", "
                       << (v.kind == 'D' ? "false" : "true") << ">";
                 return l.str();
             };
@@ -323,70 +287,7 @@ int main(int argc, char **argv)
         {
             std::ostringstream os;
             os << header_common;
-            // one (phi, Kd) evaluator per implicit cluster
-            for (const ClusterTreeNode &c : model.clusters())
-            {
-                if (c.joint_.type != ClusterType::Implicit)
-                    continue;
-                const ClusterDesc &d = c.joint_;
-                sym::Graph graph;
-                sym::GraphScope scope(graph);
-                ModelCompiler mc(model);
-                std::vector<sym::Sym> q(d.num_bodies), phi, K, Kd;
-                for (int i = 0; i < d.num_bodies; i++)
-                    q[i] = sym::Sym::input(0, i);
-                mc.implicitJacobian(d, q, nullptr, phi, K, nullptr);
-                std::vector<int> ind, dep;
-                for (int i = 0; i < d.num_bodies; i++)
-                    (d.independent[i] ? ind : dep).push_back(i);
-                for (int i = 0; i < d.num_constraints; i++)
-                    for (int j : dep)
-                        Kd.push_back(K[i * d.num_bodies + j]);
-                Program p;
-                p.outputs = {phi, Kd};
-                Emitter em(graph, p);
-                os << "struct Cluster" << c.index_ << "\n{\n    static constexpr int N = " << d.num_bodies
-                   << ", NC = " << d.num_constraints << ";\n";
-                os << "    static __device__ __forceinline__ int ind(int i) { const int t[] = {";
-                for (size_t i = 0; i < ind.size(); i++)
-                    os << ind[i] << (i + 1 < ind.size() ? ", " : "");
-                os << "}; return t[i]; }\n";
-                os << "    static __device__ __forceinline__ int dep(int i) { const int t[] = {";
-                for (size_t i = 0; i < dep.size(); i++)
-                    os << dep[i] << (i + 1 < dep.size() ? ", " : "");
-                os << "}; return t[i]; }\n";
-                os << "    static __device__ __noinline__ void eval(const double *q, double *phi, double *Kd)\n    {\n"
-                      "        typedef double real;\n        constexpr bool FAST = false;\n"
-                      "#define KC(x) ((real)(x))\n#define GRBDA_PIN(x, late) (x)\n#define GRBDA_DIV(a, b) ((a) / (b))\n#define IN0(i) q[i]\n#define OUT0(i, x) phi[i] = (x)\n"
-                      "#define OUT1(i, x) Kd[i] = (x)\n";
-                os << em.cudaBody();
-                os << "#undef KC\n#undef KT\n#undef GRBDA_PIN\n#undef GRBDA_DIV\n#undef IN0\n#undef OUT0\n#undef OUT1\n    }\n};\n\n";
-            }
-            os << "struct Gen\n{\n    static constexpr int NQ = " << nq << ", NV = " << nv << ";\n";
-            os << "    static __device__ bool run(Philox &rng, double *q, double *yd, double *aux)\n    {\n"
-                  "        bool ok = true;\n";
-            for (const ClusterTreeNode &c : model.clusters())
-            {
-                const ClusterDesc &d = c.joint_;
-                const int pi = c.position_index_;
-                if (d.type == ClusterType::FreeQuaternion || d.type == ClusterType::FreeRollPitchYaw)
-                {
-                    os << "        for (int i = 0; i < 3; i++) q[" << pi << " + i] = rng.uniform();\n";
-                    os << "        { double rpy[3]; for (int i = 0; i < 3; i++) rpy[i] = rng.uniform();\n";
-                    if (d.type == ClusterType::FreeQuaternion)
-                        os << "          rpyToQuat(rpy, q + " << pi + 3 << "); }\n";
-                    else
-                        os << "          for (int i = 0; i < 3; i++) q[" << pi + 3 << " + i] = rpy[i]; }\n";
-                }
-                else if (d.type == ClusterType::Explicit)
-                    os << "        for (int i = 0; i < " << d.num_positions << "; i++) q[" << pi
-                       << " + i] = rng.uniform();\n";
-                else
-                    os << "        ok = randomImplicitPosition<Cluster" << c.index_ << ">(rng, q + " << pi
-                       << ") && ok;\n";
-            }
-            os << "        for (int i = 0; i < NV; i++) yd[i] = rng.uniform();\n"
-                  "        for (int i = 0; i < NV; i++) aux[i] = rng.uniform();\n        return ok;\n    }\n};\n";
+            emitGenerator(os, model);
             os << "} // namespace\n\n";
             os << "static cudaError_t launchGenerate(const grbda_runtime::GenArgs &a)\n{\n"
                   "    if (a.count <= 0) return cudaSuccess;\n"

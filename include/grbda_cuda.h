@@ -19,13 +19,16 @@
  *     yd / ydd / tau are the independent velocities / accelerations / generalized forces;
  *   - `_f64` / `_f32` entry points take DEVICE pointers and are asynchronous on `stream`
  *     (a cudaStream_t passed as void*, NULL = default stream); `_host` entry points take HOST
- *     pointers, stage through pinned memory and return when the results are in the host buffers;
+ *     pointers and return when the results are in the host buffers: page-locked buffers are used in
+ *     place (copies and kernels of consecutive chunks overlap), pageable buffers are staged chunk by
+ *     chunk through pinned memory the handle owns;
  *   - a batched call enqueues two kernels on `stream` (the straight-line kernel and a normally empty
  *     pass that recomputes 128-state tiles holding a joint angle beyond 1e12 rad with the library
  *     sin/cos) and uses a small scratch buffer that the model handle keeps per stream: calls on
  *     different streams may overlap, calls can be captured in CUDA graphs after one warm-up call;
- *   - there is no CPU implementation behind this API: without a CUDA device (or without compiled
- *     kernels for the model) calls fail with GRBDA_ERR_NO_DEVICE / GRBDA_ERR_NOT_COMPILED.
+ *   - there is no CPU implementation behind this API: without a CUDA device calls fail with
+ *     GRBDA_ERR_NO_DEVICE; a model without ahead-of-time kernels is compiled at run time (below),
+ *     and fails with GRBDA_ERR_NOT_COMPILED if that is disabled or impossible.
  */
 #ifndef GRBDA_CUDA_H
 #define GRBDA_CUDA_H
@@ -160,10 +163,24 @@ grbda_status grbda_cuda_emit_source(const grbda_model *m, int program, int park,
  * (ClusterTreeDynamics.cpp:10-19 / :59-155) up to rounding. */
 grbda_status grbda_cuda_kernel_counts(const grbda_model *m, int algo, int64_t *counts8);
 
-/* The limb-parallel (one warp per limb, compiler/partition.h) form of the same program, written as a
- * role tape; info4 = {W (warps per state), communication slots, max per-role flops, sum of per-role
- * flops}. W = 1 when the model has no trunk with at least two limbs. */
-grbda_status grbda_cuda_dump_role_program(const grbda_model *m, int algo, const char *path, int64_t *info4);
+/* ---- kernel provenance / run-time compilation ------------------------------------------------- */
+/* A model that build.py did not compile ahead of time gets its kernels from the same model compiler
+ * at run time: NVRTC builds the emitted program for sm_100a when an entry point is first used and
+ * the cubin is cached on disk (GRBDA_CACHE_DIR, default ~/.cache/grbda_cuda). This is what lets
+ * grbda_cuda_model_create / _from_urdf accept ANY ClusterTreeModel, as the reference's constructors
+ * do (include/grbda/Dynamics/ClusterTreeModel.h:27-53). GRBDA_JIT=0 turns it off (create then fails
+ * with GRBDA_ERR_NOT_COMPILED), GRBDA_JIT=force ignores the ahead-of-time kernels.
+ * prepare: compile / load the kernels of one entry point now (algo 0 ID, 1 FD, 2 FK, 3 H, 4 phi,
+ * 5 gfa, 6 gfs) instead of on first use, e.g. before capturing a CUDA graph. */
+grbda_status grbda_cuda_model_prepare(const grbda_model *m, int algo, int f32);
+/* info8 = {source (0 ahead of time, 1 run-time compiled), CTA size, CTAs per SM, dynamic shared
+ * memory, program, flags (1 parked, 2 bulk-copy staged, 4 direct I/O, 8 loaded from the disk cache),
+ * NVRTC milliseconds, ready}; fields 1-6 are reported for run-time compiled kernels only. */
+grbda_status grbda_cuda_kernel_info(const grbda_model *m, int algo, int f32, int64_t *info8);
+/* The run-time compiler without a device: writes the CUDA text of one entry point (algo -1: the
+ * state generator) to source_path and / or the sm_100a cubin NVRTC makes of it to cubin_path. */
+grbda_status grbda_cuda_jit_compile(const grbda_model *m, int algo, int f32, const char *source_path,
+                                    const char *cubin_path);
 
 /* ---- batched hot path, device pointers ----------------------------------------------------- */
 /* tau = ID(q, yd, ydd). Replaces setState + ClusterTreeModel::inverseDynamics(ydd),

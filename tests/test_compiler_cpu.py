@@ -8,7 +8,9 @@ import re
 import numpy as np
 import pytest
 
-from tape import load_role_tape, load_tape, run_role_tape, run_tape
+from tape import load_tape, run_tape
+
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # product robot name -> oracle robot name
@@ -110,33 +112,6 @@ def test_rotor_reductions(grbda, oracle, tmp_path):
     assert idc["flops"] < o.count_flops(0)["flops_alg"]
     assert m.kernel_counts(grbda.ALGO_FD) == m.dump_program(grbda.PROGRAM_FD_LTL)
     assert m.kernel_counts(grbda.ALGO_ID) == idc
-
-
-@pytest.mark.parametrize("robot", ["tello", "tello_with_arms"])
-def test_limb_parallel_programs_match_oracle(grbda, oracle, robot, tmp_path):
-    """One warp per limb: each role may only use values it computed or received through a
-    communication slot (the interpreter enforces it), one barrier, same results as the oracle."""
-    m = grbda.ClusterTreeModel.from_robot(robot, device=None)
-    o = oracle.OracleModel(ROBOTS[robot])
-    q, yd, aux = o.generate_states(32, seed=21)
-    ins = [q, yd, aux]
-    res = {}
-    for algo, name in enumerate(grbda.ALGO_NAMES[:4]):
-        path = str(tmp_path / (name + ".rtape"))
-        info = m.dump_role_program(algo, path)
-        assert info["W"] == {"tello": 2, "tello_with_arms": 4}[robot]
-        res[name] = (run_role_tape(load_role_tape(path), ins), info)
-    assert res["fd"][1]["slots"] == res["fd"][1]["W"] * 27  # articulated inertia (21) + bias force (6) per limb
-    assert res["fk"][1]["slots"] == 0       # kinematics needs no exchange
-    assert rel(res["id"][0][0], o.inverse_dynamics(q, yd, aux)) < TOL
-    assert rel(res["fd"][0][0], o.forward_dynamics(q, yd, aux)) < TOL
-    assert rel(res["h"][0][0].reshape(-1, o.nv, o.nv), o.mass_matrix(q)) < TOL
-    p, R, v = o.forward_kinematics(q, yd)
-    fk = res["fk"][0]
-    assert rel(fk[0].reshape(p.shape), p) < TOL and rel(fk[1].reshape(R.shape), R) < TOL
-    assert rel(fk[2].reshape(v.shape), v) < TOL
-    # a chain has no trunk with several limbs: the partition degenerates to one role
-    assert grbda.ClusterTreeModel.from_robot("revolute_chain_with_rotor_4", device=None).dump_role_program(1)["W"] == 1
 
 
 # URDF+ models: product (URDF front end) against the oracle's hand-coded builders — the reference's
@@ -273,6 +248,46 @@ def test_schedule_round_trip(grbda):
     arrs["body_parent"][1] = 5
     with pytest.raises(grbda.GrbdaError):
         grbda.ClusterTreeModel.from_schedule(C.byref(s), device=None)
+
+
+def test_schedule_helper_round_trip(grbda):
+    """ClusterTreeModel.to_schedule() -> from_schedule() for models with every cluster type (free base,
+    explicit, implicit with recorded phi programs): same hash, i.e. the same model bit for bit."""
+    for robot in ("tello_with_arms", "mit_humanoid", "four_bar", "jvrc1_humanoid"):
+        m = grbda.ClusterTreeModel.from_robot(robot, device=None)
+        m2 = grbda.ClusterTreeModel.from_schedule(m.to_schedule(), device=None)
+        assert m2.hash == m.hash, robot
+        assert (m2.nq, m2.nv, m2.nb, m2.nc) == (m.nq, m.nv, m.nb, m.nc)
+
+
+# ---- run-time compiler (runtime/jit.cpp) without a device: model compiler -> CUDA text -> NVRTC -> sm_100a cubin
+def test_run_time_compiler_builds_cubins_for_uncompiled_models(grbda, tmp_path):
+    import subprocess
+    urdf = os.path.join(HERE, "urdf_corpus", "four_bar_branch_2_3.urdf")
+    m = grbda.ClusterTreeModel.from_urdf(urdf, device=None)
+    info = m.kernel_info(grbda.ALGO_FD)
+    assert info["source"] == "jit" and info["program"] == grbda.PROGRAM_FD_LTL and info["parked"] and info["tma"]
+    for algo in (grbda.ALGO_ID, grbda.ALGO_FD, grbda.ALGO_FK, grbda.ALGO_H, grbda.ALGO_PHI, grbda.ALGO_GFA, -1):
+        src, cubin = str(tmp_path / ("a%d.cu" % algo)), str(tmp_path / ("a%d.cubin" % algo))
+        m.jit_compile(algo, False, src, cubin)
+        blob = open(cubin, "rb").read()
+        assert blob[:4] == b"\x7fELF" and len(blob) > 10000
+        text = open(src).read()
+        assert "// kernel: grbda_kernels::" in text
+    # the bulk-copy shell really is in the run-time compiled inverse dynamics kernel
+    sass = subprocess.run(["cuobjdump", "-sass", str(tmp_path / "a0.cubin")], capture_output=True, text=True)
+    if sass.returncode == 0:
+        assert "UBLKCP" in sass.stdout and "sm_100a" in sass.stdout
+    # a model that differs from an ahead-of-time model by one ulp: other hash, still compilable
+    host = grbda.ClusterTreeModel.from_robot("mini_cheetah", device=None)
+    s = host.to_schedule()
+    s.body_xtree_r = s.body_xtree_r.copy()
+    k = int(np.flatnonzero(s.body_xtree_r)[0])
+    s.body_xtree_r[k] = np.nextafter(s.body_xtree_r[k], np.inf)
+    m2 = grbda.ClusterTreeModel.from_schedule(s, device=None)
+    assert m2.hash != host.hash and m2.kernel_info(0)["source"] == "jit" and host.kernel_info(0)["source"] == "aot"
+    m2.jit_compile(grbda.ALGO_ID, True, None, str(tmp_path / "mc.cubin"))
+    assert os.path.getsize(str(tmp_path / "mc.cubin")) > 10000
 
 
 # ---- the emitted CUDA text itself, compiled for the host ---------------------------------------------

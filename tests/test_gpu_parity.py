@@ -252,10 +252,11 @@ def test_full_size_round_trip_and_sharding(grbda, torch):
     assert abs(sa[1] + sb[1] - s[1]) <= 1e-9 * s[1]
 
 
-def test_host_buffer_path(grbda, oracle, torch):
+def test_host_buffer_path(grbda, oracle, torch, monkeypatch):
     m = grbda.ClusterTreeModel.from_robot("tello_with_arms")
     o = oracle.OracleModel("tello_with_arms")
-    B = 70000  # more than one pipeline chunk
+    monkeypatch.setenv("GRBDA_HOST_CHUNK", "16384")
+    B = 70000  # five chunks of 16 384 states: stream rotation, buffer reuse, a ragged last chunk
     q, yd, tau, _ = m.generateStates(B, seed=8)
     qh, ydh, tauh = (x.cpu().pin_memory() for x in (q, yd, tau))
     out = torch.empty((B, m.nv), dtype=torch.float64).pin_memory()
@@ -270,6 +271,23 @@ def test_host_buffer_path(grbda, oracle, torch):
     a, b = torch.empty_like(out), torch.empty_like(out)
     m.forward_inverse_host(qh, ydh, tauh, a, b)
     assert torch.equal(a, ydd_h) and torch.equal(b, out)
+    # pageable (numpy) buffers are staged through the handle's pinned buffers: same bits, both outputs
+    monkeypatch.delenv("GRBDA_HOST_CHUNK")
+    B2 = 3 * (1 << 15) + 1234  # more than three staged chunks: every stream's buffer is reused
+    q2, yd2, tau2, _ = m.generateStates(B2, seed=11)
+    qn, ydn, taun = (x.cpu().numpy().copy() for x in (q2, yd2, tau2))
+    an, bn = np.empty_like(taun), np.empty_like(taun)
+    m.forward_inverse_host(qn, ydn, taun, an, bn)
+    ydd_dev = m.forwardDynamics(q2, yd2, tau2)
+    assert np.array_equal(an, ydd_dev.cpu().numpy())
+    assert np.array_equal(bn, m.inverseDynamics(q2, yd2, ydd_dev).cpu().numpy())
+    # malformed host arrays are refused before any copy is issued
+    with pytest.raises(ValueError):
+        m.forward_inverse_host(qn.astype(np.float32), ydn, taun, an, bn)
+    with pytest.raises(ValueError):
+        m.forward_inverse_host(qn[:, ::-1], ydn, taun, an, bn)
+    with pytest.raises(ValueError):
+        m.forward_inverse_host(qn, ydn[:-1], taun, an, bn)
 
 
 def test_cuda_graph_capture(grbda, oracle, torch):
