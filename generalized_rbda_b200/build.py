@@ -58,6 +58,10 @@ MODELS = {
                                      DEFAULT_VARIANTS.replace("fd=T,128,2,ltl,park;", "fd=T,128,2,ltl,park,f32aba;"), True),
     "revolute_pair_chain_with_rotor_2": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
     "revolute_pair_chain_with_rotor_4": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    # the remaining cluster-joint classes of the reference: RevolutePair (RevolutePairChain.cpp) and
+    # RevoluteTripleWithRotor (RevoluteTripleChainWithRotor.cpp, seeded parameters)
+    "revolute_pair_chain_4": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    "revolute_triple_chain_with_rotor_6": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
 }
 
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
@@ -162,12 +166,14 @@ def build(verbose=True, jobs=None, models=None):
                               [NVCC] + NVCCFLAGS + ["-x", "cu"], hdr_digest, log)
     jit_obj = _compile_cached(os.path.join(CSRC, "runtime/jit.cpp"), BUILD,
                               [NVCC] + NVCCFLAGS + ["-x", "cu", "-I", BUILD], hdr_digest, log)
+    batched_obj = _compile_cached(os.path.join(CSRC, "host/batched.cpp"), BUILD,
+                                  [NVCC] + NVCCFLAGS + ["-x", "cu"], hdr_digest, log)
 
     # 4. link
     _run([NVCC, "-shared", "-o", LIB, "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", CXX]
-         + cuda_objs + [reg_obj, jit_obj] + host_objs + ["-lcudart", "-ldl"])
+         + cuda_objs + [reg_obj, jit_obj, batched_obj] + host_objs + ["-lcudart", "-ldl"])
     # drop stale cached objects so that _build does not grow without bound
-    keep = set(cuda_objs + [reg_obj, jit_obj, modelc_obj, modelc] + host_objs)
+    keep = set(cuda_objs + [reg_obj, jit_obj, batched_obj, modelc_obj, modelc] + host_objs)
     for f in os.listdir(BUILD):
         p = os.path.join(BUILD, f)
         if p not in keep and f.endswith(".o"):

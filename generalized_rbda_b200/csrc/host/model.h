@@ -11,6 +11,8 @@
 #include "../compiler/sym.h"
 #include "types.h"
 
+struct grbda_model; // C-ABI handle (include/grbda_cuda.h)
+
 namespace grbda
 {
     // reference: include/grbda/Dynamics/Body.h:12-43
@@ -285,6 +287,42 @@ namespace grbda
             }
         };
 
+        // reference: RevoluteTripleWithRotorJoint.cpp:10-60. Bodies must be registered in the order the
+        // reference hard-codes: link 1, 2, 3 (a serial chain), then rotor 1, 2, 3 (on the parent cluster's body).
+        // G = [1; diag(gear ratios) * belt matrix] (6 x 3), K = [-G_rotors, 1] (3 x 6).
+        struct RevoluteTripleWithRotor
+        {
+            ClusterDesc desc;
+            RevoluteTripleWithRotor(const ParallelBeltTransmissionModule &m1, const ParallelBeltTransmissionModule &m2,
+                                    const ParallelBeltTransmissionModule &m3)
+            {
+                const ParallelBeltTransmissionModule *m[3] = {&m1, &m2, &m3};
+                for (int i = 0; i < 3; i++)
+                    if (m[i]->body_.sub_index_within_cluster_ != i || m[i]->rotor_.sub_index_within_cluster_ != 3 + i ||
+                        (int)m[i]->belt_ratios_.size() != i + 1)
+                        throw std::runtime_error("RevoluteTripleWithRotor: bodies must be registered as link 1, 2, 3, "
+                                                 "rotor 1, 2, 3 and module i needs i belt ratios");
+                desc.joint_type_name = "RevoluteTripleWithRotor";
+                desc.num_bodies = 6;
+                desc.num_positions = desc.num_velocities = 3;
+                desc.num_constraints = 3;
+                desc.axes = {m1.joint_axis_, m2.joint_axis_, m3.joint_axis_, m1.rotor_axis_, m2.rotor_axis_, m3.rotor_axis_};
+                desc.G.assign(18, 0.0);
+                desc.K.assign(18, 0.0);
+                for (int i = 0; i < 3; i++)
+                {
+                    desc.G[3 * i + i] = 1.0;
+                    const auto belt = beltMatrixRowFromBeltRatios(m[i]->belt_ratios_);
+                    for (int j = 0; j <= i; j++)
+                    {
+                        desc.G[3 * (3 + i) + j] = m[i]->gear_ratio_ * belt[j];
+                        desc.K[6 * i + j] = -desc.G[3 * (3 + i) + j];
+                    }
+                    desc.K[6 * i + 3 + i] = 1.0;
+                }
+            }
+        };
+
         // reference: GenericJoint.cpp:243-288. `joint_axes` replaces the vector of
         // Joints::Revolute pointers (only revolute single joints occur inside multi-body clusters,
         // ClusterTreeParsing.cpp:232-258).
@@ -451,10 +489,43 @@ namespace grbda
             velocity_index_ += joint.num_velocities;
             motion_subspace_index_ += node.motion_subspace_dimension_;
             bodies_in_current_cluster_.clear();
+            device_model_.reset();
         }
 
+        // ---- batched extension of the model interface (host/batched.cpp) -------------------------------
+        // Counterparts of setState + inverseDynamics / forwardDynamics / getMassMatrix / forwardKinematics
+        // + getters (reference: include/grbda/Dynamics/ClusterTreeModel.h:91-97,143-165, TreeModel.h:62)
+        // over `batch` states at once. Arrays are DEVICE pointers on the CUDA device that is current when
+        // the first batched call is made, one state per column, contiguous per state: exactly the vectors
+        // setState() takes, concatenated (spanning positions for implicit clusters). Calls are
+        // asynchronous on `stream` (a cudaStream_t). Errors throw std::runtime_error like the reference.
+        // The device-side model (kernels compiled ahead of time, or by NVRTC on first use) is created
+        // lazily from the current topology and dropped when the model is modified.
+        void inverseDynamicsBatch(const double *q, const double *yd, const double *ydd, double *tau, int64_t batch,
+                                  void *stream = nullptr) const;
+        void forwardDynamicsBatch(const double *q, const double *yd, const double *tau, double *ydd, int64_t batch,
+                                  void *stream = nullptr) const;
+        void massMatrixBatch(const double *q, double *H, int64_t batch, void *stream = nullptr) const;
+        // p[3 Nb], R[9 Nb] (row-major body-to-world), v[6 Nb] ([world angular; world linear]) per state
+        void forwardKinematicsBatch(const double *q, const double *yd, double *p, double *R, double *v, int64_t batch,
+                                    void *stream = nullptr) const;
+        // C(q, yd) = inverseDynamics with ydd = 0 (getBiasForceVector, ClusterTreeModel.h:165); `zeros` is a
+        // device array of batch * nv zeros provided by the caller
+        void biasForceBatch(const double *q, const double *yd, const double *zeros, double *C, int64_t batch,
+                            void *stream = nullptr) const;
+        // random valid states for global indices [first_index, first_index + count) (ClusterJoint.cpp:74-81,
+        // FreeJoint.cpp:49-60, GenericJoint.cpp:290-385); aux = nv uniform values (a random ydd or tau)
+        void randomStatesBatch(uint64_t seed, int64_t first_index, int64_t count, double *q, double *yd, double *aux,
+                               void *stream = nullptr) const;
+        // the C-ABI handle behind the batched methods (include/grbda_cuda.h), e.g. for the *_ext entry points
+        ::grbda_model *deviceModel() const;
+
         // reference: TreeModel.h:56
-        void setGravity(const Vec3 &g) { gravity_ = g; }
+        void setGravity(const Vec3 &g)
+        {
+            gravity_ = g;
+            device_model_.reset();
+        }
         const Vec3 &getGravity() const { return gravity_; }
 
         // reference: TreeModel.h:25-28, ClusterTreeModel.h:97
@@ -494,6 +565,7 @@ namespace grbda
         std::map<int, int> body_index_to_cluster_index_;
         int position_index_ = 0, velocity_index_ = 0, motion_subspace_index_ = 0;
         Vec3 gravity_ = {0., 0., -9.81};
+        mutable std::shared_ptr<void> device_model_; // grbda_model handle + deleter; copies of the model share it
     };
 
 } // namespace grbda

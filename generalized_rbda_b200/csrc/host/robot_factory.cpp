@@ -15,6 +15,11 @@ namespace grbda
             return RevoluteChainWithRotor(std::stoi(name.substr(a.size()))).buildClusterTreeModel();
         if (name.compare(0, b.size(), b) == 0)
             return RevolutePairChainWithRotor(std::stoi(name.substr(b.size()))).buildClusterTreeModel();
+        const std::string c = "revolute_pair_chain_", d = "revolute_triple_chain_with_rotor_";
+        if (name.compare(0, c.size(), c) == 0)
+            return RevolutePairChain(std::stoi(name.substr(c.size()))).buildClusterTreeModel();
+        if (name.compare(0, d.size(), d) == 0)
+            return RevoluteTripleChainWithRotor(std::stoi(name.substr(d.size()))).buildClusterTreeModel();
         // URDF+ model: <urdf_dir>/<name>.urdf (mini_cheetah, mit_humanoid, four_bar, ...)
         const std::string path = urdf_dir + "/" + name + ".urdf";
         std::ifstream f(path);

@@ -268,4 +268,102 @@ namespace grbda
         return model;
     }
 
+    ClusterTreeModel RevolutePairChain::buildClusterTreeModel() const
+    {
+        ClusterTreeModel model;
+        model.setGravity({9.81, 0., 0.});
+        const spatial::Transform X2(I3, {1., 0., 0.});
+        std::string parent = "ground";
+        for (int i = 0; i < N_ / 2; i++)
+        {
+            const spatial::Transform X1 = i == 0 ? spatial::Transform(I3, {0., 0., 0.}) : X2;
+            const std::string k = std::to_string(i);
+            Body linkA = model.registerBody("link-A-" + k, chainLinkInertia(), parent, X1);
+            Body linkB = model.registerBody("link-B-" + k, chainLinkInertia(), "link-A-" + k, X2);
+            model.appendRegisteredBodiesAsCluster<RevolutePair>("cluster-" + k, linkA, linkB, CoordinateAxis::Z,
+                                                                CoordinateAxis::Z);
+            parent = "link-B-" + k;
+        }
+        return model;
+    }
+
+    namespace
+    {
+        // splitmix64: seeded stand-in for the reference's rand() / Eigen Random() parameter draws
+        struct ParamRng
+        {
+            uint64_t s;
+            uint64_t next()
+            {
+                uint64_t z = (s += 0x9e3779b97f4a7c15ull);
+                z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+                z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+                return z ^ (z >> 31);
+            }
+            double unit() { return (double)(next() >> 11) / 9007199254740992.0; } // [0, 1)
+            double sym() { return 2.0 * unit() - 1.0; }                           // [-1, 1)
+            int upTo(int n) { return (int)(next() % (uint64_t)n); }
+            CoordinateAxis axis() { return (CoordinateAxis)upTo(3); }
+            // spatial::randomSpatialRotation (include/grbda/Utils/Spatial.h:43-48): r and rpy uniform in [-1, 1]
+            spatial::Transform transform()
+            {
+                const Mat3 E = ori::rpyToRotMat({sym(), sym(), sym()});
+                return spatial::Transform(E, {sym(), sym(), sym()});
+            }
+            // SpatialInertia::createRandomInertia (SpatialInertia.h:144-151)
+            SpatialInertia inertia(double scaling)
+            {
+                const double mass = scaling * unit();
+                const Vec3 com = {scaling * sym(), scaling * sym(), scaling * sym()};
+                Mat3 A;
+                for (double &x : A)
+                    x = sym();
+                return SpatialInertia(mass, com, ori::scale(ori::mul(A, ori::transpose(A)), scaling));
+            }
+        };
+    } // namespace
+
+    ClusterTreeModel RevoluteTripleChainWithRotor::buildClusterTreeModel() const
+    {
+        ClusterTreeModel model;
+        ParamRng rng{seed_};
+        std::string parent = "ground";
+        for (int i = 0; i < N_ / 3; i++)
+        {
+            const std::string k = std::to_string(i);
+            const char *tag[3] = {"A", "B", "C"};
+            Body link[3], rotor[3];
+            CoordinateAxis link_axis[3], rotor_axis[3];
+            std::string prev = parent;
+            for (int j = 0; j < 3; j++)
+            {
+                const std::string name = std::string("link-") + tag[j] + "-" + k;
+                const spatial::Transform X = rng.transform();
+                const SpatialInertia I = rng.inertia(1.0);
+                link_axis[j] = rng.axis();
+                link[j] = model.registerBody(name, I, prev, X);
+                prev = name;
+            }
+            for (int j = 0; j < 3; j++)
+            {
+                const spatial::Transform X = rng.transform();
+                const SpatialInertia I = rng.inertia(1e-4);
+                rotor_axis[j] = rng.axis();
+                rotor[j] = model.registerBody(std::string("rotor-") + tag[j] + "-" + k, I, parent, X);
+            }
+            ParallelBeltTransmissionModule m[3];
+            for (int j = 0; j < 3; j++)
+            {
+                std::vector<double> belts;
+                const double gear = (double)(rng.upTo(5) + 1);
+                for (int b = 0; b <= j; b++)
+                    belts.push_back((double)(rng.upTo(5) + 1));
+                m[j] = ParallelBeltTransmissionModule{link[j], rotor[j], link_axis[j], rotor_axis[j], gear, belts};
+            }
+            model.appendRegisteredBodiesAsCluster<RevoluteTripleWithRotor>("cluster-" + k, m[0], m[1], m[2]);
+            parent = prev;
+        }
+        return model;
+    }
+
 } // namespace grbda

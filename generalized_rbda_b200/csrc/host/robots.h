@@ -48,6 +48,32 @@ namespace grbda
         int N_;
     };
 
+    // reference: src/Robots/SerialChains/RevolutePairChain.cpp:49-109 (uniform model; RevolutePair clusters, no rotors)
+    class RevolutePairChain : public Robot
+    {
+    public:
+        explicit RevolutePairChain(int N) : N_(N) {}
+        ClusterTreeModel buildClusterTreeModel() const override;
+
+    private:
+        int N_;
+    };
+
+    // reference: src/Robots/SerialChains/RevoluteTripleChainWithRotor.cpp:8-83. The reference only builds this
+    // chain with rand() parameters (buildUniformClusterTreeModel throws); here the same recipe is driven by a
+    // seeded generator (random coordinate rotations and axes, random link / rotor inertias, gear and belt
+    // ratios in 1..5), so that the model is reproducible.
+    class RevoluteTripleChainWithRotor : public Robot
+    {
+    public:
+        explicit RevoluteTripleChainWithRotor(int N, uint64_t seed = 1) : N_(N), seed_(seed) {}
+        ClusterTreeModel buildClusterTreeModel() const override;
+
+    private:
+        int N_;
+        uint64_t seed_;
+    };
+
     // URDF+ based robots (host/urdf.cpp); `urdf_dir` is the directory holding the URDF files
     ClusterTreeModel buildRobotByName(const std::string &name, const std::string &urdf_dir);
 

@@ -212,6 +212,13 @@ class OracleBuilder:
                                                 op.ctypes.data_as(ip), a.ctypes.data_as(ip), b.ctypes.data_as(ip),
                                                 _P(val), len(op), out.ctypes.data_as(ip), len(out))
 
+    def append_revolute_triple_with_rotor(self, name, axes, gears, belts):
+        """bodies registered as link1, link2, link3, rotor1, rotor2, rotor3; belts = 1 + 2 + 3 ratios"""
+        g = np.ascontiguousarray(gears, dtype=np.float64)
+        b = np.ascontiguousarray(belts, dtype=np.float64)
+        assert g.size == 3 and b.size == 6 and len(axes) == 6
+        lib().oracle_builder_append_revolute_triple_with_rotor(self._h, name.encode(), (C.c_int * 6)(*axes), _P(g), _P(b))
+
     def finish(self, generic=False):
         _check(lib().oracle_builder_finish(self._h, int(generic)))
         h, self._h = self._h, None

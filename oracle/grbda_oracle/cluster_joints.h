@@ -519,6 +519,113 @@ namespace grbda_oracle
         }
     };
 
+    // reference: src/Dynamics/ClusterJoints/RevoluteTripleWithRotorJoint.cpp:10-120
+    // (sub-indices are fixed by the reference: links 0, 1, 2, rotors 3, 4, 5)
+    template <typename T>
+    struct RevoluteTripleWithRotorCluster : ClusterJointBase<T>
+    {
+        Body<T> link1, link2, link3, rotor1, rotor2, rotor3;
+        std::shared_ptr<SingleJoint<T>> link1_joint, link2_joint, link3_joint, rotor1_joint, rotor2_joint, rotor3_joint;
+        Mat<T> X_intra_S_span, X_intra_S_span_ring;
+        Transform<T> X21, X32, X31;
+
+        RevoluteTripleWithRotorCluster(const ParallelBeltTransmissionModule<T> &m1,
+                                       const ParallelBeltTransmissionModule<T> &m2,
+                                       const ParallelBeltTransmissionModule<T> &m3)
+            : ClusterJointBase<T>(6, 3, 3), link1(m1.body), link2(m2.body), link3(m3.body), rotor1(m1.rotor),
+              rotor2(m2.rotor), rotor3(m3.rotor), X_intra_S_span(36, 6), X_intra_S_span_ring(36, 6)
+        {
+            // :20-26
+            link1_joint = std::make_shared<SingleRevolute<T>>(m1.joint_axis);
+            link2_joint = std::make_shared<SingleRevolute<T>>(m2.joint_axis);
+            link3_joint = std::make_shared<SingleRevolute<T>>(m3.joint_axis);
+            rotor1_joint = std::make_shared<SingleRevolute<T>>(m1.rotor_axis);
+            rotor2_joint = std::make_shared<SingleRevolute<T>>(m2.rotor_axis);
+            rotor3_joint = std::make_shared<SingleRevolute<T>>(m3.rotor_axis);
+            this->single_joints = {link1_joint, link2_joint, link3_joint, rotor1_joint, rotor2_joint, rotor3_joint};
+
+            // :31-47  G = [1; diag(gear ratios) * belt matrix], K = [-G_bottom, 1]
+            const std::vector<T> b1 = beltMatrixRowFromBeltRatios(m1.belt_ratios);
+            const std::vector<T> b2 = beltMatrixRowFromBeltRatios(m2.belt_ratios);
+            const std::vector<T> b3 = beltMatrixRowFromBeltRatios(m3.belt_ratios);
+            const T gear[3] = {m1.gear_ratio, m2.gear_ratio, m3.gear_ratio};
+            Mat<T> G(6, 3), K(3, 6);
+            for (int i = 0; i < 3; i++)
+                G(i, i) = T(1.0);
+            G(3, 0) = gear[0] * b1[0];
+            G(4, 0) = gear[1] * b2[0];
+            G(4, 1) = gear[1] * b2[1];
+            G(5, 0) = gear[2] * b3[0];
+            G(5, 1) = gear[2] * b3[1];
+            G(5, 2) = gear[2] * b3[2];
+            for (int i = 0; i < 3; i++)
+            {
+                for (int j = 0; j < 3; j++)
+                    K(i, j) = -G(3 + i, j);
+                K(i, 3 + i) = T(1.0);
+            }
+            this->loop_constraint = std::make_shared<StaticConstraint<T>>(G, K);
+
+            // :49-59
+            X_intra_S_span.setBlock(0, 0, link1_joint->S);
+            X_intra_S_span.setBlock(6, 1, link2_joint->S);
+            X_intra_S_span.setBlock(12, 2, link3_joint->S);
+            X_intra_S_span.setBlock(18, 3, rotor1_joint->S);
+            X_intra_S_span.setBlock(24, 4, rotor2_joint->S);
+            X_intra_S_span.setBlock(30, 5, rotor3_joint->S);
+            this->S = X_intra_S_span * this->G();
+        }
+        const char *typeName() const override { return "RevoluteTripleWithRotor"; }
+        // :62-106
+        void updateKinematics(const JointState<T> &js) override
+        {
+            JointState<T> s = this->toSpanningTreeState(js);
+            const Mat<T> &q = s.position, &qd = s.velocity;
+            link1_joint->updateKinematics(q.segment(0, 1));
+            link2_joint->updateKinematics(q.segment(1, 1));
+            link3_joint->updateKinematics(q.segment(2, 1));
+            rotor1_joint->updateKinematics(q.segment(3, 1));
+            rotor2_joint->updateKinematics(q.segment(4, 1));
+            rotor3_joint->updateKinematics(q.segment(5, 1));
+
+            X21 = link2_joint->XJ * link2.Xtree;
+            X32 = link3_joint->XJ * link3.Xtree;
+            X31 = X32 * X21;
+
+            Mat<T> v2_relative1 = link2_joint->S * qd[1];
+            Mat<T> X21_S1 = X21.transformMotionVector(link1_joint->S);
+            Mat<T> v3_relative1 = X32.transformMotionVector(v2_relative1) + link3_joint->S * qd[2];
+            Mat<T> X31_S1 = X31.transformMotionVector(link1_joint->S);
+            Mat<T> v3_relative2 = link3_joint->S * qd[2];
+            Mat<T> X32_S2 = X32.transformMotionVector(link2_joint->S);
+
+            X_intra_S_span.setBlock(6, 0, X21_S1);
+            X_intra_S_span.setBlock(12, 0, X31_S1);
+            X_intra_S_span.setBlock(12, 1, X32_S2);
+            // S top-left 18 x 3 = X_intra_S_span top-left 18 x 3 (:88-89)
+            for (int i = 0; i < 18; i++)
+                for (int j = 0; j < 3; j++)
+                    this->S(i, j) = X_intra_S_span(i, j);
+
+            X_intra_S_span_ring.setBlock(6, 0, -(motionCrossMatrix(v2_relative1) * X21_S1));
+            X_intra_S_span_ring.setBlock(12, 0, -(motionCrossMatrix(v3_relative1) * X31_S1));
+            X_intra_S_span_ring.setBlock(12, 1, -(motionCrossMatrix(v3_relative2) * X32_S2));
+
+            this->vJ = X_intra_S_span * qd;
+            this->cJ = X_intra_S_span_ring * qd;
+        }
+        // :108-120
+        void computeXup(GeneralizedTransform<T> &Xup) const override
+        {
+            Xup.X[0] = link1_joint->XJ * link1.Xtree;
+            Xup.X[1] = X21 * Xup.X[0];
+            Xup.X[2] = X31 * Xup.X[0];
+            Xup.X[3] = rotor1_joint->XJ * rotor1.Xtree;
+            Xup.X[4] = rotor2_joint->XJ * rotor2.Xtree;
+            Xup.X[5] = rotor3_joint->XJ * rotor3.Xtree;
+        }
+    };
+
     // reference: GenericJoint.cpp:243-505 (ClusterJoints::Generic)
     template <typename T>
     struct GenericCluster : ClusterJointBase<T>

@@ -41,8 +41,8 @@ namespace
         int num_constraints = 0;
         std::vector<LoopCapture> loops;
         std::vector<int> loop_rows; // rows (0..2) of each loop that are kept, flattened (loop, axis)
-        double gear[2] = {0, 0};
-        std::vector<double> belt1, belt2;
+        double gear[3] = {0, 0, 0};
+        std::vector<double> belt1, belt2, belt3;
         // kind 8: phi given as a straight-line op list (op, a, b, val), see include/grbda_cuda.h
         std::vector<int> phi_op, phi_a, phi_b, phi_out;
         std::vector<double> phi_val;
@@ -265,6 +265,25 @@ namespace
                     joint = std::make_shared<RevolutePairCluster<T>>(bodies[0], bodies[1],
                                                                      (Axis)c.axes[0], (Axis)c.axes[1]);
                     break;
+                case 9:
+                {
+                    // RevoluteTripleWithRotor: bodies in the reference's fixed order link1..3, rotor1..3
+                    auto conv = [](const std::vector<double> &v)
+                    {
+                        std::vector<T> o;
+                        for (double x : v)
+                            o.push_back(T(x));
+                        return o;
+                    };
+                    ParallelBeltTransmissionModule<T> m1{bodies[0], bodies[3], (Axis)c.axes[0], (Axis)c.axes[3],
+                                                         T(c.gear[0]), conv(c.belt1)};
+                    ParallelBeltTransmissionModule<T> m2{bodies[1], bodies[4], (Axis)c.axes[1], (Axis)c.axes[4],
+                                                         T(c.gear[1]), conv(c.belt2)};
+                    ParallelBeltTransmissionModule<T> m3{bodies[2], bodies[5], (Axis)c.axes[2], (Axis)c.axes[5],
+                                                         T(c.gear[2]), conv(c.belt3)};
+                    joint = std::make_shared<RevoluteTripleWithRotorCluster<T>>(m1, m2, m3);
+                    break;
+                }
                 default:
                     throw std::runtime_error("oracle: unknown cluster kind");
                 }
@@ -508,6 +527,23 @@ extern "C"
         c.gear[1] = gear2;
         c.belt1.assign(belt1, belt1 + nb1);
         c.belt2.assign(belt2, belt2 + nb2);
+        h->spec.clusters.push_back(c);
+        h->spec.pending = ClusterCmd();
+    }
+    // bodies registered in the order link1, link2, link3, rotor1, rotor2, rotor3; belts: 1 + 2 + 3 ratios
+    void oracle_builder_append_revolute_triple_with_rotor(void *hv, const char *name, const int *axes,
+                                                          const double *gears3, const double *belts6)
+    {
+        Handle *h = (Handle *)hv;
+        ClusterCmd &c = h->spec.pending;
+        c.name = name;
+        c.kind = 9;
+        c.axes.assign(axes, axes + 6);
+        for (int i = 0; i < 3; i++)
+            c.gear[i] = gears3[i];
+        c.belt1.assign(belts6, belts6 + 1);
+        c.belt2.assign(belts6 + 1, belts6 + 3);
+        c.belt3.assign(belts6 + 3, belts6 + 6);
         h->spec.clusters.push_back(c);
         h->spec.pending = ClusterCmd();
     }

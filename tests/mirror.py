@@ -19,6 +19,14 @@ def mirror_to_oracle(model, oracle, generic=False):
         name = "cluster-%d" % c
         if cl["type"] in (0, 1):
             b.append_simple(name, cl["type"])
+        elif cl["type"] == 2 and cl["joint_type"] == "RevolutePair" and not generic:
+            b.append_simple(name, 7, axes)
+        elif cl["type"] == 2 and cl["joint_type"] == "RevoluteTripleWithRotor" and not generic:
+            # gear / belt ratios back out of G (6 x 3): row 3 + i = gear_i * cumprod(belts_i); any factorisation
+            # gives the same G, so gear = 1 and belts = successive quotients
+            G = cl["G"]
+            belts = [G[3, 0], G[4, 0], G[4, 1] / G[4, 0], G[5, 0], G[5, 1] / G[5, 0], G[5, 2] / G[5, 1]]
+            b.append_revolute_triple_with_rotor(name, axes, [1.0, 1.0, 1.0], belts)
         elif cl["type"] == 2:
             G = cl["G"]
             K = np.zeros((n - G.shape[1], n))  # K does not enter the dynamics

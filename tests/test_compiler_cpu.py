@@ -21,12 +21,22 @@ ROBOTS = {"tello": "tello", "tello_with_arms": "tello_with_arms",
           "revolute_chain_with_rotor_8": "revolute_chain_with_rotor_8",
           "revolute_chain_with_rotor_16": "revolute_chain_with_rotor_16",
           "revolute_pair_chain_with_rotor_2": "revolute_pair_chain_with_rotor_2",
-          "revolute_pair_chain_with_rotor_4": "revolute_pair_chain_with_rotor_4"}
+          "revolute_pair_chain_with_rotor_4": "revolute_pair_chain_with_rotor_4",
+          # built by the product's robot classes; the oracle is assembled from the product's topology with the
+          # oracle's own restatements of ClusterJoints::RevolutePair / RevoluteTripleWithRotor (tests/mirror.py)
+          "revolute_pair_chain_4": None, "revolute_triple_chain_with_rotor_6": None}
 TOL = 1e-10  # north_star: <= 1e-10 relative in FP64
 
 
 def rel(a, b):
     return np.abs(a - b).max() / max(1e-300, np.abs(b).max())
+
+
+def oracle_of(oracle, m, robot):
+    if ROBOTS[robot] is not None:
+        return oracle.OracleModel(ROBOTS[robot])
+    from mirror import mirror_to_oracle
+    return mirror_to_oracle(m, oracle)
 
 
 def test_c_abi_exports_every_declared_symbol(grbda):
@@ -51,7 +61,7 @@ def test_no_cpu_fallback_without_device(grbda):
 @pytest.mark.parametrize("robot", sorted(ROBOTS))
 def test_topology_matches_oracle(grbda, oracle, robot):
     m = grbda.ClusterTreeModel.from_robot(robot, device=None)
-    o = oracle.OracleModel(ROBOTS[robot])
+    o = oracle_of(oracle, m, robot)
     assert (m.nq, m.nv, m.nb, m.nc) == (o.nq, o.nv, o.nb, o.nc)
     for a, b in zip(m.clusters(), o.clusters()):
         for k in ("parent", "num_bodies", "num_positions", "num_velocities", "position_index", "velocity_index"):
@@ -67,7 +77,7 @@ def test_topology_matches_oracle(grbda, oracle, robot):
 def test_emitted_programs_match_oracle(grbda, oracle, robot, tmp_path):
     """The straight-line programs the kernels execute, replayed in numpy, against the oracle."""
     m = grbda.ClusterTreeModel.from_robot(robot, device=None)
-    o = oracle.OracleModel(ROBOTS[robot])
+    o = oracle_of(oracle, m, robot)
     q, yd, aux = o.generate_states(48, seed=7)
     tapes = {}
     for algo, name in enumerate(grbda.ALGO_NAMES):
@@ -94,6 +104,29 @@ def test_emitted_programs_match_oracle(grbda, oracle, robot, tmp_path):
     phi = run_tape(tapes["phi"], ins)[0]
     if phi.shape[1]:
         assert np.abs(phi).max() < 1e-8  # generated states satisfy the loop constraints
+
+
+@pytest.mark.parametrize("robot", ["revolute_pair_chain_4", "revolute_triple_chain_with_rotor_6",
+                                   "revolute_pair_chain_with_rotor_4"])
+def test_specialised_cluster_joints_equal_their_generic_rebuild(grbda, oracle, robot):
+    """UnitTests/testClusterTreeModel.cpp / testHelpers.hpp:10-45 restated inside the oracle: RevolutePair,
+    RevolutePairWithRotor and RevoluteTripleWithRotor (RevoluteTripleWithRotorJoint.cpp:10-120) give the same
+    dynamics as ClusterJoints::Generic built from the same bodies, joints and loop constraint."""
+    from mirror import mirror_to_oracle
+    m = grbda.ClusterTreeModel.from_robot(robot, device=None)
+    types = {c["joint_type"] for c in m.clusters()}
+    assert types == {{"revolute_pair_chain_4": "RevolutePair", "revolute_triple_chain_with_rotor_6": "RevoluteTripleWithRotor",
+                      "revolute_pair_chain_with_rotor_4": "RevolutePairWithRotor"}[robot]}
+    special = mirror_to_oracle(m, oracle) if ROBOTS.get(robot) is None else oracle.OracleModel(robot)
+    generic = mirror_to_oracle(m, oracle, generic=True)
+    assert [c["joint_type"] for c in generic.clusters()] == ["Generic"] * m.nc
+    assert all(c["joint_type"] != "Generic" for c in special.clusters())
+    q, yd, aux = special.generate_states(32, seed=5)
+    assert rel(special.inverse_dynamics(q, yd, aux), generic.inverse_dynamics(q, yd, aux)) < 1e-12
+    assert rel(special.forward_dynamics(q, yd, aux), generic.forward_dynamics(q, yd, aux)) < 1e-10
+    assert rel(special.mass_matrix(q), generic.mass_matrix(q)) < 1e-12
+    for a, b in zip(special.forward_kinematics(q, yd), generic.forward_kinematics(q, yd)):
+        assert rel(a, b) < 1e-12
 
 
 def test_rotor_reductions(grbda, oracle, tmp_path):

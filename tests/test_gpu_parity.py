@@ -21,7 +21,9 @@ ROBOTS = {"tello": "tello", "tello_with_arms": "tello_with_arms",
           "revolute_chain_with_rotor_8": "revolute_chain_with_rotor_8",
           "revolute_chain_with_rotor_16": "revolute_chain_with_rotor_16",
           "revolute_pair_chain_with_rotor_2": "revolute_pair_chain_with_rotor_2",
-          "revolute_pair_chain_with_rotor_4": "revolute_pair_chain_with_rotor_4"}
+          "revolute_pair_chain_with_rotor_4": "revolute_pair_chain_with_rotor_4",
+          # oracle: restated ClusterJoints::RevolutePair / RevoluteTripleWithRotor on the product's topology
+          "revolute_pair_chain_4": None, "revolute_triple_chain_with_rotor_6": None}
 
 
 def oracle_for(oracle, m, robot):
