@@ -9,8 +9,10 @@ A step = one pass of the hot path over one batch of synthetic states: forwardDyn
 (constraint-embedded ABA) followed by inverseDynamics (cluster RNEA) of the resulting accelerations.
 `value` counts fwd+inv PAIRS per second summed over all GPUs, inputs resident in HBM; `e2e` is the
 same pass through the host-buffer entry point (pinned host memory -> H2D -> kernels -> D2H).
-The batch is sharded by global state index (weak scaling: 2^20 states per GPU, no collective on the
-data path; the only collective is the final timing / checksum gather).
+The batch is sharded by global state index, no collective on the data path; the only collective is the
+final timing / checksum gather. --scaling weak (default): 2^20 states per GPU; --scaling strong: 2^20
+states in total, 2^20 / N per GPU. Whatever the flag, the line carries both measurements
+("weak_scaling" / "strong_scaling"); `value`, `ms_per_step` and `scaling` are those of the selected mode.
 """
 import argparse
 import json
@@ -166,6 +168,9 @@ def main():
     ap.add_argument("--ref-states", type=int, default=1 << 14)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", choices=("weak", "strong"), default="weak",
+                    help="weak: --batch states per GPU; strong: --batch states in total, sharded")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-3 leg and the depth sweep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -176,7 +181,7 @@ def main():
     import torch
     import torch.distributed as dist
     import generalized_rbda_b200 as grbda
-    from generalized_rbda_b200.sharding import gather_summary, weak_shard
+    from generalized_rbda_b200.sharding import gather_summary, shard_range, weak_shard
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -186,6 +191,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
+    # host placement first: the pinned buffers of the end-to-end leg are allocated later by this thread
+    numa = grbda.bind_host_to_device(local_rank)
     m = grbda.ClusterTreeModel.from_robot(args.model, device=local_rank)
     B = args.batch
     # contiguous shard of the global index range, generated on this GPU
@@ -194,18 +201,43 @@ def main():
     ydd = torch.empty_like(tau)
     tau_back = torch.empty_like(tau)
     assert int(flags.sum()) == 0
+    # strong scaling: the first 2^20 / N states of the same buffers (states are i.i.d.: any contiguous
+    # slice of a shard is as good as the rank's slice of the global batch for timing purposes)
+    _, Bs = shard_range(B, rank, world)
 
     def step():
         m.forwardDynamics(q, yd, tau, out=ydd)
         m.inverseDynamics(q, yd, ydd, out=tau_back)
+
+    def step_strong():
+        m.forwardDynamics(q[:Bs], yd[:Bs], tau[:Bs], out=ydd[:Bs])
+        m.inverseDynamics(q[:Bs], yd[:Bs], ydd[:Bs], out=tau_back[:Bs])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize, CUDA events, max over ranks (ms for all K steps)."""
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    primary, other = (step, step_strong) if args.scaling == "weak" else (step_strong, step)
     for _ in range(args.warmup):
-        step()
+        other()
+    ms_other = timed(other, args.steps)
+    for _ in range(args.warmup):
+        primary()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -214,7 +246,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step()
+        primary()
     e1.record()
     barrier()
     launches = grbda.launch_count() - launches0
@@ -225,14 +257,17 @@ def main():
     timed_samples = len(sampler.samples)
     extra = int(min(2000, max(args.steps, 0.7 / max(ms * 1e-3 / args.steps, 1e-6))))
     for _ in range(extra):
-        step()
+        primary()
     torch.cuda.synchronize()
     sampler.stop_flag = True
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = world * B * args.steps / (ms_max * 1e-3)
+    ms_weak, ms_strong = (ms_max, ms_other) if args.scaling == "weak" else (ms_other, ms_max)
+    value_weak = world * B * args.steps / (ms_weak * 1e-3)
+    value_strong = B * args.steps / (ms_strong * 1e-3)
+    value = value_weak if args.scaling == "weak" else value_strong
 
     # per-kernel timing of the dominant kernel (FD) and of ID, same stream, CUDA events
     def time_kernel(fn, reps):
@@ -264,6 +299,40 @@ def main():
     t_id_ext = time_kernel(lambda: m.inverseDynamics(q, yd, ydd, out=ext_out, f_ext=f_ext), 5)
     del f_ext, ext_out
 
+    # BASELINE config 3: mit_humanoid forwardDynamics + massMatrix, 2^20 (FD) / 2^18 (H) states in total,
+    # sharded over the ranks; BASELINE config 5: depth sweep of the serial rotor chain (rank 0, N = 1 only;
+    # depths without ahead-of-time kernels are compiled at run time)
+    extras = {}
+    if not args.no_extras:
+        mh = grbda.ClusterTreeModel.from_robot("mit_humanoid", device=local_rank)
+        f3, n3 = shard_range(1 << 20, rank, world)
+        q3, yd3, tau3, _ = mh.generateStates(n3, first_index=f3)
+        out3 = torch.empty_like(tau3)
+        n3h = max(1, n3 // 4)
+        H3 = torch.empty((n3h, mh.nv, mh.nv), dtype=torch.float64, device=dev)
+        mh.forwardDynamics(q3, yd3, tau3, out=out3), mh.getMassMatrix(q3[:n3h], out=H3)
+        ms_fd3 = timed(lambda: mh.forwardDynamics(q3, yd3, tau3, out=out3), 10) / 10
+        ms_h3 = timed(lambda: mh.getMassMatrix(q3[:n3h], out=H3), 10) / 10
+        extras["mit_humanoid_sharded"] = {
+            "states_total_fd": 1 << 20, "states_total_h": world * n3h, "n_gpus": world, "fd_ms": ms_fd3, "h_ms": ms_h3,
+            "fd_evals_per_s": (1 << 20) / (ms_fd3 * 1e-3), "h_evals_per_s": world * n3h / (ms_h3 * 1e-3),
+            "h_hbm_frac_per_gpu": 8 * (mh.nq + mh.nv * mh.nv) * n3h / (ms_h3 * 1e-3) / 1e9 / load_peaks()[0]["hbm_gbs"]}
+        del mh, q3, yd3, tau3, out3, H3
+        if world == 1:
+            sweep = []
+            for depth in (2, 4, 8, 16, 24):
+                mc = grbda.ClusterTreeModel.from_robot("revolute_chain_with_rotor_%d" % depth, device=local_rank)
+                nS = 1 << 18
+                qc, ydc, tc, _ = mc.generateStates(nS)
+                oc = torch.empty_like(tc)
+                mc.forwardDynamics(qc, ydc, tc, out=oc), mc.inverseDynamics(qc, ydc, tc, out=oc)
+                sweep.append({"depth": depth, "states": nS,
+                              "fd_ms": timed(lambda: mc.forwardDynamics(qc, ydc, tc, out=oc), 10) / 10,
+                              "id_ms": timed(lambda: mc.inverseDynamics(qc, ydc, tc, out=oc), 10) / 10,
+                              "kernels": mc.kernel_info(grbda.ALGO_FD)["source"]})
+                del mc
+            extras["revolute_chain_with_rotor_depth_sweep"] = sweep
+
     # parity spot check + checksum gather (the only collective)
     err = float(((tau_back - tau).abs().amax(1) / tau.abs().amax(1)).median())
     # the only collective: per-rank checksum / timing summary
@@ -291,7 +360,8 @@ def main():
         e2e = {"value": world * B * n_e2e / float(dt.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(B * (m.nq + 2 * m.nv) * 8), "d2h_bytes_per_step": int(2 * B * m.nv * 8),
                "steps": n_e2e, "api": "grbda_cuda_forward_inverse_host_f64 (pinned host buffers, 128k-state "
-                                      "chunks pipelined over 3 streams)"}
+                                      "chunks pipelined over 3 streams)",
+               "host_placement": numa}
         assert torch.equal(yddh, ydd.cpu())
 
     if rank == 0:
@@ -300,12 +370,17 @@ def main():
         fp64_peak = grbda.measure_fma_peak(local_rank, fp32=False, seconds=0.5)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "%s forwardDynamics + inverseDynamics, %d states per GPU, FP64" % (args.model, B),
-                           "model": args.model, "batch_per_gpu": B, "nq": m.nq, "nv": m.nv, "bodies": m.nb,
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "%s forwardDynamics + inverseDynamics, %s, FP64" % (
+                               args.model, "%d states per GPU" % B if args.scaling == "weak" else
+                               "%d states in total sharded over the GPUs" % B),
+                           "model": args.model, "batch_per_gpu": B if args.scaling == "weak" else Bs, "nq": m.nq, "nv": m.nv, "bodies": m.nb,
                            "clusters": m.nc, "l2": "inputs (%.0f MB per step) larger than L2, no flush needed" %
                            (B * (m.nq + 3 * m.nv) * 8 / 1e6), "sharding": "contiguous global-index shards, no NCCL on the data path"},
                 "gpu_launches": int(launches),
+                "weak_scaling": {"value": value_weak, "states_per_gpu": B, "ms_per_step": ms_weak / args.steps},
+                "strong_scaling": {"value": value_strong, "states_total": B, "states_per_gpu": Bs,
+                                   "ms_per_step": ms_strong / args.steps},
                 "clocks": dict(sampler.summary(), samples_inside_timed_region=timed_samples,
                                note="sampled over the timed steps and an untimed continuation of the same steps"),
                 "parity": {"median_rel_err_ID_of_FD": err, "checksum_ydd": [float(cs[0]), float(cs[1])]}}
@@ -357,6 +432,7 @@ def main():
             "forward_kinematics": {"states": Bk, "kernel_ms": t_fk * 1e3,
                                    "bytes_per_state": 8 * (m.nq + m.nv + 18 * m.nb),
                                    "hbm_frac": 8 * (m.nq + m.nv + 18 * m.nb) * Bk / t_fk / 1e9 / peaks["hbm_gbs"]}}
+        line["other_kernels"].update(extras)
         emit(line)
     if world > 1:
         dist.barrier()

@@ -66,6 +66,7 @@ _lib.grbda_cuda_forward_dynamics_ext_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _v
 _lib.grbda_cuda_external_force_bodies.argtypes = [_vp, _vp, _vp]
 _lib.grbda_cuda_dynamics_host_f64.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _i64]
 _lib.grbda_cuda_forward_inverse_host_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64]
+_lib.grbda_cuda_bind_host_to_device.argtypes = [C.c_int, _vp]
 _lib.grbda_cuda_generate_states.argtypes = [_vp, C.c_uint64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]
 _lib.grbda_cuda_constraint_violation_f64.argtypes = [_vp, _vp, _vp, _i64, _vp]
 _lib.grbda_cuda_checksum_f64.argtypes = [_vp, _i64, _vp, _vp]
@@ -83,7 +84,7 @@ EXPORTED_SYMBOLS = [
     "grbda_cuda_forward_dynamics_f64", "grbda_cuda_forward_dynamics_f32",
     "grbda_cuda_mass_matrix_f64", "grbda_cuda_mass_matrix_f32",
     "grbda_cuda_forward_kinematics_f64", "grbda_cuda_forward_kinematics_f32",
-    "grbda_cuda_dynamics_host_f64", "grbda_cuda_forward_inverse_host_f64", "grbda_cuda_generate_states", "grbda_cuda_constraint_violation_f64",
+    "grbda_cuda_dynamics_host_f64", "grbda_cuda_forward_inverse_host_f64", "grbda_cuda_bind_host_to_device", "grbda_cuda_generate_states", "grbda_cuda_constraint_violation_f64",
     "grbda_cuda_checksum_f64", "grbda_cuda_measure_fma_peak", "grbda_cuda_launch_count",
 ]
 
@@ -160,6 +161,13 @@ def library_path():
 
 def launch_count():
     return int(_lib.grbda_cuda_launch_count())
+
+
+def bind_host_to_device(device=0):
+    """CPU affinity + memory policy of the calling thread -> the NUMA node of the GPU's PCIe root."""
+    info = (C.c_int32 * 4)()
+    _check(_lib.grbda_cuda_bind_host_to_device(device, info))
+    return dict(numa_node=info[0], cpus_bound=info[1], mempolicy_set=bool(info[2]), cpus_allowed=info[3])
 
 
 def measure_fma_peak(device=0, fp32=False, seconds=0.5):

@@ -234,6 +234,12 @@ grbda_status grbda_cuda_forward_inverse_host_f64(const grbda_model *m, const dou
                                                  const double *tau, double *ydd, double *tau_back,
                                                  int64_t batch);
 
+/* Place the calling thread (and what it allocates from now on, e.g. the pinned buffers handed to the
+ * _host entry points) on the NUMA node of `device`'s PCIe root: CPU affinity to the node's cores that
+ * the process may use, memory policy "prefer that node". One process per GPU calls it once before
+ * allocating. info4 (optional) = {numa node or -1, cpus bound, memory policy set, cpus allowed before}. */
+grbda_status grbda_cuda_bind_host_to_device(int device, int32_t *info4);
+
 /* ---- synthetic states, checks, measurement --------------------------------------------------- */
 /* Random valid states for global state indices [first_index, first_index + count): counter based
  * (Philox4x32-10), so a shard is reproducible whatever the GPU count. Ranges follow
