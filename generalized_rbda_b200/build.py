@@ -16,10 +16,15 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-GEN = os.path.join(CSRC, "generated")
-BUILD = os.path.join(HERE, "_build")
 URDF_DIR = os.path.join(HERE, "robot-models")
-LIB = os.path.join(HERE, "libgrbda_cuda.so")
+# kernel experiments: GRBDA_BUILD_TAG=<tag> builds explibs/<tag>/libgrbda_cuda.so (own object / generated dirs) next
+# to the product library, GRBDA_BUILD_MODELS=a,b restricts it to some models; tools/ab.py times such builds
+# against each other in one GPU session (load with GRBDA_LIB_PATH)
+_TAG = os.environ.get("GRBDA_BUILD_TAG")
+_OUT = os.path.join(HERE, "..", "explibs", _TAG) if _TAG else HERE
+GEN = os.path.join(_OUT, "generated") if _TAG else os.path.join(CSRC, "generated")
+BUILD = os.path.join(_OUT, "_build")
+LIB = os.path.join(_OUT, "libgrbda_cuda.so")
 
 # model name -> (algorithms, launch variants, build f32 variants). A variant is KIND,BLOCK,MIN_BLOCKS with
 # KIND = T (TMA bulk-copy staged tiles), S (software-staged tiles), D (direct global access),
@@ -116,6 +121,8 @@ def build(verbose=True, jobs=None, models=None):
     os.makedirs(GEN, exist_ok=True)
     os.makedirs(BUILD, exist_ok=True)
     models = models or MODELS
+    if os.environ.get("GRBDA_BUILD_MODELS"):
+        models = {k: v for k, v in MODELS.items() if k in os.environ["GRBDA_BUILD_MODELS"].split(",")}
     jobs = jobs or max(1, (os.cpu_count() or 2))
     hdr_digest = _digest(_headers())
 
