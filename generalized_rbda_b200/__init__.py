@@ -64,6 +64,9 @@ for _p in ("f64", "f32"):
 _lib.grbda_cuda_inverse_dynamics_ext_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
 _lib.grbda_cuda_forward_dynamics_ext_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
 _lib.grbda_cuda_external_force_bodies.argtypes = [_vp, _vp, _vp]
+_lib.grbda_cuda_set_external_force_bodies.argtypes = [_vp, _vp, C.c_int32]
+_lib.grbda_cuda_integrate_f64.argtypes = [_vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _i64, _vp]
+_lib.grbda_cuda_step_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _i64, _vp]
 _lib.grbda_cuda_dynamics_host_f64.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _i64]
 _lib.grbda_cuda_forward_inverse_host_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64]
 _lib.grbda_cuda_bind_host_to_device.argtypes = [C.c_int, _vp]
@@ -80,6 +83,7 @@ EXPORTED_SYMBOLS = [
     "grbda_cuda_cluster_G", "grbda_cuda_model_gravity", "grbda_cuda_cluster_phi", "grbda_cuda_dump_program", "grbda_cuda_kernel_counts", "grbda_cuda_emit_source",
     "grbda_cuda_model_prepare", "grbda_cuda_kernel_info", "grbda_cuda_jit_compile",
     "grbda_cuda_external_force_bodies", "grbda_cuda_inverse_dynamics_ext_f64", "grbda_cuda_forward_dynamics_ext_f64",
+    "grbda_cuda_integrate_f64", "grbda_cuda_step_f64", "grbda_cuda_set_external_force_bodies",
     "grbda_cuda_inverse_dynamics_f64", "grbda_cuda_inverse_dynamics_f32",
     "grbda_cuda_forward_dynamics_f64", "grbda_cuda_forward_dynamics_f32",
     "grbda_cuda_mass_matrix_f64", "grbda_cuda_mass_matrix_f32",
@@ -350,6 +354,12 @@ class ClusterTreeModel:
         _check(_lib.grbda_cuda_external_force_bodies(self._h, idx, C.byref(n)))
         return [int(idx[i]) for i in range(n.value)]
 
+    def setExternalForceBodies(self, bodies):
+        """Any distinct body indices (empty: back to the default, the terminal links); the force programs are
+        recompiled for the set at run time."""
+        arr = (C.c_int32 * max(1, len(bodies)))(*bodies)
+        _check(_lib.grbda_cuda_set_external_force_bodies(self._h, arr, len(bodies)))
+
     def _dynamics_ext(self, name, q, yd, in3, f_ext, out):
         import torch
         q = self._prep(q, self.nq, torch.float64)
@@ -441,6 +451,32 @@ class ClusterTreeModel:
         fn = getattr(_lib, "grbda_cuda_forward_dynamics_" + self._suffix(q))
         _check(fn(self._h, _ptr(q), _ptr(yd), _ptr(tau), _ptr(out), q.shape[0], _stream()))
         return out
+
+    def integrate(self, q, yd, ydd, dt, out=None):
+        """(q', yd', flags): semi-implicit Euler step, quaternion base by ori::integrateQuat, implicit clusters
+        projected back onto phi = 0; flags[b] = 1 where that projection failed."""
+        import torch
+        q = self._prep(q, self.nq, torch.float64)
+        yd, ydd = self._prep(yd, self.nv, torch.float64), self._prep(ydd, self.nv, torch.float64)
+        qo, ydo = out if out is not None else (torch.empty_like(q), torch.empty_like(yd))
+        flags = torch.empty((q.shape[0],), dtype=torch.int32, device=q.device)
+        _check(_lib.grbda_cuda_integrate_f64(self._h, _ptr(q), _ptr(yd), _ptr(ydd), float(dt), _ptr(qo), _ptr(ydo),
+                                             _ptr(flags), q.shape[0], _stream()))
+        return qo, ydo, flags
+
+    def step(self, q, yd, tau, dt, f_ext=None, out=None):
+        """One simulation step: forwardDynamics (+ external forces) and integrate."""
+        import torch
+        q = self._prep(q, self.nq, torch.float64)
+        yd, tau = self._prep(yd, self.nv, torch.float64), self._prep(tau, self.nv, torch.float64)
+        B = q.shape[0]
+        if f_ext is not None:
+            f_ext = self._prep(f_ext.reshape(B, -1), 6 * len(self.externalForceBodies()), torch.float64)
+        qo, ydo = out if out is not None else (torch.empty_like(q), torch.empty_like(yd))
+        flags = torch.empty((B,), dtype=torch.int32, device=q.device)
+        _check(_lib.grbda_cuda_step_f64(self._h, _ptr(q), _ptr(yd), _ptr(tau), _ptr(f_ext), float(dt), _ptr(qo),
+                                        _ptr(ydo), _ptr(flags), B, _stream()))
+        return qo, ydo, flags
 
     def getMassMatrix(self, q, out=None):
         """H[batch, nv, nv]   (ClusterTreeModel::getMassMatrix)"""

@@ -32,12 +32,13 @@ LIB = os.path.join(_OUT, "libgrbda_cuda.so")
 # GRBDA_KERNEL_VARIANT selects another one at run time (tools/sweep_variants.py).
 # Kernel variants per entry point: KIND,BLOCK,MIN_BLOCKS[,SYNC][,ltl] separated by ';' (first = default,
 # GRBDA_KERNEL_VARIANT=k selects the k-th). KIND: T = TMA-staged tiles, S = software-staged tiles,
-# D = direct global I/O, R = one warp per limb. 'ltl' = forward dynamics as CRBA + bias + sparse LTDL
-# (otherwise the articulated-body sweep); 'park' = long-lived values parked in dead slots of the thread's
+# D = direct global I/O. 'ltl' = forward dynamics as CRBA + bias + sparse LTDL (otherwise the
+# articulated-body sweep), 'auto' = whichever of the two the measured rule picks for the model
+# (compiler/compile.h chooseForwardDynamicsProgram); 'park' = long-lived values parked in dead slots of the thread's
 # shared-memory tile row instead of being spilled (T and S only); 'f32aba' = the FP32 kernel of the variant runs the
 # articulated-body sweep. Measured on B200 (profiles/README.md): T,128,2 is the fastest
 # and the most device-independent shape for every entry point.
-DEFAULT_VARIANTS = "id=T,128,2;S,128,2|fd=T,128,2,ltl,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2"
+DEFAULT_VARIANTS = "id=T,128,2;S,128,2|fd=T,128,2,auto,park;T,128,2,ltl,park;T,128,2;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2"
 SYNC_EVERY = int(os.environ.get("GRBDA_SYNC_EVERY", "0"))  # alignment barriers measured useless (profiles/)
 MODELS = {
     "tello_with_arms": ("id,fd,fk,h,phi,gfa,gfs,gen", "id=T,128,2;S,128,2|fd=T,128,2,ltl,park;T,128,2,ltl;S,128,2,ltl,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2", True),
@@ -51,7 +52,7 @@ MODELS = {
     # 58 bodies: the tile rows of a 128-thread CTA take 163 KB (one CTA per SM); 64-thread CTAs fit twice.
     # Both dynamics kernels spill and are parked (ID 1.01 -> 0.86 ms, FD 3.3-4.2 ms per 2^20 states, L2 dependent)
     "jvrc1_humanoid": ("id,fd,fk,h,phi,gfa,gfs,gen",
-                       "id=T,64,2,park;T,128,2,park;S,128,2|fd=T,64,2,ltl,park;T,128,2,ltl,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2", True),
+                       "id=T,64,2,park;T,128,2,park;S,128,2|fd=T,64,2,ltl,park;T,128,2,ltl,park;T,64,2,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2", True),
     "revolute_rotor_chain": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_2": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_4": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
@@ -60,7 +61,7 @@ MODELS = {
     # FP32: forward dynamics of the 16-link fixed-base chain (cond(H) ~ 2e4) through the articulated-body sweep:
     # median error 6e-7 instead of 1e-4 with the factorisation (measured, tests/test_gpu_parity.py)
     "revolute_chain_with_rotor_16": ("id,fd,fk,h,gfa,gfs,gen",
-                                     DEFAULT_VARIANTS.replace("fd=T,128,2,ltl,park;", "fd=T,128,2,ltl,park,f32aba;"), True),
+                                     DEFAULT_VARIANTS.replace("fd=T,128,2,auto,park;", "fd=T,128,2,auto,park,f32aba;"), True),
     "revolute_pair_chain_with_rotor_2": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
     "revolute_pair_chain_with_rotor_4": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
     # the remaining cluster-joint classes of the reference: RevolutePair (RevolutePairChain.cpp) and

@@ -567,6 +567,8 @@ namespace grbda
             // ---------------------------------------------------------------------------------
             static std::vector<int> externalForceBodies(const ClusterTreeModel &model)
             {
+                if (!model.externalForceBodies().empty())
+                    return model.externalForceBodies(); // chosen by the caller (any bodies, rotors included)
                 ModelCompiler probe(model);
                 std::vector<char> has_child(model.getNumBodies(), 0);
                 for (const Body &b : model.bodies())

@@ -186,6 +186,25 @@ namespace grbda
             return out;
         }
 
+        // Which program runs forwardDynamics by default. Both are ClusterTreeModel::forwardDynamics; the
+        // factorisation (cluster CRBA + bias + branch-sparse L^T D L) keeps far fewer values alive between its two
+        // sweeps and wins on floating-base robots with short limbs, the articulated-body sweep is O(depth) and
+        // wins on deep chains. Measured on B200 (profiles/r2_fd_program_sweep.jsonl, 15 models): the
+        // factorisation is the faster kernel exactly when it executes fewer than ~0.85 x the operations of the
+        // sweep (Tello 0.77 -> 2.3x faster; 8-link chain 0.91 -> 1.7x slower; 24-link chain 2.85 -> 6x slower).
+        inline int chooseForwardDynamicsProgram(const ClusterTreeModel &model)
+        {
+            if (const char *force = std::getenv("GRBDA_FD_PROGRAM")) // "aba" / "ltl": experiments
+                return std::string(force) == "aba" ? (int)ALGO_FD : (int)PROGRAM_FD_LTL;
+            auto flops = [&](int program) {
+                sym::Graph graph;
+                sym::GraphScope scope(graph);
+                const Program p = buildProgram(model, program);
+                return (double)Emitter(graph, p).stats().flops();
+            };
+            return flops(PROGRAM_FD_LTL) < 0.85 * flops(ALGO_FD) ? (int)PROGRAM_FD_LTL : (int)ALGO_FD;
+        }
+
         // The generated `struct Body` of one program: sizes, range check, run<real, FAST>(). Shared by the
         // build-time tool (tools/modelc.cpp) and grbda_cuda_emit_source (host-compiled emitter self test).
         inline void emitBodyStruct(std::ostream &os, const std::string &struct_name, const CompiledAlgo &c)
@@ -307,6 +326,34 @@ namespace grbda
             }
             os << "        for (int i = 0; i < NV; i++) yd[i] = rng.uniform();\n"
                   "        for (int i = 0; i < NV; i++) aux[i] = rng.uniform();\n        return ok;\n    }\n};\n";
+            // integration step: positions from the NEW velocities (semi-implicit Euler), cluster by cluster
+            os << "struct Step\n{\n    static constexpr int NQ = " << nq << ", NV = " << nv << ";\n";
+            os << "    static __device__ bool run(const double *q, const double *yd, double dt, double *qn)\n    {\n"
+                  "        bool ok = true;\n";
+            for (const ClusterTreeNode &c : model.clusters())
+            {
+                const ClusterDesc &d = c.joint_;
+                const int pi = c.position_index_, vi = c.velocity_index_;
+                if (d.type == ClusterType::FreeQuaternion)
+                    os << "        integrateFreeQuaternion(q + " << pi << ", yd + " << vi << ", dt, qn + " << pi << ");\n";
+                else if (d.type == ClusterType::FreeRollPitchYaw) // no reference counterpart (integrateQuat only): refused per state
+                    os << "        for (int i = 0; i < 6; i++) qn[" << pi << " + i] = q[" << pi << " + i];\n        ok = false;\n";
+                else if (d.type == ClusterType::Explicit)
+                    os << "        for (int i = 0; i < " << d.num_positions << "; i++) qn[" << pi << " + i] = q[" << pi
+                       << " + i] + dt * yd[" << vi << " + i];\n";
+                else
+                {
+                    // independent spanning coordinates advance with their velocities, dependent ones start from
+                    // their old values and are projected back onto phi = 0
+                    os << "        for (int i = 0; i < " << d.num_bodies << "; i++) qn[" << pi << " + i] = q[" << pi << " + i];\n";
+                    int k = 0;
+                    for (int i = 0; i < d.num_bodies; i++)
+                        if (d.independent[i])
+                            os << "        qn[" << pi + i << "] += dt * yd[" << vi + k++ << "];\n";
+                    os << "        ok = projectImplicitPosition<Cluster" << c.index_ << ">(qn + " << pi << ") && ok;\n";
+                }
+            }
+            os << "        return ok;\n    }\n};\n";
         }
 
         // Binary tape: int32 header {magic, n_ops, n_arrays, n_in0, n_in1, n_in2}, then op,a,b,c,e

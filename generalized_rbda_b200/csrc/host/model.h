@@ -528,6 +528,23 @@ namespace grbda
         }
         const Vec3 &getGravity() const { return gravity_; }
 
+        // Bodies that take external forces in the batched *_ext entry points (TreeModel::setExternalForces,
+        // TreeModel.cpp:215-239, names any set of bodies per call; the batched path fixes the set per model so
+        // that the force programs can be specialised). Empty: the default set, every terminal link.
+        void setExternalForceBodies(const std::vector<int> &bodies)
+        {
+            std::vector<char> seen(bodies_.size(), 0);
+            for (int b : bodies)
+            {
+                if (b < 0 || b >= (int)bodies_.size() || seen[b])
+                    throw std::runtime_error("setExternalForceBodies: body indices must be distinct and in range");
+                seen[b] = 1;
+            }
+            external_force_bodies_ = bodies;
+            device_model_.reset();
+        }
+        const std::vector<int> &externalForceBodies() const { return external_force_bodies_; }
+
         // reference: TreeModel.h:25-28, ClusterTreeModel.h:97
         int getNumPositions() const { return position_index_; }
         int getNumDegreesOfFreedom() const { return velocity_index_; }
@@ -565,6 +582,7 @@ namespace grbda
         std::map<int, int> body_index_to_cluster_index_;
         int position_index_ = 0, velocity_index_ = 0, motion_subspace_index_ = 0;
         Vec3 gravity_ = {0., 0., -9.81};
+        std::vector<int> external_force_bodies_;
         mutable std::shared_ptr<void> device_model_; // grbda_model handle + deleter; copies of the model share it
     };
 

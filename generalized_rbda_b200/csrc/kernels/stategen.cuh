@@ -241,6 +241,102 @@ namespace grbda_kernels
         return false;
     }
 
+    // ---- integration step ------------------------------------------------------------------
+    // quaternion (w, x, y, z) after rotating for dt with the WORLD-frame angular velocity omega:
+    // ori::integrateQuat, include/grbda/Utils/OrientationTools.h:387-413 (axis-angle increment, product, renormalise)
+    __device__ inline void integrateQuat(const double q[4], const double omega[3], double dt, double out[4])
+    {
+        double ang = sqrt(omega[0] * omega[0] + omega[1] * omega[1] + omega[2] * omega[2]);
+        double axis[3] = {1.0, 0.0, 0.0};
+        if (ang > 0.0)
+            for (int i = 0; i < 3; i++)
+                axis[i] = omega[i] / ang;
+        ang *= dt;
+        double s, c;
+        sincos(0.5 * ang, &s, &c);
+        const double d[4] = {c, s * axis[0], s * axis[1], s * axis[2]};
+        // quatProduct(d, q) (OrientationTools.h:343-360)
+        double r[4] = {d[0] * q[0] - d[1] * q[1] - d[2] * q[2] - d[3] * q[3],
+                       d[0] * q[1] + d[1] * q[0] + d[2] * q[3] - d[3] * q[2],
+                       d[0] * q[2] - d[1] * q[3] + d[2] * q[0] + d[3] * q[1],
+                       d[0] * q[3] + d[1] * q[2] - d[2] * q[1] + d[3] * q[0]};
+        const double n = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]);
+        for (int i = 0; i < 4; i++)
+            out[i] = r[i] / n;
+    }
+    // Free joint (Joint.h:61-68, FreeJoint.cpp:29-46): q = [p world; quat], yd = [omega_body; v_body]. With
+    // E = R(quat)^T (world -> body, OrientationTools.h:251-269): p' = p + dt E^T v_body, quat' =
+    // integrateQuat(quat, E^T omega_body, dt).
+    __device__ inline void integrateFreeQuaternion(const double *q, const double *yd, double dt, double *q_out)
+    {
+        const double w = q[3], x = q[4], y = q[5], z = q[6];
+        // body -> world rotation R(quat)
+        const double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                             2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                             2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)};
+        double om[3], v[3];
+        for (int i = 0; i < 3; i++)
+        {
+            om[i] = R[3 * i] * yd[0] + R[3 * i + 1] * yd[1] + R[3 * i + 2] * yd[2];
+            v[i] = R[3 * i] * yd[3] + R[3 * i + 1] * yd[4] + R[3 * i + 2] * yd[5];
+        }
+        for (int i = 0; i < 3; i++)
+            q_out[i] = q[i] + dt * v[i];
+        integrateQuat(q + 3, om, dt, q_out + 3);
+    }
+    // Dependent coordinates of an implicit cluster back onto phi(q) = 0 (Newton on the dependent coordinates,
+    // independent ones held; the same iteration the state generator uses). Returns false when it did not converge.
+    template <typename C>
+    __device__ inline bool projectImplicitPosition(double *q)
+    {
+        constexpr int NC = C::NC;
+        double phi[NC], Kd[NC * NC];
+        for (int it = 0; it < 30; it++)
+        {
+            C::eval(q, phi, Kd);
+            double nrm = 0;
+            for (int i = 0; i < NC; i++)
+                nrm = fmax(nrm, fabs(phi[i]));
+            if (!(nrm == nrm))
+                return false;
+            if (nrm < 1e-13)
+                return true;
+            if (!smallSolve<NC>(Kd, phi))
+                return false;
+            for (int i = 0; i < NC; i++)
+                q[C::dep(i)] -= phi[i];
+        }
+        C::eval(q, phi, Kd);
+        double s = 0;
+        for (int i = 0; i < NC; i++)
+            s += phi[i] * phi[i];
+        return sqrt(s) < 1e-10;
+    }
+
+    // Step::run advances one state (generated per model): semi-implicit Euler, yd' = yd + dt ydd, q' from yd'
+    template <typename Step>
+    __global__ void __launch_bounds__(128)
+        grbda_integrate_kernel(const double *__restrict__ q, const double *__restrict__ yd, const double *__restrict__ ydd,
+                               double dt, int64_t count, double *__restrict__ q_out, double *__restrict__ yd_out,
+                               int32_t *__restrict__ flags)
+    {
+        const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= count)
+            return;
+        double ql[Step::NQ], ydl[Step::NV], qn[Step::NQ];
+        for (int k = 0; k < Step::NQ; k++)
+            ql[k] = q[i * Step::NQ + k];
+        for (int k = 0; k < Step::NV; k++)
+            ydl[k] = yd[i * Step::NV + k] + dt * ydd[i * Step::NV + k];
+        const bool ok = Step::run(ql, ydl, dt, qn);
+        for (int k = 0; k < Step::NQ; k++)
+            q_out[i * Step::NQ + k] = qn[k];
+        for (int k = 0; k < Step::NV; k++)
+            yd_out[i * Step::NV + k] = ydl[k];
+        if (flags)
+            flags[i] = ok ? 0 : 1;
+    }
+
     // Gen::run fills one state (generated per model, csrc/generated/<model>_gen.cu)
     template <typename Gen>
     __global__ void __launch_bounds__(128)

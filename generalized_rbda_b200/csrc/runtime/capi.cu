@@ -34,6 +34,9 @@ struct grbda_model
     int device = -1;
     const ModelKernels *kernels = nullptr;         // ahead-of-time kernels (build.py MODELS), or
     std::unique_ptr<grbda_runtime::JitModel> jit;  // kernels compiled at run time (runtime/jit.h)
+    // external-force programs for a caller-chosen body set (grbda_cuda_set_external_force_bodies): always
+    // compiled at run time, also for models whose other kernels were built ahead of time
+    std::unique_ptr<grbda_runtime::JitModel> jit_ext;
     bool hasKernels() const { return kernels || jit; }
     // host-buffer pipeline (grbda_cuda_dynamics_host_f64)
     std::mutex host_mutex;
@@ -214,7 +217,8 @@ namespace
         int n_in[3], n_out[3];
         grbda_runtime::LaunchFn fn = nullptr;
         const grbda_runtime::JitKernel *jk = nullptr;
-        if (m->kernels)
+        const bool custom_forces = m->jit_ext && (algo == compiler::ALGO_GFA || algo == compiler::ALGO_GFS);
+        if (m->kernels && !custom_forces)
         {
             const grbda_runtime::AlgoKernels &ak = m->kernels->algo[algo];
             entrySizes(m, algo, f32, n_in, n_out);
@@ -231,9 +235,10 @@ namespace
         else
         {
             std::string err;
-            if (!grbda_runtime::jitPrepare(*m->jit, m->model, m->hash, m->device, algo, f32, err))
+            grbda_runtime::JitModel &jm = custom_forces ? *m->jit_ext : *m->jit;
+            if (!grbda_runtime::jitPrepare(jm, m->model, m->hash, m->device, algo, f32, err))
                 return fail(GRBDA_ERR_NOT_COMPILED, std::string("kernel '") + compiler::algoName(algo) + "': " + err);
-            jk = &m->jit->algo[algo][f32 ? 1 : 0];
+            jk = &jm.algo[algo][f32 ? 1 : 0];
             std::memcpy(n_in, jk->n_in, sizeof(jk->n_in));
             std::memcpy(n_out, jk->n_out, sizeof(jk->n_out));
         }
@@ -311,6 +316,8 @@ extern "C"
                 cudaFree(kv.second.ptr);
         if (m->jit)
             grbda_runtime::jitRelease(*m->jit);
+        if (m->jit_ext)
+            grbda_runtime::jitRelease(*m->jit_ext);
         delete m;
         return GRBDA_OK;
     }
@@ -483,6 +490,40 @@ extern "C"
                     body_indices[i] = b[i];
             return (grbda_status)GRBDA_OK; });
     }
+    grbda_status grbda_cuda_set_external_force_bodies(grbda_model *m, const int32_t *body_indices, int32_t count)
+    {
+        if (!m || count < 0 || (count > 0 && !body_indices))
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        return guarded([&]
+                       {
+            // launches that still use the old programs must have finished
+            if (m->device >= 0)
+            {
+                DeviceScope scope(m->device);
+                cudaDeviceSynchronize();
+            }
+            m->model.setExternalForceBodies(std::vector<int>(body_indices, body_indices + count));
+            if (m->jit_ext)
+                grbda_runtime::jitRelease(*m->jit_ext);
+            m->jit_ext.reset();
+            if (count > 0 && m->device >= 0)
+            {
+                if (grbda_runtime::jitMode() == 0 && m->kernels)
+                    return fail(GRBDA_ERR_NOT_COMPILED, "a custom external-force body set needs run-time compilation (GRBDA_JIT=0)");
+                m->jit_ext.reset(new grbda_runtime::JitModel());
+            }
+            if (m->jit) // a run-time compiled model: its force programs are rebuilt for the new set
+                for (int a : {compiler::ALGO_GFA, compiler::ALGO_GFS})
+                    for (int p = 0; p < 2; p++)
+                        if (m->jit->algo[a][p].ready || !m->jit->algo[a][p].error.empty())
+                        {
+                            if (m->jit->algo[a][p].library)
+                                cudaLibraryUnload(m->jit->algo[a][p].library);
+                            m->jit->algo[a][p] = grbda_runtime::JitKernel();
+                        }
+            return (grbda_status)GRBDA_OK; });
+    }
+
     grbda_status grbda_cuda_inverse_dynamics_ext_f64(const grbda_model *m, const double *q, const double *yd,
                                                      const double *ydd, const double *f_ext, double *tau,
                                                      int64_t batch, void *stream)
@@ -788,6 +829,54 @@ extern "C"
                 f.write(cubin.data(), (std::streamsize)cubin.size());
             }
             return (grbda_status)GRBDA_OK; });
+    }
+
+    // ---- integration step / simulation step ---------------------------------------------------
+    grbda_status grbda_cuda_integrate_f64(const grbda_model *m, const double *q, const double *yd, const double *ydd,
+                                          double dt, double *q_out, double *yd_out, int32_t *flags, int64_t batch,
+                                          void *stream)
+    {
+        if (!m || !q || !yd || !ydd || !q_out || !yd_out || batch < 0)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        if (m->device < 0 || !m->hasKernels())
+            return fail(GRBDA_ERR_NO_DEVICE, "model was created without a CUDA device (host-only handle)");
+        if (m->kernels && !m->kernels->integrate)
+            return fail(GRBDA_ERR_NOT_COMPILED, "integration step was not compiled for this model");
+        DeviceScope scope(m->device);
+        if (scope.error != cudaSuccess)
+            return cudaFail(scope.error, "cudaSetDevice");
+        grbda_runtime::StepArgs a{q, yd, ydd, dt, batch, q_out, yd_out, flags, (cudaStream_t)stream};
+        if (m->jit)
+        {
+            std::string err;
+            if (!grbda_runtime::jitPrepareGenerate(*m->jit, m->model, m->hash, m->device, err))
+                return fail(GRBDA_ERR_NOT_COMPILED, "integration step: " + err);
+        }
+        const cudaError_t e = m->jit ? grbda_runtime::jitLaunchIntegrate(m->jit->generate, a) : m->kernels->integrate(a);
+        if (e != cudaSuccess)
+            return cudaFail(e, "integrate launch");
+        g_launches++;
+        return GRBDA_OK;
+    }
+
+    grbda_status grbda_cuda_step_f64(const grbda_model *m, const double *q, const double *yd, const double *tau,
+                                     const double *f_ext, double dt, double *q_out, double *yd_out, int32_t *flags,
+                                     int64_t batch, void *stream)
+    {
+        if (!m || batch < 0)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        if (batch == 0)
+            return GRBDA_OK;
+        if (m->device < 0 || !m->hasKernels())
+            return fail(GRBDA_ERR_NO_DEVICE, "model was created without a CUDA device (host-only handle)");
+        const size_t bytes = (size_t)batch * m->model.getNumDegreesOfFreedom() * sizeof(double);
+        double *ydd = (double *)m->scratchFor((cudaStream_t)stream, bytes, 2);
+        if (!ydd)
+            return fail(GRBDA_ERR_CUDA, "cannot allocate the acceleration buffer: " + m->scratch_error);
+        grbda_status st = grbda_cuda_forward_dynamics_ext_f64(m, q, yd, tau, f_ext, ydd, batch, stream);
+        if (st != GRBDA_OK)
+            return st;
+        return grbda_cuda_integrate_f64(m, q, yd, ydd, dt, q_out, yd_out, flags, batch, stream);
     }
 
     // ---- host placement for the host-buffer path ------------------------------------------------------------

@@ -61,6 +61,7 @@ namespace grbda_runtime
                             std::string &error);
     cudaError_t jitLaunch(const JitKernel &k, bool f32, const LaunchArgs &a);
     cudaError_t jitLaunchGenerate(const JitKernel &k, const GenArgs &a);
+    cudaError_t jitLaunchIntegrate(const JitKernel &k, const StepArgs &a); // k = JitModel::generate (second kernel of that module)
     void jitRelease(JitModel &jm);
 
     // The CUDA text handed to NVRTC for one entry point (tests compile it without a device).

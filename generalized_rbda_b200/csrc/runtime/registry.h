@@ -22,6 +22,16 @@ namespace grbda_runtime
         cudaStream_t stream;
     };
     typedef cudaError_t (*GenFn)(const GenArgs &);
+    struct StepArgs
+    {
+        const double *q, *yd, *ydd;
+        double dt;
+        int64_t count;
+        double *q_out, *yd_out;
+        int32_t *flags;
+        cudaStream_t stream;
+    };
+    typedef cudaError_t (*StepFn)(const StepArgs &);
 
     enum
     {
@@ -43,6 +53,7 @@ namespace grbda_runtime
         int nq, nv, nb, nc;
         AlgoKernels algo[7]; // id, fd, fk, h, phi, gfa, gfs (compiler::ALGO_COUNT)
         GenFn generate;
+        StepFn integrate;
     };
 
     // Records are assembled from the per-algorithm translation units at load time.
@@ -61,9 +72,11 @@ namespace grbda_runtime
     };
     struct GenRegistrar
     {
-        GenRegistrar(uint64_t hash, const char *name, int nq, int nv, int nb, int nc, GenFn fn)
+        GenRegistrar(uint64_t hash, const char *name, int nq, int nv, int nb, int nc, GenFn fn, StepFn step = nullptr)
         {
-            modelRecord(hash, name, nq, nv, nb, nc)->generate = fn;
+            ModelKernels *k = modelRecord(hash, name, nq, nv, nb, nc);
+            k->generate = fn;
+            k->integrate = step;
         }
     };
 } // namespace grbda_runtime

@@ -139,6 +139,8 @@ int main(int argc, char **argv)
             {
                 if (p[t] == "ltl")
                     var.program = PROGRAM_FD_LTL;
+                else if (p[t] == "auto") // forward dynamics: the program the measured rule picks (compile.h)
+                    var.program = -2;
                 else if (p[t] == "park")
                     var.park = var.kind == 'S' || var.kind == 'T';
                 else if (p[t] == "f32aba")
@@ -190,8 +192,12 @@ int main(int argc, char **argv)
                     v.sync = sync_every;
             const int out_chunk = grbda_kernels::OUT_CHUNK; // only arrays with more than 64 values use it
             for (auto &v : variants)
-                if (v.program >= 0 && algoOfProgram(v.program) != a)
-                    v.program = -1; // "ltl" only applies to fd
+            {
+                if (v.program == -2)
+                    v.program = a == ALGO_FD ? chooseForwardDynamicsProgram(model) : -1;
+                if (v.program >= 0 && (algoOfProgram(v.program) != a || v.program == a))
+                    v.program = -1; // "ltl" / "auto" only apply to fd
+            }
             {
                 // a parked body writes into its tile rows: only where the flagged-tile pass stages them too
                 int n_in[3], n_out[3];
@@ -295,8 +301,14 @@ int main(int argc, char **argv)
                   "    grbda_generate_kernel<Gen><<<(unsigned)((a.count + block - 1) / block), block, 0, a.stream>>>(\n"
                   "        a.seed, a.first_index, a.count, a.q, a.yd, a.aux, a.flags);\n"
                   "    return cudaGetLastError();\n}\n";
+            os << "static cudaError_t launchIntegrate(const grbda_runtime::StepArgs &a)\n{\n"
+                  "    if (a.count <= 0) return cudaSuccess;\n"
+                  "    const int block = 128;\n"
+                  "    grbda_integrate_kernel<Step><<<(unsigned)((a.count + block - 1) / block), block, 0, a.stream>>>(\n"
+                  "        a.q, a.yd, a.ydd, a.dt, a.count, a.q_out, a.yd_out, a.flags);\n"
+                  "    return cudaGetLastError();\n}\n";
             os << "static grbda_runtime::GenRegistrar r_gen(0x" << std::hex << hash << std::dec << "ull, \""
-               << model_name << "\", " << nq << ", " << nv << ", " << nb << ", " << nc << ", &launchGenerate);\n";
+               << model_name << "\", " << nq << ", " << nv << ", " << nb << ", " << nc << ", &launchGenerate, &launchIntegrate);\n";
             writeIfChanged(out_dir + "/" + id + "_gen.cu", os.str());
         }
         writeIfChanged(out_dir + "/" + id + ".json", json.str());

@@ -190,18 +190,39 @@ grbda_status grbda_cuda_inverse_dynamics_f64(const grbda_model *m, const double 
 grbda_status grbda_cuda_inverse_dynamics_f32(const grbda_model *m, const float *q, const float *yd,
                                              const float *ydd, float *tau, int64_t batch, void *stream);
 /* External forces (TreeModel::setExternalForces, src/Dynamics/TreeModel.cpp:215-239; applied at
- * TreeModel.cpp:189-193 and ClusterTreeDynamics.cpp:100-105). Supported on the model's terminal links
- * (leaf bodies that are not motor rotors: feet, hands, chain tips): body_indices receives their body
- * indices in the order the f_ext arrays use; pass body_indices = NULL to query the count.
+ * TreeModel.cpp:189-193 and ClusterTreeDynamics.cpp:100-105). By default on the model's terminal links
+ * (leaf bodies that are not motor rotors: feet, hands, chain tips), or on the set chosen with
+ * grbda_cuda_set_external_force_bodies: body_indices receives the body indices in the order the
+ * f_ext arrays use; pass body_indices = NULL to query the count.
  * f_ext[batch][count][6] = one spatial force [n; f] per listed body, in WORLD coordinates as the
  * reference takes them. f_ext = NULL means no external forces. */
 grbda_status grbda_cuda_external_force_bodies(const grbda_model *m, int32_t *body_indices, int32_t *count);
+/* Choose the bodies that take external forces: ANY distinct bodies of the model (the reference's test
+ * puts a force on every body, UnitTests/testRigidBodyDynamicsAlgos.cpp:201-236); count = 0 restores
+ * the default (terminal links). The force programs are specialised for the set and compiled at run
+ * time when it is first used. Not to be called while launches on this handle are in flight (it is the
+ * one mutating call of an otherwise immutable handle; it synchronises the device). */
+grbda_status grbda_cuda_set_external_force_bodies(grbda_model *m, const int32_t *body_indices, int32_t count);
 grbda_status grbda_cuda_inverse_dynamics_ext_f64(const grbda_model *m, const double *q, const double *yd,
                                                  const double *ydd, const double *f_ext, double *tau,
                                                  int64_t batch, void *stream);
 grbda_status grbda_cuda_forward_dynamics_ext_f64(const grbda_model *m, const double *q, const double *yd,
                                                  const double *tau, const double *f_ext, double *ydd,
                                                  int64_t batch, void *stream);
+/* Integration step (semi-implicit Euler): yd_out = yd + dt ydd, q_out = q advanced with yd_out -
+ * revolute coordinates q + dt yd; free base p + dt R v_body and ori::integrateQuat(quat, R omega_body,
+ * dt) (include/grbda/Utils/OrientationTools.h:387-413); clusters with an implicit loop constraint
+ * advance their independent coordinates and are projected back onto phi(q) = 0 (Newton on the
+ * dependent coordinates, the iteration of GenericJoint.cpp:290-385). flags (optional, int32 per
+ * state): 1 where the projection did not converge. q_out / yd_out may alias q / yd. */
+grbda_status grbda_cuda_integrate_f64(const grbda_model *m, const double *q, const double *yd, const double *ydd,
+                                      double dt, double *q_out, double *yd_out, int32_t *flags, int64_t batch,
+                                      void *stream);
+/* One simulation step: forwardDynamics (with external forces when f_ext != NULL) followed by the
+ * integration step above; the accelerations live in a per-stream scratch buffer of the handle. */
+grbda_status grbda_cuda_step_f64(const grbda_model *m, const double *q, const double *yd, const double *tau,
+                                 const double *f_ext, double dt, double *q_out, double *yd_out, int32_t *flags,
+                                 int64_t batch, void *stream);
 /* ydd = FD(q, yd, tau). Replaces setState + ClusterTreeModel::forwardDynamics(tau),
  * src/Dynamics/ClusterTreeDynamics.cpp:85-191. */
 grbda_status grbda_cuda_forward_dynamics_f64(const grbda_model *m, const double *q, const double *yd,

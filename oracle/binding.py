@@ -143,6 +143,14 @@ class OracleModel:
                                             C.c_int64(q.shape[0]), threads))
         return valid.astype(bool)
 
+    def integrate(self, q, yd, ydd, dt, threads=0):
+        """(q', yd', flags) of the semi-implicit Euler step (oracle/grbda_oracle/rng.h integrateState)."""
+        qo, ydo = np.zeros_like(q), np.zeros_like(yd)
+        flags = np.zeros(q.shape[0], dtype=np.int32)
+        _check(lib().oracle_integrate(self._h, _P(q), _P(yd), _P(ydd), C.c_double(dt), _P(qo), _P(ydo),
+                                      flags.ctypes.data_as(C.POINTER(C.c_int)), C.c_int64(q.shape[0]), threads))
+        return qo, ydo, flags
+
     def cluster_constraint(self, cluster, q, yd):
         G, K, g, k = np.zeros(1024), np.zeros(1024), np.zeros(64), np.zeros(64)
         dims = (C.c_int * 4)()

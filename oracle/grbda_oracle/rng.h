@@ -160,4 +160,91 @@ namespace grbda_oracle
             aux[i] = rng.uniform();
     }
 
+    // ---- integration step (test infrastructure for the product's grbda_cuda_integrate_f64) -------------------
+    // reference: include/grbda/Utils/OrientationTools.h:365-377 (quatProduct)
+    inline void quatProduct(const double a[4], const double b[4], double out[4])
+    {
+        const double r = a[0] * b[0] - (a[1] * b[1] + a[2] * b[2] + a[3] * b[3]);
+        const double v[3] = {a[0] * b[1] + b[0] * a[1] + (a[2] * b[3] - a[3] * b[2]),
+                             a[0] * b[2] + b[0] * a[2] + (a[3] * b[1] - a[1] * b[3]),
+                             a[0] * b[3] + b[0] * a[3] + (a[1] * b[2] - a[2] * b[1])};
+        out[0] = r, out[1] = v[0], out[2] = v[1], out[3] = v[2];
+    }
+    // reference: include/grbda/Utils/OrientationTools.h:387-413 (integrateQuat; omega in INERTIAL coordinates)
+    inline void integrateQuat(const double quat[4], const double omega[3], double dt, double out[4])
+    {
+        double axis[3] = {1.0, 0.0, 0.0};
+        double ang = std::sqrt(omega[0] * omega[0] + omega[1] * omega[1] + omega[2] * omega[2]);
+        if (ang > 0)
+            for (int i = 0; i < 3; i++)
+                axis[i] = omega[i] / ang;
+        ang *= dt;
+        const double s = std::sin(ang / 2), quatD[4] = {std::cos(ang / 2), s * axis[0], s * axis[1], s * axis[2]};
+        double qn[4];
+        quatProduct(quatD, quat, qn);
+        const double n = std::sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+        for (int i = 0; i < 4; i++)
+            out[i] = qn[i] / n;
+    }
+    // Semi-implicit Euler step of one state: yd' = yd + dt ydd; positions advance with yd' - revolute
+    // coordinates linearly, the free base through its body-frame twist (Joints::Free, Joint.h:61-68: the
+    // joint transform is (E = R(quat)^T, p), so world rates are R omega_body and R v_body), implicit clusters
+    // on their independent coordinates followed by the Newton projection onto phi = 0 used by
+    // GenericJoint.cpp:290-385. Returns false when a projection did not converge.
+    inline bool integrateState(ClusterTreeModel<double> &model, const double *q, const double *yd, const double *ydd,
+                               double dt, double *q_out, double *yd_out)
+    {
+        const int nv = model.getNumDegreesOfFreedom();
+        for (int i = 0; i < nv; i++)
+            yd_out[i] = yd[i] + dt * ydd[i];
+        bool ok = true;
+        for (auto &node : model.nodes)
+        {
+            const double *qc = q + node->position_index, *vc = yd_out + node->velocity_index;
+            double *qo = q_out + node->position_index;
+            auto lc = node->joint->loop_constraint;
+            if (dynamic_cast<FreeCluster<double> *>(node->joint.get()) || dynamic_cast<FreeConstraint<double> *>(lc.get()))
+            {
+                if (node->num_positions != 7)
+                {
+                    for (int i = 0; i < node->num_positions; i++)
+                        qo[i] = qc[i];
+                    ok = false;
+                    continue;
+                }
+                Mat<double> quat(4, 1);
+                for (int i = 0; i < 4; i++)
+                    quat[i] = qc[3 + i];
+                const Mat<double> R = quaternionToRotationMatrix(quat).transpose(); // body -> world
+                double om[3], v[3];
+                for (int i = 0; i < 3; i++)
+                {
+                    om[i] = R(i, 0) * vc[0] + R(i, 1) * vc[1] + R(i, 2) * vc[2];
+                    v[i] = R(i, 0) * vc[3] + R(i, 1) * vc[4] + R(i, 2) * vc[5];
+                }
+                for (int i = 0; i < 3; i++)
+                    qo[i] = qc[i] + dt * v[i];
+                integrateQuat(qc + 3, om, dt, qo + 3);
+            }
+            else if (lc->isExplicit())
+            {
+                for (int i = 0; i < node->num_positions; i++)
+                    qo[i] = qc[i] + dt * vc[i];
+            }
+            else
+            {
+                auto *gi = dynamic_cast<GenericImplicitConstraint<double> *>(lc.get());
+                Mat<double> qs(node->num_positions, 1);
+                for (int i = 0; i < node->num_positions; i++)
+                    qs[i] = qc[i];
+                for (size_t k = 0; k < gi->ind_coords.size(); k++)
+                    qs[gi->ind_coords[k]] += dt * vc[k];
+                ok = solveImplicitPosition(*gi, qs) && ok;
+                for (int i = 0; i < node->num_positions; i++)
+                    qo[i] = qs[i];
+            }
+        }
+        return ok;
+    }
+
 } // namespace grbda_oracle

@@ -715,6 +715,19 @@ extern "C"
 
     // Operation counts of one evaluation with the counting scalar (F_alg definition, scalar.h).
     // algo: 0 ID, 1 FD, 2 FK, 3 H. out[10] = {add,mul,div,sqrt,trig}_all, {..}_alg
+    // semi-implicit Euler step (rng.h integrateState); flags[b] = 1 where an implicit cluster could not be projected
+    int oracle_integrate(void *hv, const double *q, const double *yd, const double *ydd, double dt, double *q_out,
+                         double *yd_out, int *flags, int64_t batch, int threads)
+    {
+        Handle *h = (Handle *)hv;
+        const int nq = h->model->getNumPositions(), nv = h->model->getNumDegreesOfFreedom();
+        return runBatch(h, batch, threads, [&](ClusterTreeModel<double> &m, int64_t b)
+                        {
+                            const bool ok = integrateState(m, q + b * nq, yd + b * nv, ydd + b * nv, dt, q_out + b * nq,
+                                                           yd_out + b * nv);
+                            if (flags)
+                                flags[b] = ok ? 0 : 1; });
+    }
     int oracle_count_flops(void *hv, int algo, uint64_t *out)
     {
         Handle *h = (Handle *)hv;

@@ -299,7 +299,14 @@ def test_run_time_compiler_builds_cubins_for_uncompiled_models(grbda, tmp_path):
     urdf = os.path.join(HERE, "urdf_corpus", "four_bar_branch_2_3.urdf")
     m = grbda.ClusterTreeModel.from_urdf(urdf, device=None)
     info = m.kernel_info(grbda.ALGO_FD)
-    assert info["source"] == "jit" and info["program"] == grbda.PROGRAM_FD_LTL and info["parked"] and info["tma"]
+    # forward dynamics program by the measured rule (compile.h chooseForwardDynamicsProgram): the factorisation
+    # when it executes fewer than 0.85 x the operations of the articulated-body sweep
+    ltl_wins = m.dump_program(grbda.PROGRAM_FD_LTL)["flops"] < 0.85 * m.dump_program(grbda.ALGO_FD)["flops"]
+    assert info["source"] == "jit" and info["tma"]
+    assert info["program"] == (grbda.PROGRAM_FD_LTL if ltl_wins else grbda.ALGO_FD) and info["parked"] == ltl_wins
+    tello = grbda.ClusterTreeModel.from_schedule(grbda.ClusterTreeModel.from_robot("tello", device=None).to_schedule(), device=None)
+    chain = grbda.ClusterTreeModel.from_robot("revolute_chain_with_rotor_24", device=None)
+    assert chain.kernel_info(grbda.ALGO_FD)["program"] == grbda.ALGO_FD        # deep chain: O(depth) sweep
     for algo in (grbda.ALGO_ID, grbda.ALGO_FD, grbda.ALGO_FK, grbda.ALGO_H, grbda.ALGO_PHI, grbda.ALGO_GFA, -1):
         src, cubin = str(tmp_path / ("a%d.cu" % algo)), str(tmp_path / ("a%d.cubin" % algo))
         m.jit_compile(algo, False, src, cubin)
@@ -518,6 +525,61 @@ def test_external_force_programs(grbda, oracle, robot, tmp_path):
     tau_eff = run_tape(tapes["gfa"], [q, f_flat, aux])[0]
     ydd_ext = o.dynamics_with_external_forces(q, yd, aux, f_full, forward=True)
     assert rel(o.forward_dynamics(q, yd, tau_eff), ydd_ext) < 1e-9
+
+
+@pytest.mark.parametrize("robot", ["tello_with_arms", "mit_humanoid", "revolute_chain_with_rotor_4"])
+def test_external_forces_on_every_body(grbda, oracle, robot, tmp_path):
+    """UnitTests/testRigidBodyDynamicsAlgos.cpp:201-236 puts a random force on EVERY body (rotors included):
+    setExternalForceBodies(all bodies) specialises the force programs for that set."""
+    m = grbda.ClusterTreeModel.from_robot(robot, device=None)
+    o = oracle.OracleModel(ROBOTS[robot]) if ROBOTS.get(robot) else oracle.OracleModel(robot)
+    default = m.externalForceBodies()
+    m.setExternalForceBodies(list(range(m.nb)))
+    assert m.externalForceBodies() == list(range(m.nb))
+    q, yd, aux = o.generate_states(8, seed=41)
+    rng = np.random.default_rng(6)
+    f = rng.uniform(-20, 20, size=(q.shape[0], m.nb, 6))
+    path = str(tmp_path / "gfs")
+    m.dump_program(grbda.ALGO_GFS, path)
+    tau_plain = o.inverse_dynamics(q, yd, aux)
+    tau_ext = o.dynamics_with_external_forces(q, yd, aux, f, forward=False)
+    assert rel(run_tape(load_tape(path), [q, f.reshape(q.shape[0], -1), tau_plain])[0], tau_ext) < TOL
+    # a subset in caller order, then back to the default
+    subset = [m.nb - 1, 0]
+    m.setExternalForceBodies(subset)
+    f_full = np.zeros_like(f)
+    f_full[:, subset, :] = f[:, :2, :]
+    m.dump_program(grbda.ALGO_GFS, path)
+    tau_sub = o.dynamics_with_external_forces(q, yd, aux, f_full, forward=False)
+    assert rel(run_tape(load_tape(path), [q, f[:, :2, :].reshape(q.shape[0], -1), tau_plain])[0], tau_sub) < TOL
+    m.setExternalForceBodies([])
+    assert m.externalForceBodies() == default
+    with pytest.raises(grbda.GrbdaError):
+        m.setExternalForceBodies([0, 0])
+
+
+def test_oracle_integration_step(oracle):
+    """oracle/grbda_oracle/rng.h integrateState (ori::integrateQuat restated, OrientationTools.h:387-413):
+    unit quaternions stay unit, implicit clusters stay on phi = 0, a constant body twist moves the base origin
+    by dt R v_body, and a full turn about one axis returns the orientation."""
+    o = oracle.OracleModel("tello_with_arms")
+    q, yd, ydd = o.generate_states(64, seed=3)
+    q1, yd1, flags = o.integrate(q, yd, ydd, 1e-3)
+    assert not flags.any() and np.allclose(yd1, yd + 1e-3 * ydd, rtol=0, atol=1e-15)
+    assert np.abs(np.linalg.norm(q1[:, 3:7], axis=1) - 1).max() < 1e-14
+    assert o.validate_states(q1).all()
+    p0, R0, _ = o.forward_kinematics(q, yd1)
+    v_world = np.einsum("bij,bj->bi", R0[:, 0], yd1[:, 3:6])       # R (body -> world) times v_body
+    assert np.abs(q1[:, :3] - (q[:, :3] + 1e-3 * v_world)).max() < 1e-15
+    # pure rotation about the body z axis, one full turn in 1000 steps
+    qa = q[:1].copy()
+    w = np.zeros((1, o.nv))
+    w[0, 2] = 2 * np.pi
+    qb = qa.copy()
+    for _ in range(1000):
+        qb, _, _ = o.integrate(qb, w, np.zeros_like(w), 1e-3)
+    sign = np.sign(np.dot(qa[0, 3:7], qb[0, 3:7]))
+    assert np.abs(sign * qb[0, 3:7] - qa[0, 3:7]).max() < 1e-9 and np.abs(qb[0, :3] - qa[0, :3]).max() < 1e-12
 
 
 @pytest.mark.parametrize("robot", ["jvrc1_humanoid", "mit_humanoid"])

@@ -145,6 +145,63 @@ def test_external_forces(grbda, oracle, torch, robot):
     assert torch.equal(m.forwardDynamics(q, yd, aux, f_ext=zero), m.forwardDynamics(q, yd, aux))
 
 
+@pytest.mark.parametrize("robot", ["tello_with_arms", "mini_cheetah", "revolute_rotor_chain"])
+def test_external_forces_on_every_body(grbda, oracle, torch, robot):
+    """The reference's own external-force test (UnitTests/testRigidBodyDynamicsAlgos.cpp:201-236): a random
+    spatial force on EVERY body, rotors included. The force programs are specialised for the chosen body set
+    at run time (NVRTC) even though the model's other kernels were built ahead of time."""
+    m = grbda.ClusterTreeModel.from_robot(robot)
+    o = oracle_for(oracle, m, robot)
+    m.setExternalForceBodies(list(range(m.nb)))
+    B = 300
+    q, yd, aux, _ = m.generateStates(B, seed=19)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    f = (torch.rand((B, m.nb, 6), dtype=torch.float64, device="cuda", generator=g) - 0.5) * 40.0
+    qn, ydn, auxn, fn = q.cpu().numpy(), yd.cpu().numpy(), aux.cpu().numpy(), f.cpu().numpy()
+    tau = m.inverseDynamics(q, yd, aux, f_ext=f)
+    assert relrows(tau.cpu().numpy(), o.dynamics_with_external_forces(qn, ydn, auxn, fn, forward=False)) < TOL64
+    ydd = m.forwardDynamics(q, yd, aux, f_ext=f)
+    assert relrows(ydd.cpu().numpy(), o.dynamics_with_external_forces(qn, ydn, auxn, fn, forward=True)) < TOL64
+    # back to the default set: the ahead-of-time programs again
+    m.setExternalForceBodies([])
+    bodies = m.externalForceBodies()
+    f_def = f[:, bodies, :].contiguous()
+    f_full = np.zeros_like(fn)
+    f_full[:, bodies, :] = fn[:, bodies, :]
+    tau = m.inverseDynamics(q, yd, aux, f_ext=f_def)
+    assert relrows(tau.cpu().numpy(), o.dynamics_with_external_forces(qn, ydn, auxn, f_full, forward=False)) < TOL64
+
+
+@pytest.mark.parametrize("robot", ["tello_with_arms", "mit_humanoid", "four_bar", "revolute_chain_with_rotor_4"])
+def test_integration_step(grbda, oracle, torch, robot):
+    """grbda_cuda_integrate_f64 / grbda_cuda_step_f64 against the oracle's restatement (ori::integrateQuat,
+    OrientationTools.h:387-413; implicit clusters projected back onto phi = 0), a short trajectory of the whole
+    simulation step, and energy behaviour of the unforced system."""
+    m = grbda.ClusterTreeModel.from_robot(robot)
+    o = oracle_for(oracle, m, robot)
+    B, dt = 500, 1e-3
+    q, yd, aux, _ = m.generateStates(B, seed=29)
+    ydd = m.forwardDynamics(q, yd, aux)
+    q1, yd1, flags = m.integrate(q, yd, ydd, dt)
+    assert int(flags.sum()) == 0
+    qo, ydo, fo = o.integrate(q.cpu().numpy(), yd.cpu().numpy(), ydd.cpu().numpy(), dt)
+    assert not fo.any()
+    assert np.abs(q1.cpu().numpy() - qo).max() < 1e-12 and np.abs(yd1.cpu().numpy() - ydo).max() < 1e-13
+    assert float(m.constraintViolation(q1).max()) < 1e-10
+    # step = forwardDynamics + integrate; ten steps on the device against ten steps of the oracle
+    qs, yds = q.clone(), yd.clone()
+    qn, ydn, taun = q.cpu().numpy(), yd.cpu().numpy(), aux.cpu().numpy()
+    for _ in range(10):
+        qs, yds, fl = m.step(qs, yds, aux, dt)
+        assert int(fl.sum()) == 0
+        qn, ydn, _ = o.integrate(qn, ydn, o.forward_dynamics(qn, ydn, taun), dt)
+    assert np.abs(qs.cpu().numpy() - qn).max() < 1e-8 and relrows(yds.cpu().numpy(), ydn) < 1e-8
+    # in place (q_out = q, yd_out = yd) gives the same result
+    qa, yda = q.clone(), yd.clone()
+    m.integrate(qa, yda, ydd, dt, out=(qa, yda))
+    assert torch.equal(qa, q1) and torch.equal(yda, yd1)
+
+
 @pytest.mark.parametrize("dtype_name", ["float64", "float32"])
 def test_angles_beyond_the_fast_sincos_range(grbda, oracle, torch, dtype_name):
     """Joint angles beyond the range of the branch-free sin/cos reduction (arguments up to 1e12 in FP64, 1e6 in FP32):

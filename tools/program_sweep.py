@@ -32,7 +32,7 @@ def timeit(fn, reps=10):
 
 models = [("robot", r) for r in ("tello_with_arms", "mit_humanoid", "mini_cheetah", "jvrc1_humanoid")]
 models += [("robot", "revolute_chain_with_rotor_%d" % d) for d in (2, 4, 6, 8, 10, 12, 16, 20, 24)]
-models += [("urdf", os.path.join(CORPUS, f)) for f in ("explicit_parallel_chains_depth20_loop_size4.urdf",
+models += [("urdf", os.path.join(CORPUS, f)) for f in ("explicit_parallel_chains_depth20_loop_size6.urdf",
                                                        "explicit_parallel_chains_depth40_loop_size8.urdf")]
 for kind, name in models:
     rec = {"model": os.path.basename(name), "states": 1 << LOG2}
