@@ -30,6 +30,7 @@ _lib = C.CDLL(_LIB_PATH)
 ALGO_ID, ALGO_FD, ALGO_FK, ALGO_H, ALGO_PHI = 0, 1, 2, 3, 4
 ALGO_NAMES = ["id", "fd", "fk", "h", "phi"]
 ALGO_GFA, ALGO_GFS = 5, 6  # tau_in +/- J^T f_ext (external forces on the terminal links)
+ALGO_CONTACT_KIN, ALGO_CONTACT_JAC, ALGO_TEST_FORCE, ALGO_OSIM = 8, 9, 10, 11  # operational space (contact points)
 PROGRAM_FD_LTL = 7  # dump_program only: forward dynamics as CRBA + bias + sparse L^T D L (kernel variant "ltl")
 
 _vp = C.c_void_p
@@ -65,6 +66,13 @@ _lib.grbda_cuda_inverse_dynamics_ext_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _v
 _lib.grbda_cuda_forward_dynamics_ext_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
 _lib.grbda_cuda_external_force_bodies.argtypes = [_vp, _vp, _vp]
 _lib.grbda_cuda_set_external_force_bodies.argtypes = [_vp, _vp, C.c_int32]
+_lib.grbda_cuda_set_contact_points.argtypes = [_vp, C.c_int32, _vp, _vp, _vp]
+_lib.grbda_cuda_num_contact_points.argtypes = [_vp]
+_lib.grbda_cuda_num_end_effectors.argtypes = [_vp]
+_lib.grbda_cuda_contact_kinematics_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp]
+_lib.grbda_cuda_contact_jacobians_f64.argtypes = [_vp, _vp, _vp, _i64, _vp]
+_lib.grbda_cuda_apply_test_force_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp]
+_lib.grbda_cuda_inverse_osim_f64.argtypes = [_vp, _vp, _vp, _i64, _vp]
 _lib.grbda_cuda_integrate_f64.argtypes = [_vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _i64, _vp]
 _lib.grbda_cuda_step_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _i64, _vp]
 _lib.grbda_cuda_dynamics_host_f64.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _i64]
@@ -84,6 +92,9 @@ EXPORTED_SYMBOLS = [
     "grbda_cuda_model_prepare", "grbda_cuda_kernel_info", "grbda_cuda_jit_compile",
     "grbda_cuda_external_force_bodies", "grbda_cuda_inverse_dynamics_ext_f64", "grbda_cuda_forward_dynamics_ext_f64",
     "grbda_cuda_integrate_f64", "grbda_cuda_step_f64", "grbda_cuda_set_external_force_bodies",
+    "grbda_cuda_set_contact_points", "grbda_cuda_num_contact_points", "grbda_cuda_num_end_effectors",
+    "grbda_cuda_contact_kinematics_f64", "grbda_cuda_contact_jacobians_f64", "grbda_cuda_apply_test_force_f64",
+    "grbda_cuda_inverse_osim_f64",
     "grbda_cuda_inverse_dynamics_f64", "grbda_cuda_inverse_dynamics_f32",
     "grbda_cuda_forward_dynamics_f64", "grbda_cuda_forward_dynamics_f32",
     "grbda_cuda_mass_matrix_f64", "grbda_cuda_mass_matrix_f32",
@@ -451,6 +462,61 @@ class ClusterTreeModel:
         fn = getattr(_lib, "grbda_cuda_forward_dynamics_" + self._suffix(q))
         _check(fn(self._h, _ptr(q), _ptr(yd), _ptr(tau), _ptr(out), q.shape[0], _stream()))
         return out
+
+    # ---- operational space (contact points) -----------------------------------------------------
+    def setContactPoints(self, bodies, offsets, end_effector=None):
+        """Contact points: body indices, offsets in the body frames [n, 3], end-effector flags."""
+        n = len(bodies)
+        b = np.ascontiguousarray(bodies, dtype=np.int32)
+        o = np.ascontiguousarray(offsets, dtype=np.float64).reshape(n, 3)
+        e = np.ascontiguousarray(end_effector if end_effector is not None else np.zeros(n), dtype=np.uint8)
+        _check(_lib.grbda_cuda_set_contact_points(self._h, n, b.ctypes.data_as(_vp), o.ctypes.data_as(_vp),
+                                                  e.ctypes.data_as(_vp)))
+
+    @property
+    def ncp(self):
+        return _lib.grbda_cuda_num_contact_points(self._h)
+
+    @property
+    def nee(self):
+        return _lib.grbda_cuda_num_end_effectors(self._h)
+
+    def contactKinematics(self, q, yd):
+        """(p[batch, n_cp, 3], v[batch, n_cp, 3]): world position / linear velocity of the contact points."""
+        import torch
+        q = self._prep(q, self.nq, torch.float64)
+        yd = self._prep(yd, self.nv, torch.float64)
+        p = torch.empty((q.shape[0], self.ncp, 3), dtype=torch.float64, device=q.device)
+        v = torch.empty_like(p)
+        _check(_lib.grbda_cuda_contact_kinematics_f64(self._h, _ptr(q), _ptr(yd), _ptr(p), _ptr(v), q.shape[0], _stream()))
+        return p, v
+
+    def contactJacobians(self, q):
+        """J[batch, n_cp, 6, nv], world frame, rows [angular; linear] (contactJacobianWorldFrame)."""
+        import torch
+        q = self._prep(q, self.nq, torch.float64)
+        J = torch.empty((q.shape[0], self.ncp, 6, self.nv), dtype=torch.float64, device=q.device)
+        _check(_lib.grbda_cuda_contact_jacobians_f64(self._h, _ptr(q), _ptr(J), q.shape[0], _stream()))
+        return J
+
+    def applyTestForce(self, q, force):
+        """force[batch, n_cp, 3] (world) -> (dstate[batch, n_cp, nv], lambda_inv[batch, n_cp])."""
+        import torch
+        q = self._prep(q, self.nq, torch.float64)
+        f = self._prep(force.reshape(q.shape[0], -1), 3 * self.ncp, torch.float64)
+        d = torch.empty((q.shape[0], self.ncp, self.nv), dtype=torch.float64, device=q.device)
+        lam = torch.empty((q.shape[0], self.ncp), dtype=torch.float64, device=q.device)
+        _check(_lib.grbda_cuda_apply_test_force_f64(self._h, _ptr(q), _ptr(f), _ptr(d), _ptr(lam), q.shape[0], _stream()))
+        return d, lam
+
+    def inverseOperationalSpaceInertiaMatrix(self, q):
+        """Lambda^-1 [batch, 6 n_ee, 6 n_ee] over the end-effectors."""
+        import torch
+        q = self._prep(q, self.nq, torch.float64)
+        n = 6 * self.nee
+        L = torch.empty((q.shape[0], n, n), dtype=torch.float64, device=q.device)
+        _check(_lib.grbda_cuda_inverse_osim_f64(self._h, _ptr(q), _ptr(L), q.shape[0], _stream()))
+        return L
 
     def integrate(self, q, yd, ydd, dt, out=None):
         """(q', yd', flags): semi-implicit Euler step, quaternion base by ori::integrateQuat, implicit clusters

@@ -185,6 +185,12 @@ namespace grbda
         public:
             explicit ModelCompiler(const ClusterTreeModel &model) : m_(model) { findAxisymmetricLeaves(); }
 
+            // Inputs of the programs. The operational-space programs (contact Jacobians aside) reuse the dynamics
+            // below with substituted inputs: velocities and gravity set to zero, generalized forces given as
+            // expressions (solveMassMatrix); structural zeros then fold everything velocity-dependent away.
+            Sym inYd(int i) const { return yd_override_ ? (*yd_override_)[i] : Sym::input(IN_YD, i); }
+            Sym inAux(int i) const { return aux_override_ ? (*aux_override_)[i] : Sym::input(IN_AUX, i); }
+
             // A leaf body whose inertia is symmetric about its own joint axis (a motor rotor: centre of
             // mass on the axis, equal transverse moments, no products of inertia) exerts the same force
             // on its parent and the same joint torque at every joint angle: with R the joint rotation,
@@ -301,7 +307,7 @@ namespace grbda
                 for (int i = 0; i < d.num_positions; i++)
                     y[i] = Sym::input(IN_Q, c.position_index_ + i);
                 for (int i = 0; i < n; i++)
-                    yd[i] = with_velocity ? Sym::input(IN_YD, c.velocity_index_ + i) : Sym(0.0);
+                    yd[i] = with_velocity ? inYd(c.velocity_index_ + i) : Sym(0.0);
                 ck.G.assign(N * n, Sym(0.0));
                 ck.g.assign(N, Sym(0.0));
                 if (d.type == ClusterType::Explicit)
@@ -433,7 +439,7 @@ namespace grbda
                         b.Xup = b.Xl;
                         b.anc = -1;
                         for (int i = 0; i < 6; i++)
-                            b.v[i] = with_velocity ? Sym::input(IN_YD, c.velocity_index_ + i) : Sym(0.0);
+                            b.v[i] = with_velocity ? inYd(c.velocity_index_ + i) : Sym(0.0);
                         b.vJ = b.v;
                         if (with_subspace)
                         {
@@ -513,8 +519,9 @@ namespace grbda
             SV minusGravity() const
             {
                 SV a;
-                for (int i = 0; i < 3; i++)
-                    a[3 + i] = Sym(-m_.getGravity()[i]);
+                if (!zero_gravity_)
+                    for (int i = 0; i < 3; i++)
+                        a[3 + i] = Sym(-m_.getGravity()[i]);
                 return a;
             }
 
@@ -607,7 +614,7 @@ namespace grbda
                         {
                             SV fw;
                             for (int k = 0; k < 6; k++)
-                                fw[k] = Sym::input(IN_YD, 6 * slot[i] + k);
+                                fw[k] = Sym::input(IN_YD, 6 * slot[i] + k); // the force array travels in the velocity slot
                             f[i] = Xa[i].applyForce(fw);
                         }
                     }
@@ -657,7 +664,7 @@ namespace grbda
                     const int n = d.num_velocities;
                     std::vector<Sym> ydd(n);
                     for (int k = 0; k < n; k++)
-                        ydd[k] = Sym::input(IN_AUX, c.velocity_index_ + k);
+                        ydd[k] = inAux(c.velocity_index_ + k);
                     const bool is_free = d.type == ClusterType::FreeQuaternion ||
                                          d.type == ClusterType::FreeRollPitchYaw;
                     for (int i = 0; i < d.num_bodies; i++)
@@ -941,7 +948,7 @@ namespace grbda
                             D[k * n + l] = s;
                             D[l * n + k] = s;
                         }
-                        Sym s = Sym::input(IN_AUX, c.velocity_index_ + k);
+                        Sym s = inAux(c.velocity_index_ + k);
                         for (int i = 0; i < N; i++)
                             s = s - dot(bk_[b0 + i].S[k], pA[b0 + i]);
                         A.u[k] = s;
@@ -1367,7 +1374,7 @@ namespace grbda
                         std::vector<Sym> row(anc.size());
                         for (size_t x = 0; x < anc.size(); x++)
                             row[x] = reduced(anc[x]);
-                        const Sym w = Sym::input(IN_AUX, k) - bias[k] - accb[k];
+                        const Sym w = inAux(k) - bias[k] - accb[k];
                         z[k] = w * dinv;
                         for (size_t x = 0; x < anc.size(); x++)
                         {
@@ -1415,6 +1422,169 @@ namespace grbda
                     for (auto &kv : trace)
                         std::fprintf(stderr, "ltl nodes %-14s %ld\n", kv.first.c_str(), kv.second);
                 return ydd_out;
+            }
+
+            // ---------------------------------------------------------------------------------
+            // operational space: contact points, their Jacobians, apply-test-force, inverse OSIM
+            // ---------------------------------------------------------------------------------
+            // H^-1 b: the factorisation program with zero velocities and zero gravity (the bias vanishes
+            // structurally) and b in the place of tau. Called once per right-hand side inside ONE graph scope:
+            // hash-consing makes the kinematics, the mass matrix rows and the factor common to all of them.
+            std::vector<Sym> solveMassMatrix(const std::vector<Sym> &b)
+            {
+                const std::vector<Sym> zeros(m_.getNumDegreesOfFreedom(), Sym(0.0));
+                yd_override_ = &zeros;
+                aux_override_ = &b;
+                zero_gravity_ = true;
+                std::vector<Sym> x = forwardDynamicsLTL();
+                yd_override_ = aux_override_ = nullptr;
+                zero_gravity_ = false;
+                return x;
+            }
+
+            // absolute transform (world -> body) of every body and the kinematics the contact programs need
+            void contactSetup(bool with_velocity, std::vector<Xf> &Xa)
+            {
+                const bool fr = freeze_leaves_;
+                freeze_leaves_ = false; // a contact point may sit on any body: true poses everywhere
+                kinematics(with_velocity, true);
+                freeze_leaves_ = fr;
+                Xa.assign(m_.getNumBodies(), Xf());
+                for (int i = 0; i < m_.getNumBodies(); i++)
+                {
+                    const int p = m_.bodies()[i].parent_index_;
+                    Xa[i] = p >= 0 ? bk_[i].Xl * Xa[p] : bk_[i].Xl;
+                }
+            }
+            // TreeModel::contactPointForwardKinematics (TreeModel.cpp:60-78): world position and world linear
+            // velocity of every contact point
+            void contactKinematics(std::vector<Sym> &p_out, std::vector<Sym> &v_out)
+            {
+                std::vector<Xf> Xa;
+                contactSetup(true, Xa);
+                for (const ContactPoint &cp : m_.contactPoints())
+                {
+                    const Xf &X = Xa[cp.body_index_];
+                    const V3 d = mulT(X.E, constV3(cp.local_offset_)); // offset in world orientation
+                    const V3 pos = X.r + d;
+                    const V3 w = mulT(X.E, bk_[cp.body_index_].v.ang()), vo = mulT(X.E, bk_[cp.body_index_].v.lin());
+                    const V3 vel = vo + cross(w, d);
+                    for (int k = 0; k < 3; k++)
+                    {
+                        p_out.push_back(pos[k]);
+                        v_out.push_back(vel[k]);
+                    }
+                }
+            }
+            // contactJacobianWorldFrame (ClusterTreeDynamics.cpp:10-45): 6 x nv, [angular; linear] rows, world
+            // orientation, at the contact point. Column of dof k of an ancestor cluster: the motion S_k of the
+            // ancestor body (its own coordinates) seen at the contact point.
+            std::vector<std::vector<Sym>> contactJacobianWorld(const ContactPoint &cp, const std::vector<Xf> &Xa) const
+            {
+                const int nv = m_.getNumDegreesOfFreedom();
+                std::vector<std::vector<Sym>> J(6, std::vector<Sym>(nv, Sym(0.0)));
+                const V3 pc = Xa[cp.body_index_].r + mulT(Xa[cp.body_index_].E, constV3(cp.local_offset_));
+                for (int j = cp.body_index_; j >= 0; j = bk_[j].anc)
+                {
+                    const ClusterTreeNode &c = m_.clusters()[m_.getIndexOfClusterContainingBody(j)];
+                    const V3 arm = pc - Xa[j].r;
+                    for (int k = 0; k < c.joint_.num_velocities; k++)
+                    {
+                        const V3 w = mulT(Xa[j].E, bk_[j].S[k].ang()), v = mulT(Xa[j].E, bk_[j].S[k].lin()) + cross(w, arm);
+                        for (int r = 0; r < 3; r++)
+                        {
+                            J[r][c.velocity_index_ + k] = w[r];
+                            J[3 + r][c.velocity_index_ + k] = v[r];
+                        }
+                    }
+                }
+                return J;
+            }
+            // all contact points: [n_cp][6][nv], row-major
+            std::vector<Sym> contactJacobians()
+            {
+                std::vector<Xf> Xa;
+                contactSetup(false, Xa);
+                std::vector<Sym> out;
+                for (const ContactPoint &cp : m_.contactPoints())
+                    for (auto &row : contactJacobianWorld(cp, Xa))
+                        out.insert(out.end(), row.begin(), row.end());
+                return out;
+            }
+            // applyTestForce (ClusterTreeDynamics.cpp:193-234): a world-frame force f on contact point c changes
+            // the accelerations by dstate = H^-1 J_lin^T f; lambda_inv = f^T J_lin H^-1 J_lin^T f. f[3 n_cp] travels
+            // in the velocity slot. out: dstate [n_cp][nv], lambda_inv [n_cp].
+            void applyTestForce(std::vector<Sym> &dstate, std::vector<Sym> &lambda_inv)
+            {
+                const int nv = m_.getNumDegreesOfFreedom();
+                std::vector<std::vector<Sym>> rhs;
+                {
+                    std::vector<Xf> Xa;
+                    contactSetup(false, Xa);
+                    int c = 0;
+                    for (const ContactPoint &cp : m_.contactPoints())
+                    {
+                        const auto J = contactJacobianWorld(cp, Xa);
+                        std::vector<Sym> t(nv, Sym(0.0));
+                        for (int k = 0; k < nv; k++)
+                            for (int r = 0; r < 3; r++)
+                                t[k] = t[k] + J[3 + r][k] * Sym::input(IN_YD, 3 * c + r);
+                        rhs.push_back(t);
+                        c++;
+                    }
+                }
+                for (const auto &t : rhs)
+                {
+                    const std::vector<Sym> x = solveMassMatrix(t);
+                    Sym l(0.0);
+                    for (int k = 0; k < nv; k++)
+                        l = l + t[k] * x[k];
+                    dstate.insert(dstate.end(), x.begin(), x.end());
+                    lambda_inv.push_back(l);
+                }
+            }
+            // inverseOperationalSpaceInertiaMatrix (ClusterTreeDynamics.cpp:292-435, the EFPA): Lambda^-1 =
+            // J H^-1 J^T over the end-effectors, J = their 6 x nv Jacobians in the orientation of their own body
+            // (the reference's X_offset = createSXform(1, local_offset)), [6 n_ee][6 n_ee] row-major.
+            std::vector<Sym> inverseOperationalSpaceInertiaMatrix()
+            {
+                const int nv = m_.getNumDegreesOfFreedom();
+                std::vector<std::vector<Sym>> Jb; // 6 n_ee rows
+                {
+                    std::vector<Xf> Xa;
+                    contactSetup(false, Xa);
+                    for (const ContactPoint &cp : m_.contactPoints())
+                    {
+                        if (!cp.is_end_effector_)
+                            continue;
+                        const auto Jw = contactJacobianWorld(cp, Xa);
+                        const M3 &E = Xa[cp.body_index_].E;
+                        for (int half = 0; half < 2; half++)
+                            for (int r = 0; r < 3; r++)
+                            {
+                                std::vector<Sym> row(nv, Sym(0.0));
+                                for (int k = 0; k < nv; k++)
+                                    for (int cidx = 0; cidx < 3; cidx++)
+                                        row[k] = row[k] + E(r, cidx) * Jw[3 * half + cidx][k];
+                                Jb.push_back(row);
+                            }
+                    }
+                }
+                const int m = (int)Jb.size();
+                std::vector<std::vector<Sym>> X(m); // H^-1 J^T, column by column
+                for (int i = 0; i < m; i++)
+                    X[i] = solveMassMatrix(Jb[i]);
+                std::vector<Sym> out(m * m, Sym(0.0));
+                for (int i = 0; i < m; i++)
+                    for (int j = 0; j <= i; j++)
+                    {
+                        Sym s(0.0);
+                        for (int k = 0; k < nv; k++)
+                            s = s + Jb[i][k] * X[j][k];
+                        out[i * m + j] = s;
+                        out[j * m + i] = s;
+                    }
+                return out;
             }
 
             const std::vector<BodyKin> &bodyKinematics() const { return bk_; }
@@ -1499,6 +1669,8 @@ namespace grbda
             }
 
             const ClusterTreeModel &m_;
+            const std::vector<Sym> *yd_override_ = nullptr, *aux_override_ = nullptr;
+            bool zero_gravity_ = false;
             bool freeze_leaves_ = true, gyrostats_ = true;
             std::vector<char> axisym_leaf_;
             std::vector<BodyKin> bk_;

@@ -24,13 +24,19 @@ namespace grbda
             ALGO_COUNT = 7,   // entry points / registry slots
             // alternative programs of an entry point (selected per kernel variant, same I/O as the entry)
             PROGRAM_FD_LTL = 7, // forward dynamics as H^-1 (tau - C): CRBA + RNEA bias + sparse L^T D L
-            PROGRAM_COUNT = 8
+            // operational space (model.contactPoints()); always compiled at run time for the contact set
+            ALGO_CONTACT_KIN = 8,  // in: q, yd          out: p_c[3 n_cp], v_c[3 n_cp] (world)
+            ALGO_CONTACT_JAC = 9,  // in: q              out: J[n_cp][6][nv] (world frame, [angular; linear])
+            ALGO_TEST_FORCE = 10,  // in: q, f[3 n_cp]   out: dstate[n_cp][nv], lambda_inv[n_cp]
+            ALGO_OSIM = 11,        // in: q              out: Lambda^-1 [6 n_ee][6 n_ee]
+            PROGRAM_COUNT = 12
         };
         // registry slot a program belongs to
         inline int algoOfProgram(int program) { return program == PROGRAM_FD_LTL ? ALGO_FD : program; }
         inline const char *algoName(int a)
         {
-            static const char *names[] = {"id", "fd", "fk", "h", "phi", "gfa", "gfs", "fd_ltl"};
+            static const char *names[] = {"id", "fd", "fk", "h", "phi", "gfa", "gfs", "fd_ltl", "contact_kin", "contact_jac",
+                                          "test_force", "osim"};
             return names[a];
         }
 
@@ -78,6 +84,19 @@ namespace grbda
                         n_out[0] += c.joint_.num_constraints;
                         n_out[1] += c.joint_.num_constraints * (c.joint_.num_bodies - c.joint_.num_velocities);
                     }
+                break;
+            case ALGO_CONTACT_KIN:
+                n_in[1] = nv, n_out[0] = n_out[1] = 3 * (int)model.contactPoints().size();
+                break;
+            case ALGO_CONTACT_JAC:
+                n_out[0] = 6 * nv * (int)model.contactPoints().size();
+                break;
+            case ALGO_TEST_FORCE:
+                n_in[1] = 3 * (int)model.contactPoints().size();
+                n_out[0] = nv * (int)model.contactPoints().size(), n_out[1] = (int)model.contactPoints().size();
+                break;
+            case ALGO_OSIM:
+                n_out[0] = 36 * model.getNumEndEffectors() * model.getNumEndEffectors();
                 break;
             default:
                 throw std::runtime_error("algoSizes: unknown program");
@@ -147,6 +166,30 @@ namespace grbda
                 p.outputs = {phi_all, Kd_all};
                 break;
             }
+            case ALGO_CONTACT_KIN:
+            {
+                p.n_in[0] = nq, p.n_in[1] = nv;
+                std::vector<sym::Sym> pos, vel;
+                mc.contactKinematics(pos, vel);
+                p.outputs = {pos, vel};
+                break;
+            }
+            case ALGO_CONTACT_JAC:
+                p.n_in[0] = nq;
+                p.outputs.push_back(mc.contactJacobians());
+                break;
+            case ALGO_TEST_FORCE:
+            {
+                p.n_in[0] = nq, p.n_in[1] = 3 * (int)model.contactPoints().size();
+                std::vector<sym::Sym> dstate, lambda_inv;
+                mc.applyTestForce(dstate, lambda_inv);
+                p.outputs = {dstate, lambda_inv};
+                break;
+            }
+            case ALGO_OSIM:
+                p.n_in[0] = nq;
+                p.outputs.push_back(mc.inverseOperationalSpaceInertiaMatrix());
+                break;
             default:
                 throw std::runtime_error("compileAlgo: unknown algorithm");
             }

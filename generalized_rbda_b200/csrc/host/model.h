@@ -364,6 +364,16 @@ namespace grbda
         };
     } // namespace ClusterJoints
 
+    // reference: include/grbda/Dynamics/StateRepresentation.h (ContactPoint: body, offset in the body frame,
+    // end-effector flag); appended with TreeModel::appendContactPoint / appendEndEffector
+    struct ContactPoint
+    {
+        int body_index_ = -1;
+        Vec3 local_offset_ = {0., 0., 0.};
+        std::string name_;
+        bool is_end_effector_ = false;
+    };
+
     // reference: Nodes/TreeNode.h:16-75 (topology part only)
     struct ClusterTreeNode
     {
@@ -528,6 +538,40 @@ namespace grbda
         }
         const Vec3 &getGravity() const { return gravity_; }
 
+        // reference: ClusterTreeModel::appendContactPoint / appendEndEffector (src/Dynamics/ClusterTreeModel.cpp:129-190)
+        void appendContactPoint(const std::string &body_name, const Vec3 &local_offset, const std::string &cp_name,
+                                bool is_end_effector = false)
+        {
+            auto it = body_name_to_body_index_.find(body_name);
+            if (it == body_name_to_body_index_.end() || it->second < 0)
+                throw std::runtime_error("appendContactPoint: unknown body '" + body_name + "'");
+            for (const ContactPoint &c : contact_points_)
+                if (c.name_ == cp_name)
+                    throw std::runtime_error("appendContactPoint: contact point '" + cp_name + "' exists already");
+            contact_points_.push_back(ContactPoint{it->second, local_offset, cp_name, is_end_effector});
+            device_model_.reset();
+        }
+        void appendEndEffector(const std::string &body_name, const Vec3 &local_offset, const std::string &cp_name)
+        {
+            appendContactPoint(body_name, local_offset, cp_name, true);
+        }
+        void setContactPoints(const std::vector<ContactPoint> &points)
+        {
+            for (const ContactPoint &c : points)
+                if (c.body_index_ < 0 || c.body_index_ >= (int)bodies_.size())
+                    throw std::runtime_error("setContactPoints: body index out of range");
+            contact_points_ = points;
+            device_model_.reset();
+        }
+        const std::vector<ContactPoint> &contactPoints() const { return contact_points_; }
+        int getNumEndEffectors() const
+        {
+            int n = 0;
+            for (const ContactPoint &c : contact_points_)
+                n += c.is_end_effector_;
+            return n;
+        }
+
         // Bodies that take external forces in the batched *_ext entry points (TreeModel::setExternalForces,
         // TreeModel.cpp:215-239, names any set of bodies per call; the batched path fixes the set per model so
         // that the force programs can be specialised). Empty: the default set, every terminal link.
@@ -583,6 +627,7 @@ namespace grbda
         int position_index_ = 0, velocity_index_ = 0, motion_subspace_index_ = 0;
         Vec3 gravity_ = {0., 0., -9.81};
         std::vector<int> external_force_bodies_;
+        std::vector<ContactPoint> contact_points_;
         mutable std::shared_ptr<void> device_model_; // grbda_model handle + deleter; copies of the model share it
     };
 

@@ -36,7 +36,8 @@ struct grbda_model
     std::unique_ptr<grbda_runtime::JitModel> jit;  // kernels compiled at run time (runtime/jit.h)
     // external-force programs for a caller-chosen body set (grbda_cuda_set_external_force_bodies): always
     // compiled at run time, also for models whose other kernels were built ahead of time
-    std::unique_ptr<grbda_runtime::JitModel> jit_ext;
+    mutable std::unique_ptr<grbda_runtime::JitModel> jit_ext;
+    mutable std::mutex jit_ext_mutex;
     bool hasKernels() const { return kernels || jit; }
     // host-buffer pipeline (grbda_cuda_dynamics_host_f64)
     std::mutex host_mutex;
@@ -201,6 +202,7 @@ namespace
         compiler::algoSizes(m->model, algo, n_in, n_out);
         return n_out[0] > 0;
     }
+    bool validEntry(int algo) { return algo >= 0 && algo < compiler::PROGRAM_COUNT && algo != compiler::PROGRAM_FD_LTL; }
 
     grbda_status launchAlgo(const grbda_model *m, int algo, bool f32, const void *in0, const void *in1,
                             const void *in2, void *out0, void *out1, void *out2, int64_t batch, void *stream)
@@ -217,7 +219,18 @@ namespace
         int n_in[3], n_out[3];
         grbda_runtime::LaunchFn fn = nullptr;
         const grbda_runtime::JitKernel *jk = nullptr;
-        const bool custom_forces = m->jit_ext && (algo == compiler::ALGO_GFA || algo == compiler::ALGO_GFS);
+        // programs that depend on caller-chosen sets (force bodies, contact points) are always run-time compiled
+        const bool runtime_only = algo >= compiler::ALGO_CONTACT_KIN;
+        if (runtime_only)
+        {
+            if (grbda_runtime::jitMode() == 0)
+                return fail(GRBDA_ERR_NOT_COMPILED, "operational-space programs need run-time compilation (GRBDA_JIT=0)");
+            std::lock_guard<std::mutex> lock(m->jit_ext_mutex);
+            if (!m->jit_ext)
+                m->jit_ext.reset(new grbda_runtime::JitModel());
+        }
+        const bool custom_forces = runtime_only || (m->jit_ext && !m->model.externalForceBodies().empty() &&
+                                                    (algo == compiler::ALGO_GFA || algo == compiler::ALGO_GFS));
         if (m->kernels && !custom_forces)
         {
             const grbda_runtime::AlgoKernels &ak = m->kernels->algo[algo];
@@ -751,10 +764,12 @@ extern "C"
     // ---- kernel provenance / run-time compilation ------------------------------------------------------
     grbda_status grbda_cuda_model_prepare(const grbda_model *m, int algo, int f32)
     {
-        if (!m || algo < 0 || algo >= compiler::ALGO_COUNT)
+        if (!m || !validEntry(algo))
             return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
         if (m->device < 0 || !m->hasKernels())
             return fail(GRBDA_ERR_NO_DEVICE, "model was created without a CUDA device (host-only handle)");
+        if (algo >= compiler::ALGO_CONTACT_KIN)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "operational-space programs are compiled when first used");
         if (m->kernels)
             return (f32 ? m->kernels->algo[algo].f32[0] : m->kernels->algo[algo].f64[0])
                        ? GRBDA_OK
@@ -767,10 +782,10 @@ extern "C"
 
     grbda_status grbda_cuda_kernel_info(const grbda_model *m, int algo, int f32, int64_t *info8)
     {
-        if (!m || !info8 || algo < 0 || algo >= compiler::ALGO_COUNT)
+        if (!m || !info8 || !validEntry(algo))
             return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
         std::memset(info8, 0, 8 * sizeof(int64_t));
-        if (m->kernels)
+        if (m->kernels && algo < compiler::ALGO_COUNT)
         {
             info8[0] = 0;
             info8[7] = (f32 ? m->kernels->algo[algo].f32[0] : m->kernels->algo[algo].f64[0]) ? 1 : 0;
@@ -783,6 +798,8 @@ extern "C"
             std::string err;
             if (m->jit && m->jit->algo[algo][f32 ? 1 : 0].ready)
                 k = &m->jit->algo[algo][f32 ? 1 : 0];
+            else if (m->jit_ext && m->jit_ext->algo[algo][f32 ? 1 : 0].ready)
+                k = &m->jit_ext->algo[algo][f32 ? 1 : 0];
             else if (!grbda_runtime::jitDescribe(m->model, algo, f32 != 0, local, err))
                 return fail(GRBDA_ERR_NOT_COMPILED, err);
             info8[0] = 1;
@@ -800,7 +817,7 @@ extern "C"
     grbda_status grbda_cuda_jit_compile(const grbda_model *m, int algo, int f32, const char *source_path,
                                         const char *cubin_path)
     {
-        if (!m || algo < -1 || algo >= compiler::ALGO_COUNT)
+        if (!m || (algo != -1 && !validEntry(algo)))
             return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
         return guarded([&]
                        {
@@ -829,6 +846,67 @@ extern "C"
                 f.write(cubin.data(), (std::streamsize)cubin.size());
             }
             return (grbda_status)GRBDA_OK; });
+    }
+
+    // ---- operational space ---------------------------------------------------------------------
+    grbda_status grbda_cuda_set_contact_points(grbda_model *m, int32_t count, const int32_t *body_indices,
+                                               const double *local_offsets, const uint8_t *is_end_effector)
+    {
+        if (!m || count < 0 || (count > 0 && (!body_indices || !local_offsets)))
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "bad arguments");
+        return guarded([&]
+                       {
+            if (m->device >= 0)
+            {
+                DeviceScope scope(m->device);
+                cudaDeviceSynchronize();
+            }
+            std::vector<ContactPoint> pts;
+            for (int i = 0; i < count; i++)
+                pts.push_back(ContactPoint{body_indices[i], {local_offsets[3 * i], local_offsets[3 * i + 1], local_offsets[3 * i + 2]},
+                                           "contact-" + std::to_string(i), is_end_effector && is_end_effector[i] != 0});
+            m->model.setContactPoints(pts);
+            std::lock_guard<std::mutex> lock(m->jit_ext_mutex);
+            if (m->jit_ext)
+                for (int a = compiler::ALGO_CONTACT_KIN; a < compiler::PROGRAM_COUNT; a++)
+                    for (int p = 0; p < 2; p++)
+                    {
+                        if (m->jit_ext->algo[a][p].library)
+                            cudaLibraryUnload(m->jit_ext->algo[a][p].library);
+                        m->jit_ext->algo[a][p] = grbda_runtime::JitKernel();
+                    }
+            return (grbda_status)GRBDA_OK; });
+    }
+    int grbda_cuda_num_contact_points(const grbda_model *m) { return m ? (int)m->model.contactPoints().size() : -1; }
+    int grbda_cuda_num_end_effectors(const grbda_model *m) { return m ? m->model.getNumEndEffectors() : -1; }
+
+    grbda_status grbda_cuda_contact_kinematics_f64(const grbda_model *m, const double *q, const double *yd, double *p,
+                                                   double *v, int64_t batch, void *stream)
+    {
+        if (m && m->model.contactPoints().empty())
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "the model has no contact points (grbda_cuda_set_contact_points)");
+        return launchAlgo(m, compiler::ALGO_CONTACT_KIN, false, q, yd, nullptr, p, v, nullptr, batch, stream);
+    }
+    grbda_status grbda_cuda_contact_jacobians_f64(const grbda_model *m, const double *q, double *J, int64_t batch,
+                                                  void *stream)
+    {
+        if (m && m->model.contactPoints().empty())
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "the model has no contact points (grbda_cuda_set_contact_points)");
+        return launchAlgo(m, compiler::ALGO_CONTACT_JAC, false, q, nullptr, nullptr, J, nullptr, nullptr, batch, stream);
+    }
+    grbda_status grbda_cuda_apply_test_force_f64(const grbda_model *m, const double *q, const double *force,
+                                                 double *dstate, double *lambda_inv, int64_t batch, void *stream)
+    {
+        if (m && m->model.contactPoints().empty())
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "the model has no contact points (grbda_cuda_set_contact_points)");
+        return launchAlgo(m, compiler::ALGO_TEST_FORCE, false, q, force, nullptr, dstate, lambda_inv, nullptr, batch, stream);
+    }
+    grbda_status grbda_cuda_inverse_osim_f64(const grbda_model *m, const double *q, double *lambda_inv, int64_t batch,
+                                             void *stream)
+    {
+        if (m && m->model.getNumEndEffectors() == 0)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "the model has no end-effectors (grbda_cuda_set_contact_points)");
+        return launchAlgo(m, compiler::ALGO_OSIM, false, q, nullptr, nullptr, lambda_inv, nullptr, nullptr, batch, stream);
     }
 
     // ---- integration step / simulation step ---------------------------------------------------

@@ -44,7 +44,7 @@ namespace grbda_runtime
     struct JitModel
     {
         std::mutex mutex;
-        JitKernel algo[grbda::compiler::ALGO_COUNT][2]; // [entry point][0 f64, 1 f32]
+        JitKernel algo[grbda::compiler::PROGRAM_COUNT][2]; // [entry point][0 f64, 1 f32] (slot 7 unused)
         JitKernel generate;
     };
 

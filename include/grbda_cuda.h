@@ -209,6 +209,34 @@ grbda_status grbda_cuda_inverse_dynamics_ext_f64(const grbda_model *m, const dou
 grbda_status grbda_cuda_forward_dynamics_ext_f64(const grbda_model *m, const double *q, const double *yd,
                                                  const double *tau, const double *f_ext, double *ydd,
                                                  int64_t batch, void *stream);
+/* ---- operational space: contact points, Jacobians, apply-test-force, inverse OSIM ------------------ */
+/* Contact points of the model (TreeModel::appendContactPoint / appendEndEffector,
+ * src/Dynamics/ClusterTreeModel.cpp:129-190): body index, offset in the body frame, end-effector flag
+ * (NULL: none is). Replaces any earlier set; the programs below are specialised for it and compiled at
+ * run time when first used. Like grbda_cuda_set_external_force_bodies it mutates the handle. */
+grbda_status grbda_cuda_set_contact_points(grbda_model *m, int32_t count, const int32_t *body_indices,
+                                           const double *local_offsets, const uint8_t *is_end_effector);
+int grbda_cuda_num_contact_points(const grbda_model *m);
+int grbda_cuda_num_end_effectors(const grbda_model *m);
+/* p[batch][n_cp][3] world position, v[batch][n_cp][3] world linear velocity of every contact point.
+ * Replaces setState + contactPointForwardKinematics, src/Dynamics/TreeModel.cpp:60-78. */
+grbda_status grbda_cuda_contact_kinematics_f64(const grbda_model *m, const double *q, const double *yd, double *p,
+                                               double *v, int64_t batch, void *stream);
+/* J[batch][n_cp][6][nv]: world-frame contact Jacobians, rows [angular; linear]. Replaces
+ * contactJacobianWorldFrame, src/Dynamics/ClusterTreeDynamics.cpp:10-45. */
+grbda_status grbda_cuda_contact_jacobians_f64(const grbda_model *m, const double *q, double *J, int64_t batch,
+                                              void *stream);
+/* For a world-frame force[batch][n_cp][3] on each contact point (one at a time): dstate[batch][n_cp][nv]
+ * = H^-1 J_lin^T f and lambda_inv[batch][n_cp] = f^T J_lin H^-1 J_lin^T f. Replaces applyTestForce,
+ * src/Dynamics/ClusterTreeDynamics.cpp:193-290. */
+grbda_status grbda_cuda_apply_test_force_f64(const grbda_model *m, const double *q, const double *force,
+                                             double *dstate, double *lambda_inv, int64_t batch, void *stream);
+/* lambda_inv[batch][6 n_ee][6 n_ee] = J H^-1 J^T over the end-effectors (6-row Jacobians in the
+ * orientation of their body, at the contact point). Replaces inverseOperationalSpaceInertiaMatrix
+ * (the extended force propagator algorithm), src/Dynamics/ClusterTreeDynamics.cpp:292-435. */
+grbda_status grbda_cuda_inverse_osim_f64(const grbda_model *m, const double *q, double *lambda_inv, int64_t batch,
+                                         void *stream);
+
 /* Integration step (semi-implicit Euler): yd_out = yd + dt ydd, q_out = q advanced with yd_out -
  * revolute coordinates q + dt yd; free base p + dt R v_body and ori::integrateQuat(quat, R omega_body,
  * dt) (include/grbda/Utils/OrientationTools.h:387-413); clusters with an implicit loop constraint

@@ -143,6 +143,37 @@ class OracleModel:
                                             C.c_int64(q.shape[0]), threads))
         return valid.astype(bool)
 
+    # ---- operational space (contact points) ---------------------------------------------------------
+    def set_contact_points(self, bodies, offsets, end_effector=None):
+        n = len(bodies)
+        b = (C.c_int * max(1, n))(*[int(x) for x in bodies])
+        o = np.ascontiguousarray(offsets, dtype=np.float64).reshape(n, 3)
+        e = (C.c_int * max(1, n))(*[int(x) for x in (end_effector if end_effector is not None else [0] * n)])
+        _check(lib().oracle_set_contact_points(self._h, n, b, _P(o), e))
+        self.ncp, self.nee = n, int(sum(e[:n]))
+
+    def contact_kinematics(self, q, yd, threads=0):
+        p, v = np.zeros((q.shape[0], self.ncp, 3)), np.zeros((q.shape[0], self.ncp, 3))
+        _check(lib().oracle_contact_kinematics(self._h, _P(q), _P(yd), _P(p), _P(v), C.c_int64(q.shape[0]), threads))
+        return p, v
+
+    def contact_jacobians(self, q, world=True, threads=0):
+        J = np.zeros((q.shape[0], self.ncp, 6, self.nv))
+        _check(lib().oracle_contact_jacobians(self._h, _P(q), _P(J), int(world), C.c_int64(q.shape[0]), threads))
+        return J
+
+    def apply_test_force(self, q, force, threads=0):
+        d, lam = np.zeros((q.shape[0], self.ncp, self.nv)), np.zeros((q.shape[0], self.ncp))
+        f = np.ascontiguousarray(force, dtype=np.float64)
+        _check(lib().oracle_apply_test_force(self._h, _P(q), _P(f), _P(d), _P(lam), C.c_int64(q.shape[0]), threads))
+        return d, lam
+
+    def inverse_osim(self, q, threads=0):
+        n = 6 * self.nee
+        L = np.zeros((q.shape[0], n, n))
+        _check(lib().oracle_inverse_osim(self._h, _P(q), _P(L), C.c_int64(q.shape[0]), threads))
+        return L
+
     def integrate(self, q, yd, ydd, dt, threads=0):
         """(q', yd', flags) of the semi-implicit Euler step (oracle/grbda_oracle/rng.h integrateState)."""
         qo, ydo = np.zeros_like(q), np.zeros_like(yd)

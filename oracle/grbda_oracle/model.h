@@ -30,9 +30,19 @@ namespace grbda_oracle
         Mat<T> IA, pA, U, D, u, D_inv_UT, D_inv_u, Ia;
     };
 
+    // reference: include/grbda/Dynamics/StateRepresentation.h (ContactPoint)
+    template <typename T>
+    struct ContactPoint
+    {
+        int body_index;
+        Mat<T> local_offset; // 3 x 1, body frame
+        bool is_end_effector;
+    };
+
     template <typename T>
     struct ClusterTreeModel
     {
+        std::vector<ContactPoint<T>> contact_points;
         std::vector<Body<T>> bodies;
         std::vector<Body<T>> bodies_in_current_cluster;
         std::vector<std::shared_ptr<ClusterTreeNode<T>>> nodes;
@@ -350,6 +360,110 @@ namespace grbda_oracle
                 }
             }
             return H;
+        }
+
+        ////////////////////////////////////////////////////////////////////////////////////////
+        // Operational space: contact points (ClusterTreeModel.cpp:129-190 appendContactPoint / appendEndEffector)
+        ////////////////////////////////////////////////////////////////////////////////////////
+        void appendContactPoint(int body_index, const Mat<T> &local_offset, bool is_end_effector)
+        {
+            contact_points.push_back(ContactPoint<T>{body_index, local_offset, is_end_effector});
+        }
+        int getNumEndEffectors() const
+        {
+            int n = 0;
+            for (auto &c : contact_points)
+                n += c.is_end_effector;
+            return n;
+        }
+        // reference: Spatial.h:238-250 (createSXform)
+        static Mat<T> createSXform(const Mat<T> &R, const Mat<T> &r)
+        {
+            Mat<T> X(6, 6), rhat(3, 3);
+            rhat(0, 1) = -r[2], rhat(0, 2) = r[1], rhat(1, 0) = r[2], rhat(1, 2) = -r[0], rhat(2, 0) = -r[1], rhat(2, 1) = r[0];
+            X.setBlock(0, 0, R);
+            X.setBlock(3, 3, R);
+            X.setBlock(3, 0, -(R * rhat));
+            return X;
+        }
+        // TreeModel::contactPointForwardKinematics, TreeModel.cpp:60-78 (forwardKinematics() done by the caller)
+        void contactPointKinematics(int cp_index, T *pos, T *vel)
+        {
+            const ContactPoint<T> &cp = contact_points[cp_index];
+            const Body<T> &b = bodies[cp.body_index];
+            auto &node = nodes[clusterContainingBody(cp.body_index)];
+            const Transform<T> &Xa = node->Xa[b.sub_index_within_cluster];
+            const Mat<T> v_body = node->v.segment(6 * b.sub_index_within_cluster, 6);
+            const Mat<T> position = Xa.inverseTransformPoint(cp.local_offset);
+            const Mat<T> vw = Xa.inverseTransformMotionVector(v_body);
+            // spatialToLinearVelocity(v, x) = v_lin + w x x   (Spatial.h:296-307)
+            const Mat<T> w = vw.segment(0, 3), vl = vw.segment(3, 3);
+            const T lin[3] = {vl[0] + w[1] * position[2] - w[2] * position[1], vl[1] + w[2] * position[0] - w[0] * position[2],
+                              vl[2] + w[0] * position[1] - w[1] * position[0]};
+            for (int i = 0; i < 3; i++)
+            {
+                pos[i] = position[i];
+                vel[i] = lin[i];
+            }
+        }
+        // contactJacobianWorldFrame, ClusterTreeDynamics.cpp:10-45 (world = true) and contactJacobianBodyFrame,
+        // :47-77 (world = false): 6 x nv
+        Mat<T> contactJacobian(int cp_index, bool world)
+        {
+            const ContactPoint<T> &cp = contact_points[cp_index];
+            Mat<T> J(6, getNumDegreesOfFreedom());
+            const Body<T> &body_i = bodies[cp.body_index];
+            auto &cluster_i = nodes[clusterContainingBody(cp.body_index)];
+            Mat<T> R(3, 3);
+            for (int k = 0; k < 3; k++)
+                R(k, k) = T(1.0);
+            if (world)
+                R = cluster_i->Xa[body_i.sub_index_within_cluster].E.transpose(); // R_link_to_world
+            Mat<T> Xout = createSXform(R, cp.local_offset);
+            int j = cp.body_index;
+            while (j > -1)
+            {
+                const Body<T> &body_j = bodies[j];
+                auto &cluster_j = nodes[clusterContainingBody(j)];
+                const int sub = body_j.sub_index_within_cluster;
+                const Mat<T> S = cluster_j->joint->S.block(6 * sub, 0, 6, cluster_j->num_velocities);
+                J.setBlock(0, cluster_j->velocity_index, Xout * S);
+                Xout = Xout * cluster_j->Xup.X[sub].toMatrix();
+                j = body_j.cluster_ancestor_index;
+            }
+            return J;
+        }
+        // What the reference's own tests hold applyTestForce and the EFPA to
+        // (UnitTests/testRigidBodyDynamicsAlgos.cpp:241-335): with H = getMassMatrix(),
+        //   dstate = H^-1 J_lin^T f,  lambda_inv = f^T J_lin H^-1 J_lin^T f        (world-frame J, linear rows)
+        //   Lambda^-1 = J H^-1 J^T over the end-effectors                          (body-frame 6-row J)
+        void applyTestForceReference(int cp_index, const T *force, T *dstate, T *lambda_inv)
+        {
+            const int nv = getNumDegreesOfFreedom();
+            const Mat<T> H = getMassMatrix();
+            const Mat<T> J = contactJacobian(cp_index, true);
+            Mat<T> rhs(nv, 1);
+            for (int k = 0; k < nv; k++)
+                rhs[k] = J(3, k) * force[0] + J(4, k) * force[1] + J(5, k) * force[2];
+            const Mat<T> x = solve(H, rhs);
+            T l = T(0.0);
+            for (int k = 0; k < nv; k++)
+            {
+                dstate[k] = x[k];
+                l = l + rhs[k] * x[k];
+            }
+            *lambda_inv = l;
+        }
+        Mat<T> inverseOperationalSpaceInertiaMatrixReference()
+        {
+            const int nv = getNumDegreesOfFreedom(), ne = getNumEndEffectors();
+            const Mat<T> H = getMassMatrix();
+            Mat<T> J(6 * ne, nv);
+            int k = 0;
+            for (size_t i = 0; i < contact_points.size(); i++)
+                if (contact_points[i].is_end_effector)
+                    J.setBlock(6 * k++, 0, contactJacobian((int)i, false));
+            return J * solve(H, J.transpose());
         }
 
         ////////////////////////////////////////////////////////////////////////////////////////

@@ -325,8 +325,11 @@ namespace
     void ensureWorkers(Handle *h, int n)
     {
         while ((int)h->workers.size() < n)
+        {
             h->workers.push_back(
                 std::make_unique<ClusterTreeModel<double>>(h->spec.instantiate<double>()));
+            h->workers.back()->contact_points = h->model->contact_points;
+        }
     }
 
     int resolveThreads(int threads)
@@ -715,6 +718,79 @@ extern "C"
 
     // Operation counts of one evaluation with the counting scalar (F_alg definition, scalar.h).
     // algo: 0 ID, 1 FD, 2 FK, 3 H. out[10] = {add,mul,div,sqrt,trig}_all, {..}_alg
+    // ---- operational space -----------------------------------------------------------------------------------
+    int oracle_set_contact_points(void *hv, int count, const int *bodies, const double *offsets, const int *is_ee)
+    {
+        Handle *h = (Handle *)hv;
+        return guarded([&]
+                       {
+            auto apply = [&](ClusterTreeModel<double> &m) {
+                m.contact_points.clear();
+                for (int i = 0; i < count; i++)
+                    m.appendContactPoint(bodies[i], toVec(offsets + 3 * i, 3), is_ee && is_ee[i]);
+            };
+            apply(*h->model);
+            for (auto &w : h->workers)
+                apply(*w);
+        });
+    }
+    // p, v: [batch][n_cp][3]
+    int oracle_contact_kinematics(void *hv, const double *q, const double *yd, double *p, double *v, int64_t batch, int threads)
+    {
+        Handle *h = (Handle *)hv;
+        const int nq = h->model->getNumPositions(), nv = h->model->getNumDegreesOfFreedom();
+        const int nc = (int)h->model->contact_points.size();
+        return runBatch(h, batch, threads, [&](ClusterTreeModel<double> &m, int64_t b)
+                        {
+                            m.setState(toVec(q + b * nq, nq), toVec(yd + b * nv, nv));
+                            m.forwardKinematics();
+                            for (int c = 0; c < nc; c++)
+                                m.contactPointKinematics(c, p + (b * nc + c) * 3, v + (b * nc + c) * 3); });
+    }
+    // J: [batch][n_cp][6][nv]; world != 0: contactJacobianWorldFrame, else contactJacobianBodyFrame
+    int oracle_contact_jacobians(void *hv, const double *q, double *J, int world, int64_t batch, int threads)
+    {
+        Handle *h = (Handle *)hv;
+        const int nq = h->model->getNumPositions(), nv = h->model->getNumDegreesOfFreedom();
+        const int nc = (int)h->model->contact_points.size();
+        return runBatch(h, batch, threads, [&](ClusterTreeModel<double> &m, int64_t b)
+                        {
+                            m.setState(toVec(q + b * nq, nq), Mat<double>(nv, 1));
+                            m.forwardKinematics();
+                            for (int c = 0; c < nc; c++)
+                            {
+                                const Mat<double> Jc = m.contactJacobian(c, world != 0);
+                                for (int i = 0; i < 6 * nv; i++)
+                                    J[((b * nc + c) * 6) * nv + i] = Jc.a[i];
+                            } });
+    }
+    // force: [batch][n_cp][3] -> dstate [batch][n_cp][nv], lambda_inv [batch][n_cp]
+    int oracle_apply_test_force(void *hv, const double *q, const double *force, double *dstate, double *lambda_inv,
+                                int64_t batch, int threads)
+    {
+        Handle *h = (Handle *)hv;
+        const int nq = h->model->getNumPositions(), nv = h->model->getNumDegreesOfFreedom();
+        const int nc = (int)h->model->contact_points.size();
+        return runBatch(h, batch, threads, [&](ClusterTreeModel<double> &m, int64_t b)
+                        {
+                            m.setState(toVec(q + b * nq, nq), Mat<double>(nv, 1));
+                            for (int c = 0; c < nc; c++)
+                                m.applyTestForceReference(c, force + (b * nc + c) * 3, dstate + (b * nc + c) * nv,
+                                                          lambda_inv + b * nc + c); });
+    }
+    // Lambda^-1: [batch][6 n_ee][6 n_ee]
+    int oracle_inverse_osim(void *hv, const double *q, double *L, int64_t batch, int threads)
+    {
+        Handle *h = (Handle *)hv;
+        const int nq = h->model->getNumPositions(), nv = h->model->getNumDegreesOfFreedom();
+        const int n = 6 * h->model->getNumEndEffectors();
+        return runBatch(h, batch, threads, [&](ClusterTreeModel<double> &m, int64_t b)
+                        {
+                            m.setState(toVec(q + b * nq, nq), Mat<double>(nv, 1));
+                            const Mat<double> Li = m.inverseOperationalSpaceInertiaMatrixReference();
+                            for (int i = 0; i < n * n; i++)
+                                L[b * n * n + i] = Li.a[i]; });
+    }
     // semi-implicit Euler step (rng.h integrateState); flags[b] = 1 where an implicit cluster could not be projected
     int oracle_integrate(void *hv, const double *q, const double *yd, const double *ydd, double dt, double *q_out,
                          double *yd_out, int *flags, int64_t batch, int threads)

@@ -558,6 +558,55 @@ def test_external_forces_on_every_body(grbda, oracle, robot, tmp_path):
         m.setExternalForceBodies([0, 0])
 
 
+def contact_set(m):
+    """Contact points for the tests: one on every terminal link (end-effectors) with an offset, one on the trunk /
+    first body and one on an interior link (plain contact points)."""
+    feet = m.externalForceBodies()
+    bodies = list(feet) + [0, feet[0] - 1 if feet[0] > 1 else 1]
+    rng = np.random.default_rng(11)
+    offsets = rng.uniform(-0.2, 0.2, size=(len(bodies), 3))
+    ee = [1] * len(feet) + [0, 0]
+    return bodies, offsets, ee
+
+
+@pytest.mark.parametrize("robot", ["tello_with_arms", "mini_cheetah", "revolute_pair_chain_with_rotor_4"])
+def test_operational_space_programs(grbda, oracle, robot, tmp_path):
+    """Contact kinematics, contact Jacobians, applyTestForce and the inverse operational-space inertia matrix
+    (ClusterTreeDynamics.cpp:10-77,193-435, TreeModel.cpp:60-78): the emitted programs replayed in numpy against
+    the oracle's restatement of the Jacobians and the quantities the reference's own tests compare the EFPA with
+    (J H^-1 J^T, UnitTests/testRigidBodyDynamicsAlgos.cpp:241-335)."""
+    m = grbda.ClusterTreeModel.from_robot(robot, device=None)
+    o = oracle.OracleModel(ROBOTS.get(robot) or robot)
+    bodies, offsets, ee = contact_set(m)
+    m.setContactPoints(bodies, offsets, ee)
+    o.set_contact_points(bodies, offsets, ee)
+    assert (m.ncp, m.nee) == (len(bodies), sum(ee))
+    q, yd, aux = o.generate_states(12, seed=13)
+    B = q.shape[0]
+
+    def tape(algo, name):
+        path = str(tmp_path / name)
+        m.dump_program(algo, path)
+        return load_tape(path)
+    p, v = run_tape(tape(grbda.ALGO_CONTACT_KIN, "ck"), [q, yd, aux])
+    po, vo = o.contact_kinematics(q, yd)
+    assert rel(p.reshape(po.shape), po) < TOL and rel(v.reshape(vo.shape), vo) < TOL
+    J = run_tape(tape(grbda.ALGO_CONTACT_JAC, "cj"), [q, yd, aux])[0].reshape(B, m.ncp, 6, m.nv)
+    Jo = o.contact_jacobians(q, world=True)
+    assert rel(J, Jo) < TOL
+    # the Jacobian maps yd to the contact point velocity (linear rows)
+    assert rel(np.einsum("bcik,bk->bci", J[:, :, 3:, :], yd), vo) < 1e-12
+    f = np.random.default_rng(2).uniform(-1, 1, size=(B, m.ncp, 3))
+    d, lam = run_tape(tape(grbda.ALGO_TEST_FORCE, "tf"), [q, f.reshape(B, -1), aux])
+    do, lamo = o.apply_test_force(q, f)
+    assert rel(d.reshape(do.shape), do) < 1e-9 and rel(lam.reshape(lamo.shape), lamo) < 1e-9
+    L = run_tape(tape(grbda.ALGO_OSIM, "os"), [q, yd, aux])[0].reshape(B, 6 * m.nee, 6 * m.nee)
+    Lo = o.inverse_osim(q)
+    assert rel(L, Lo) < 1e-9 and rel(L, np.swapaxes(L, 1, 2)) < 1e-13
+    ev = np.linalg.eigvalsh(L)
+    assert (ev > -1e-9 * ev.max()).all()                                       # positive semi-definite (rank <= nv)
+
+
 def test_oracle_integration_step(oracle):
     """oracle/grbda_oracle/rng.h integrateState (ori::integrateQuat restated, OrientationTools.h:387-413):
     unit quaternions stay unit, implicit clusters stay on phi = 0, a constant body twist moves the base origin

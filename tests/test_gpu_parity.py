@@ -172,6 +172,43 @@ def test_external_forces_on_every_body(grbda, oracle, torch, robot):
     assert relrows(tau.cpu().numpy(), o.dynamics_with_external_forces(qn, ydn, auxn, f_full, forward=False)) < TOL64
 
 
+@pytest.mark.parametrize("robot", ["tello_with_arms", "mit_humanoid", "mini_cheetah"])
+def test_operational_space(grbda, oracle, torch, robot):
+    """Batched contact kinematics, contact Jacobians, applyTestForce and inverse operational-space inertia matrix
+    (ClusterTreeDynamics.cpp:10-77,193-435) on the feet / hands of the three BASELINE robots, against
+    the oracle (restated Jacobians; J H^-1 J^T as the reference's own tests define the expected values)."""
+    from test_compiler_cpu import contact_set
+    m = grbda.ClusterTreeModel.from_robot(robot)
+    o = oracle_for(oracle, m, robot)
+    bodies, offsets, ee = contact_set(m)
+    m.setContactPoints(bodies, offsets, ee)
+    o.set_contact_points(bodies, offsets, ee)
+    B = 300
+    q, yd, aux, _ = m.generateStates(B, seed=31)
+    qn, ydn = q.cpu().numpy(), yd.cpu().numpy()
+    p, v = m.contactKinematics(q, yd)
+    po, vo = o.contact_kinematics(qn, ydn)
+    assert relrows(p.cpu().numpy(), po) < TOL64 and relrows(v.cpu().numpy(), vo) < TOL64
+    J = m.contactJacobians(q)
+    assert relrows(J.cpu().numpy(), o.contact_jacobians(qn, world=True)) < TOL64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    f = torch.rand((B, m.ncp, 3), dtype=torch.float64, device="cuda", generator=g) - 0.5
+    d, lam = m.applyTestForce(q, f)
+    do, lamo = o.apply_test_force(qn, f.cpu().numpy())
+    assert relrows(d.cpu().numpy(), do) < 1e-8 and relrows(lam.cpu().numpy(), lamo, floor=1e-12) < 1e-8
+    # the device's own mass matrix agrees: H dstate = J_lin^T f
+    H = m.getMassMatrix(q)
+    lhs = torch.einsum("bij,bcj->bci", H, d)
+    rhs = torch.einsum("bcik,bci->bck", J[:, :, 3:, :], f)
+    assert float((lhs - rhs).abs().max() / rhs.abs().max()) < 1e-9
+    L = m.inverseOperationalSpaceInertiaMatrix(q)
+    assert relrows(L.cpu().numpy(), o.inverse_osim(qn)) < 1e-8
+    # a new contact set replaces the programs
+    m.setContactPoints(bodies[:1], offsets[:1], [1])
+    o.set_contact_points(bodies[:1], offsets[:1], [1])
+    assert relrows(m.inverseOperationalSpaceInertiaMatrix(q).cpu().numpy(), o.inverse_osim(qn)) < 1e-8
+
+
 @pytest.mark.parametrize("robot", ["tello_with_arms", "mit_humanoid", "four_bar", "revolute_chain_with_rotor_4"])
 def test_integration_step(grbda, oracle, torch, robot):
     """grbda_cuda_integrate_f64 / grbda_cuda_step_f64 against the oracle's restatement (ori::integrateQuat,

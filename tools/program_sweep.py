@@ -37,7 +37,7 @@ models += [("urdf", os.path.join(CORPUS, f)) for f in ("explicit_parallel_chains
 for kind, name in models:
     rec = {"model": os.path.basename(name), "states": 1 << LOG2}
     for prog in ("ltl", "aba"):
-        os.environ["GRBDA_JIT_FD_PROGRAM"] = prog
+        os.environ["GRBDA_FD_PROGRAM"] = prog
         m = grbda.ClusterTreeModel.from_robot(name) if kind == "robot" else grbda.ClusterTreeModel.from_urdf(name)
         B = 1 << LOG2
         q, yd, tau, _ = m.generateStates(B)
