@@ -50,6 +50,7 @@ namespace grbda
             bool parked = false;     // body parks long-lived values in the thread's shared-memory row
             int num_parked = 0;
             int stage_buffers = 1;   // chunked outputs: staging buffers per warp (1, or one per output array)
+            bool vector_stores = false; // large outputs leave as 256-bit stores of the thread's own row (emit.h)
             ProgramStats stats;
             Tape tape;
         };
@@ -221,9 +222,11 @@ namespace grbda
                 if (const char *gap = std::getenv("GRBDA_PARK_GAP")) // tuning experiments
                     pc.min_gap = std::atoi(gap);
                 out.parked = park && sync_every == 0;
-                out.body = em.cudaBody(sync_every, out_chunk, out.parked ? &pc : nullptr);
+                const bool vec = !(std::getenv("GRBDA_NO_VECTOR_STORES") && std::getenv("GRBDA_NO_VECTOR_STORES")[0] == '1');
+                out.body = em.cudaBody(sync_every, out_chunk, out.parked ? &pc : nullptr, vec);
                 out.num_parked = em.numParked();
                 out.stage_buffers = em.stageBuffers();
+                out.vector_stores = em.vectorStores();
                 out.range_check = em.cudaRangeCheck();
             }
             return out;
@@ -259,6 +262,7 @@ namespace grbda
                << ", N_OUT2 = " << c.n_out[2] << ";\n";
             os << "    static constexpr bool RANGE_CHECKED = " << (c.range_check == "true" ? "false" : "true") << ";\n";
             os << "    static constexpr int STAGE_BUFFERS = " << c.stage_buffers << ";\n";
+            os << "    static constexpr bool VECTOR_STORES = " << (c.vector_stores ? "true" : "false") << ";\n";
             os << "    static constexpr bool PARKED = " << (c.parked ? "true" : "false") << "; // " << c.num_parked
                << " values parked in the thread's tile row\n";
             os << "    template <typename real>\n    static __device__ __forceinline__ bool inRange(const real "
@@ -286,6 +290,8 @@ namespace grbda
             os << "#define KC(x) ((real)(x))\n#define KT(i) kc_table<real>(i)\n"
                   "#define OUT1(i, x) out1[i] = (x)\n#define OUT2(i, x) out2[i] = (x)\n"
                   "#define GRBDA_ALIGN() __syncwarp()\n#define GRBDA_PIN(x, late) GRBDA_PIN_IMPL(x, late, stage.zero)\n"
+                  "#define STGV4(k, m, base, a, b, c, d) if (stage.cls[k] == (m)) storeRow4(out##k + (base), a, b, c, d)\n"
+                  "#define STGV1(k, m, base, a) if (stage.cls[k] == (m)) storeRow1(out##k + (base), a)\n"
                   "#define STG_PUT(j, x) stage.lane[j] = (x)\n"
                   "#define STG_PUTK(k, j, x) stage.lane[(k) * stage.buf_stride + (j)] = (x)\n"
                   "#define STG_FLUSHI0(base, count) flushChunk<real, N_OUT0, count>(stage.g[0], base, stage.warp, stage.valid)\n"
@@ -295,7 +301,7 @@ namespace grbda
                   "#define STG_FLUSH1(base, count) flushChunk<real, N_OUT1, count>(stage.g[1], base, stage.warp, stage.valid)\n"
                   "#define STG_FLUSH2(base, count) flushChunk<real, N_OUT2, count>(stage.g[2], base, stage.warp, stage.valid)\n";
             os << c.body;
-            os << "#undef KC\n#undef KT\n#undef IN0\n#undef IN1\n#undef IN2\n#undef OUT0\n#undef OUT1\n#undef OUT2\n#undef GRBDA_ALIGN\n#undef GRBDA_PIN\n#undef PARK_ST\n#undef PARK_LD\n#undef STG_PUT\n#undef STG_PUTK\n#undef STG_FLUSHI0\n#undef STG_FLUSHI1\n#undef STG_FLUSHI2\n#undef STG_FLUSH0\n#undef STG_FLUSH1\n#undef STG_FLUSH2\n";
+            os << "#undef KC\n#undef KT\n#undef IN0\n#undef IN1\n#undef IN2\n#undef OUT0\n#undef OUT1\n#undef OUT2\n#undef GRBDA_ALIGN\n#undef GRBDA_PIN\n#undef PARK_ST\n#undef PARK_LD\n#undef STGV4\n#undef STGV1\n#undef STG_PUT\n#undef STG_PUTK\n#undef STG_FLUSHI0\n#undef STG_FLUSHI1\n#undef STG_FLUSHI2\n#undef STG_FLUSH0\n#undef STG_FLUSH1\n#undef STG_FLUSH2\n";
             os << "    }\n};\n";
         }
 

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <string>
 #include "sym.h"
+#include "../kernels/shapes.h"
 
 namespace grbda
 {
@@ -134,6 +135,7 @@ namespace grbda
             const ProgramStats &stats() const { return stats_; }
             int numParked() const { return num_parked_; }       // after cudaBody(..., park)
             int stageBuffers() const { return stage_buffers_; } // after cudaBody: staging buffers per warp
+            bool vectorStores() const { return vector_stores_; } // after cudaBody: outputs leave as 256-bit row stores
 
             Tape tape() const
             {
@@ -288,7 +290,13 @@ namespace grbda
             // `out_chunk` consecutive elements are held until the chunk is complete, written to the
             // warp's shared-memory staging buffer (STG_PUT) and flushed with coalesced stores
             // (STG_FLUSHk: 32 states x chunk, 128 contiguous bytes per state).
-            std::string cudaBody(int sync_every = 0, int out_chunk = 0, const ParkConfig *park = nullptr) const
+            // vector_stores: large output arrays skip the staging altogether: the shell maps the four warps of a CTA to the states s = 0..3 (mod 4) of
+            // its tile, so the position of a row inside the 32-byte sector grid, (s N + e) mod 4, is warp-uniform
+            // ("class" m = (warp N) mod 4), and every thread writes its own row with 256-bit stores of whole sectors
+            // (STGV4; the one or two ragged quads at the row ends go out as 64-bit stores, STGV1). A quad of a class
+            // is stored as soon as its last element exists: about one conditional store per element.
+            std::string cudaBody(int sync_every = 0, int out_chunk = 0, const ParkConfig *park = nullptr,
+                                 bool vector_stores = false) const
             {
                 std::ostringstream os;
                 int since_sync = 0;
@@ -312,7 +320,7 @@ namespace grbda
                     // output 0 is staged as a whole row when it is small (<= 64 values); every other output
                     // with more than one chunk's worth of values goes through the chunked path (direct
                     // stores of a thread's own row touch 32 sectors per instruction)
-                    chunked[arr] = out_chunk > 0 && (n > 64 || (arr > 0 && n > out_chunk));
+                    chunked[arr] = out_chunk > 0 && grbda_kernels::shapeLargeOutput((int)arr, n);
                     ready[arr].assign(n, 0);
                     if (chunked[arr])
                     {
@@ -355,7 +363,50 @@ namespace grbda
                     stage_buffers_ = 1;
                     if (n_imm > 0)
                         stage_buffers_ = (int)n_arr; // buffer k belongs to array k
+                    int n_chunked = 0;
+                    for (size_t arr = 0; arr < n_arr; arr++)
+                        n_chunked += chunked[arr];
+                    // only for arrays whose elements appear in ascending order (forward kinematics): a quad then waits
+                    // for at most three values. The mass matrix fills its rows out of order (H_ij and H_ji in different
+                    // rows, ancestors last): holding its quads costs registers (measured 0.53 against 0.28 ms per 2^18
+                    // Tello states), it keeps the chunk staging.
+                    vector_stores_ = vector_stores && n_chunked > 0 && n_imm == n_chunked;
+                    if (vector_stores_)
+                        stage_buffers_ = 0; // no staging buffers at all
                 }
+                // vector stores: per array and class, the elements each sector-aligned quad still waits for
+                auto classesOf = [](int n) { return n % 4 == 0 ? 1 : (n % 2 == 0 ? 2 : 4); };
+                auto classOffset = [&](int n, int c) { return classesOf(n) == 4 ? c : (classesOf(n) == 2 ? 2 * c : 0); };
+                std::vector<std::vector<std::vector<int>>> quad_missing(n_arr);
+                if (vector_stores_)
+                    for (size_t arr = 0; arr < n_arr; arr++)
+                    {
+                        if (!chunked[arr])
+                            continue;
+                        const int n = (int)p_.outputs[arr].size();
+                        quad_missing[arr].assign(classesOf(n), std::vector<int>((n + 3) / 4 + 1, 0));
+                        for (int c = 0; c < classesOf(n); c++)
+                            for (int e = 0; e < n; e++)
+                                quad_missing[arr][c][(e + classOffset(n, c)) / 4]++;
+                    }
+                auto vectorStore = [&](int arr, int el) {
+                    const int n = (int)p_.outputs[arr].size();
+                    auto val = [&](int e) { return ref(p_.outputs[arr][e].id); };
+                    for (int c = 0; c < classesOf(n); c++)
+                    {
+                        const int m = classOffset(n, c); // row start inside the sector grid
+                        const int quad = (el + m) / 4;
+                        if (--quad_missing[arr][c][quad] != 0)
+                            continue;
+                        const int first = std::max(0, 4 * quad - m), last = std::min(n - 1, 4 * quad - m + 3);
+                        if (last - first + 1 == 4)
+                            os << "STGV4(" << arr << ", " << m << ", " << first << ", " << val(first) << ", " << val(first + 1)
+                               << ", " << val(first + 2) << ", " << val(first + 3) << ");\n";
+                        else
+                            for (int e = first; e <= last; e++)
+                                os << "STGV1(" << arr << ", " << m << ", " << e << ", " << val(e) << ");\n";
+                    }
+                };
                 auto drain = [&](int arr) {
                     const int n = (int)p_.outputs[arr].size();
                     while (drain_next[arr] < n && ready[arr][drain_next[arr]])
@@ -380,6 +431,11 @@ namespace grbda
                     if (ready[arr][el])
                         return;
                     ready[arr][el] = 1;
+                    if (vector_stores_)
+                    {
+                        vectorStore(arr, el);
+                        return;
+                    }
                     if (immediate[arr])
                     {
                         drain(arr);
@@ -876,6 +932,7 @@ namespace grbda
             mutable std::vector<std::string> alias_; // name of a value after it was reloaded from its parking slot
             mutable int num_parked_ = 0;
             mutable int stage_buffers_ = 1;
+            mutable bool vector_stores_ = false;
             std::vector<int> uses_;
             std::vector<int32_t> partner_;
             ProgramStats stats_;

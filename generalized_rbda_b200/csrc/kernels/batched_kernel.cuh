@@ -311,7 +311,37 @@ namespace grbda_kernels
         int valid;    // number of states of this warp that exist (tail of the batch)
         int zero;     // 0 at run time, unknown at compile time (see pinAfter)
         int buf_stride; // elements between the staging buffers of consecutive output arrays (Body::STAGE_BUFFERS > 1)
+        // Body::VECTOR_STORES: position of this thread's row of output k inside the 32-byte sector grid,
+        // (state N_OUTk) mod 4 - warp-uniform by the state mapping of the shells - or -1 for a thread without a state
+        int cls[3];
     };
+    // 256-bit store of one whole sector of the thread's own output row (SASS STG.E.256), evict-first
+    __device__ __forceinline__ void storeRow4(double *p, double a, double b, double c, double d)
+    {
+#ifdef GRBDA_NO_V256 // compilers before CUDA 12.9 (PTX ISA 8.8): the same sector as two 128-bit halves
+        asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n\tst.global.cs.v2.f64 [%0+16], {%3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#else
+        asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#endif
+    }
+    __device__ __forceinline__ void storeRow4(float *p, float a, float b, float c, float d)
+    {
+        // FP32 rows sit on a 16-byte grid for the same classes: one 128-bit store
+        asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+    }
+    template <typename real>
+    __device__ __forceinline__ void storeRow1(real *p, real a) { __stcs(p, a); }
+    // state (row of the tile) a thread works on. Vector-store bodies: warp w takes the states w, w + 4, w + 8, ...
+    template <typename Body, int BLOCK>
+    __device__ __forceinline__ int threadState(int tid)
+    {
+        // (CTAs that are not a multiple of four warps keep the identity: the class is then a per-thread value and the
+        // conditional stores diverge - correct, slower; no shipped shape does that for a vector-store body)
+        if constexpr (Body::VECTOR_STORES && BLOCK % 128 == 0)
+            return (tid & 127) / 32 + (tid & 31) * 4 + (tid & ~127);
+        else
+            return tid;
+    }
     // Flush of one staged chunk: 32 states x COUNT values, COUNT * sizeof(real) contiguous bytes per
     // state. FK / H bodies flush 40-70 chunks. Two things were measured on the way: fully unrolled
     // inline copies with index arithmetic made the kernels 15-19 k instructions long and
@@ -385,9 +415,14 @@ namespace grbda_kernels
     }
     template <typename Body, typename real>
     __device__ __forceinline__ OutStage<real> makeOutStage(unsigned char *stage_base, real *out0, real *out1,
-                                                           real *out2, int64_t first, int rows, int64_t batch)
+                                                           real *out2, int64_t first, int rows, int64_t batch,
+                                                           int ts = 0)
     {
         OutStage<real> o;
+        // ts = state of the tile this thread works on (threadState); tiles start at multiples of four states
+        o.cls[0] = ts < rows ? (ts * Body::N_OUT0) & 3 : -1;
+        o.cls[1] = ts < rows ? (ts * Body::N_OUT1) & 3 : -1;
+        o.cls[2] = ts < rows ? (ts * Body::N_OUT2) & 3 : -1;
         o.zero = (int)((uint64_t)batch >> 62); // batch < 2^62: always 0, but the compiler cannot know
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         real *buf = reinterpret_cast<real *>(stage_base) + (size_t)warp * 32 * (OUT_CHUNK + 1);
@@ -461,13 +496,15 @@ namespace grbda_kernels
             const int rows = remaining < BLOCK ? (int)remaining : BLOCK;
             // Every thread runs the body (it may contain CTA-wide alignment barriers); threads past the end
             // of the batch recompute the last valid state, so their duplicate stores are benign.
-            const int t = min((int)threadIdx.x, rows - 1);
+            const int ts = threadState<Body, BLOCK>((int)threadIdx.x);
+            const bool has_state = ts < rows;
+            const int t = min(ts, rows - 1);
             const int64_t state = first + t;
 
             if constexpr (STAGED)
             {
                 real *smem = reinterpret_cast<real *>(smem_raw);
-                const OutStage<real> stage = makeOutStage<Body, real>(smem_raw + L::TILE_BYTES, out0, out1, out2, first, rows, batch);
+                const OutStage<real> stage = makeOutStage<Body, real>(smem_raw + L::TILE_BYTES, out0, out1, out2, first, rows, batch, ts);
                 if (Body::N_IN0)
                     stage_in<real, Body::N_IN0 ? Body::N_IN0 : 1, BLOCK>(in0 + first * Body::N_IN0, smem, rows);
                 if (Body::N_IN1)
@@ -490,7 +527,7 @@ namespace grbda_kernels
                     real *o0 = L::STAGE_OUT0 ? smem + L::OFFO + t * L::SO : out0 + state * Body::N_OUT0;
                     real *o1 = Body::N_OUT1 ? out1 + state * Body::N_OUT1 : nullptr;
                     real *o2 = Body::N_OUT2 ? out2 + state * Body::N_OUT2 : nullptr;
-                    if (!Body::PARKED || (int)threadIdx.x < rows) // parked rows are private: no tail replicas
+                    if (!Body::PARKED || has_state) // parked rows are private: no tail replicas
                         Body::template run<real, FAST>(i0, i1, i2, o0, o1, o2, stage);
                     if (L::STAGE_OUT0)
                     {
@@ -502,7 +539,7 @@ namespace grbda_kernels
             }
             else
             {
-                const OutStage<real> stage = makeOutStage<Body, real>(smem_raw, out0, out1, out2, first, rows, batch);
+                const OutStage<real> stage = makeOutStage<Body, real>(smem_raw, out0, out1, out2, first, rows, batch, ts);
                 const real *i0 = in0 + state * Body::N_IN0, *i1 = in1 + state * Body::N_IN1, *i2 = in2 + state * Body::N_IN2;
                 bool ok = true;
                 if (FAST && GRBDA_RANGE_CHECKED(Body))
@@ -744,12 +781,14 @@ namespace grbda_kernels
         mbarWait(bar, 0);
 
         // every thread runs the body (alignment barriers inside); tail threads redo the last valid state
-        const int t = min(tid, rows - 1);
+        const int ts = threadState<Body, BLOCK>(tid);
+        const bool has_state = ts < rows;
+        const int t = min(ts, rows - 1);
         const int64_t state = first + t;
         real *o0 = L::STAGE_OUT0 ? so + t * L::SO : out0 + state * Body::N_OUT0;
         real *o1 = Body::N_OUT1 ? out1 + state * Body::N_OUT1 : nullptr;
         real *o2 = Body::N_OUT2 ? out2 + state * Body::N_OUT2 : nullptr;
-        const OutStage<real> stage = makeOutStage<Body, real>(smem_raw + L::TILE_BYTES, out0, out1, out2, first, rows, batch);
+        const OutStage<real> stage = makeOutStage<Body, real>(smem_raw + L::TILE_BYTES, out0, out1, out2, first, rows, batch, ts);
         const real *i0 = s0 + t * L::S0, *i1 = s1 + t * L::S1, *i2 = s2 + t * L::S2;
         if (GRBDA_RANGE_CHECKED(Body))
         {
@@ -759,7 +798,7 @@ namespace grbda_kernels
             if (!ok)
                 return; // CTA-uniform: the second pass recomputes this tile
         }
-        if (!Body::PARKED || tid < rows) // parked rows are private: no tail replicas
+        if (!Body::PARKED || has_state) // parked rows are private: no tail replicas
             Body::template run<real, true>(i0, i1, i2, o0, o1, o2, stage);
 
         if (L::STAGE_OUT0)

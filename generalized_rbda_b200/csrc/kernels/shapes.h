@@ -25,6 +25,11 @@ namespace grbda_kernels
     // pairs per half warp for 8-byte elements.
     GRBDA_HD constexpr int oddStride(int n) { return n | 1; }
 
+    // Output array k of a program leaves through the large-output path (256-bit stores of whole sectors of the
+    // thread's own row, or chunk staging) rather than as a staged row / plain stores. The emitter
+    // (compiler/emit.h) and the host-side alignment check (runtime/capi.cu) share this rule.
+    GRBDA_HD constexpr bool shapeLargeOutput(int k, int n) { return n > 64 || (k > 0 && n > OUT_CHUNK); }
+
     // elem = sizeof(real); the static_asserts in the kernels keep these in step with TileLayout / TmaLayout
     GRBDA_HD constexpr size_t shapeAlign16(size_t x) { return (x + 15) & ~(size_t)15; }
     GRBDA_HD constexpr size_t shapeStageBytes(const int *n_out, int stage_buffers, int block, int elem)

@@ -265,6 +265,10 @@ namespace
                 return fail(GRBDA_ERR_INVALID_ARGUMENT, "null input pointer");
             if (n_out[i] && !outs[i])
                 return fail(GRBDA_ERR_INVALID_ARGUMENT, "null output pointer");
+            // large outputs (FK p/R/v, H, J, ...) are written with 256-bit (FP32: 128-bit) stores of whole sectors
+            if (grbda_kernels::shapeLargeOutput(i, n_out[i]) && ((uintptr_t)outs[i] & (f32 ? 15 : 31)))
+                return fail(GRBDA_ERR_INVALID_ARGUMENT, f32 ? "large output arrays must be 16-byte aligned"
+                                                            : "large output arrays must be 32-byte aligned");
         }
         grbda_kernels::LaunchArgs a;
         for (int i = 0; i < 3; i++)

@@ -29,7 +29,12 @@ namespace host_body
         int valid;
         int zero;
         int buf_stride;
+        int cls[3]; // vector-store bodies: the host stand-in runs "warp 0" (class 0 of every array)
     };
+    template <typename real>
+    inline void storeRow4(real *p, real a, real b, real c, real d) { p[0] = a, p[1] = b, p[2] = c, p[3] = d; }
+    template <typename real>
+    inline void storeRow1(real *p, real a) { p[0] = a; }
     template <typename real, int N, int COUNT>
     inline void flushChunk(real *g, int base, const real *stg, int valid)
     {

@@ -363,6 +363,8 @@ int main(int argc, char **argv)
         st.lane = st.warp = stg;
         st.g[0] = &out0[b * M0], st.g[1] = &out1[b * M1], st.g[2] = &out2[b * M2];
         st.valid = 1, st.zero = 0, st.buf_stride = OUT_CHUNK + 1;
+        // vector-store bodies: state b plays a thread of warp b % 4, so all four store schedules are exercised
+        st.cls[0] = (int)((b % 4) * M0) & 3, st.cls[1] = (int)((b % 4) * M1) & 3, st.cls[2] = (int)((b % 4) * M2) & 3;
         const bool staged_out = M0 <= 64;
         Body::run<double, true>(r0, r1, r2, staged_out ? o0 : &out0[b * M0], &out1[b * M1], &out2[b * M2], st);
         if (staged_out)
@@ -407,7 +409,7 @@ def run_emitted_source(m, program, park, ins, tmp_path, tag):
 
 
 @pytest.mark.parametrize("robot", ["tello_with_arms", "four_bar"])
-def test_emitted_cuda_text_on_the_host(grbda, oracle, robot, tmp_path):
+def test_emitted_cuda_text_on_the_host(grbda, oracle, robot, tmp_path, monkeypatch):
     """What the tapes cannot see: the emitted CUDA text (statement order, sin/cos pairing and pins, chunked
     output staging, parking of long-lived values in the tile rows, the generated range check) is compiled
     with g++ against host stand-ins of the kernel helpers (tests/host_body_prelude.h) and compared with the
@@ -426,13 +428,26 @@ def test_emitted_cuda_text_on_the_host(grbda, oracle, robot, tmp_path):
         assert in_range == q.shape[0]
         if park and robot == "tello_with_arms":
             assert "PARKED = true" in text and text.count("PARK_ST(") >= (50 if program == LTL else 5)
-    # forward kinematics: three chunk-staged output arrays
+    # forward kinematics: three large output arrays written with 256-bit row stores (the host run plays all four
+    # alignment classes), and the chunk-staged form they replace (GRBDA_NO_VECTOR_STORES=1, kept for A/B timing)
     p, R, v = o.forward_kinematics(q, yd)
-    outs, in_range, text = run_emitted_source(m, 2, False, [q, yd], tmp_path, "fk")
-    assert rel(outs[0].reshape(p.shape), p) < TOL and rel(outs[1].reshape(R.shape), R) < TOL
-    assert rel(outs[2].reshape(v.shape), v) < TOL
+    for tag, legacy in (("fk", False), ("fk_chunks", True)):
+        if legacy:
+            monkeypatch.setenv("GRBDA_NO_VECTOR_STORES", "1")
+        outs, in_range, text = run_emitted_source(m, 2, False, [q, yd], tmp_path, tag)
+        monkeypatch.delenv("GRBDA_NO_VECTOR_STORES", raising=False)
+        assert rel(outs[0].reshape(p.shape), p) < TOL and rel(outs[1].reshape(R.shape), R) < TOL
+        assert rel(outs[2].reshape(v.shape), v) < TOL
+        if robot == "tello_with_arms":
+            if legacy:
+                assert "STAGE_BUFFERS = 3" in text and "STG_PUTK(" in text
+            else:
+                assert "VECTOR_STORES = true" in text and text.count("STGV4(") > 300
+    # the mass matrix fills its rows out of order and keeps the chunk staging (emit.h)
+    outs, _, text = run_emitted_source(m, 3, False, [q], tmp_path, "h_chunks")
+    assert rel(outs[0].reshape(-1, o.nv, o.nv), o.mass_matrix(q)) < TOL
     if robot == "tello_with_arms":
-        assert "STAGE_BUFFERS = 3" in text and "STG_PUTK(" in text
+        assert "VECTOR_STORES = false" in text and "STG_FLUSH0(" in text
     # the generated range check rejects a joint angle beyond the fast sin/cos range
     q_far = q.copy()
     q_far[3, m.clusters()[-1]["position_index"]] = 3.0e13
