@@ -31,6 +31,7 @@ ALGO_ID, ALGO_FD, ALGO_FK, ALGO_H, ALGO_PHI = 0, 1, 2, 3, 4
 ALGO_NAMES = ["id", "fd", "fk", "h", "phi"]
 ALGO_GFA, ALGO_GFS = 5, 6  # tau_in +/- J^T f_ext (external forces on the terminal links)
 ALGO_CONTACT_KIN, ALGO_CONTACT_JAC, ALGO_TEST_FORCE, ALGO_OSIM = 8, 9, 10, 11  # operational space (contact points)
+ALGO_ID_DERIV, ALGO_FD_DERIV = 12, 13  # derivatives of the dynamics
 PROGRAM_FD_LTL = 7  # dump_program only: forward dynamics as CRBA + bias + sparse L^T D L (kernel variant "ltl")
 
 _vp = C.c_void_p
@@ -73,6 +74,8 @@ _lib.grbda_cuda_contact_kinematics_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64
 _lib.grbda_cuda_contact_jacobians_f64.argtypes = [_vp, _vp, _vp, _i64, _vp]
 _lib.grbda_cuda_apply_test_force_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp]
 _lib.grbda_cuda_inverse_osim_f64.argtypes = [_vp, _vp, _vp, _i64, _vp]
+_lib.grbda_cuda_inverse_dynamics_derivatives_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
+_lib.grbda_cuda_forward_dynamics_derivatives_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]
 _lib.grbda_cuda_integrate_f64.argtypes = [_vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _i64, _vp]
 _lib.grbda_cuda_step_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _i64, _vp]
 _lib.grbda_cuda_dynamics_host_f64.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _i64]
@@ -95,6 +98,7 @@ EXPORTED_SYMBOLS = [
     "grbda_cuda_set_contact_points", "grbda_cuda_num_contact_points", "grbda_cuda_num_end_effectors",
     "grbda_cuda_contact_kinematics_f64", "grbda_cuda_contact_jacobians_f64", "grbda_cuda_apply_test_force_f64",
     "grbda_cuda_inverse_osim_f64",
+    "grbda_cuda_inverse_dynamics_derivatives_f64", "grbda_cuda_forward_dynamics_derivatives_f64",
     "grbda_cuda_inverse_dynamics_f64", "grbda_cuda_inverse_dynamics_f32",
     "grbda_cuda_forward_dynamics_f64", "grbda_cuda_forward_dynamics_f32",
     "grbda_cuda_mass_matrix_f64", "grbda_cuda_mass_matrix_f32",
@@ -517,6 +521,29 @@ class ClusterTreeModel:
         L = torch.empty((q.shape[0], n, n), dtype=torch.float64, device=q.device)
         _check(_lib.grbda_cuda_inverse_osim_f64(self._h, _ptr(q), _ptr(L), q.shape[0], _stream()))
         return L
+
+    def inverseDynamicsDerivatives(self, q, yd, ydd):
+        """(dtau_dq, dtau_dyd), each [batch, nv, nv], [b, i, j] = d tau_i / d x_j; dq is the tangent-space
+        perturbation of the reference's derivative test (d tau / d ydd is getMassMatrix)."""
+        import torch
+        q = self._prep(q, self.nq, torch.float64)
+        yd, ydd = self._prep(yd, self.nv, torch.float64), self._prep(ydd, self.nv, torch.float64)
+        dq = torch.empty((q.shape[0], self.nv, self.nv), dtype=torch.float64, device=q.device)
+        dv = torch.empty_like(dq)
+        _check(_lib.grbda_cuda_inverse_dynamics_derivatives_f64(self._h, _ptr(q), _ptr(yd), _ptr(ydd), _ptr(dq), _ptr(dv),
+                                                                q.shape[0], _stream()))
+        return dq, dv
+
+    def forwardDynamicsDerivatives(self, q, yd, tau):
+        """(dydd_dq, dydd_dyd, dydd_dtau), each [batch, nv, nv]; dydd_dtau = H^-1."""
+        import torch
+        q = self._prep(q, self.nq, torch.float64)
+        yd, tau = self._prep(yd, self.nv, torch.float64), self._prep(tau, self.nv, torch.float64)
+        dq = torch.empty((q.shape[0], self.nv, self.nv), dtype=torch.float64, device=q.device)
+        dv, dt = torch.empty_like(dq), torch.empty_like(dq)
+        _check(_lib.grbda_cuda_forward_dynamics_derivatives_f64(self._h, _ptr(q), _ptr(yd), _ptr(tau), _ptr(dq), _ptr(dv),
+                                                                _ptr(dt), q.shape[0], _stream()))
+        return dq, dv, dt
 
     def integrate(self, q, yd, ydd, dt, out=None):
         """(q', yd', flags): semi-implicit Euler step, quaternion base by ori::integrateQuat, implicit clusters

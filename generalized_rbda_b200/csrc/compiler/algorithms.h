@@ -33,6 +33,7 @@
 #include <map>
 #include "../host/model.h"
 #include "spatial_sym.h"
+#include "autodiff.h"
 
 namespace grbda
 {
@@ -751,6 +752,118 @@ namespace grbda
                 for (int r : roots_)
                     visit(r);
                 return tau;
+            }
+
+            // ---------------------------------------------------------------------------------
+            // derivatives of the inverse dynamics: d tau / d dq and d tau / d yd, both nv x nv,
+            // row-major [i][j] = d tau_i / d x_j. (d tau / d ydd is the mass matrix.)
+            // dq is the tangent-space perturbation of the reference's derivative test
+            // (UnitTests/testHelpers.hpp:50-112, `plus`): q + dq for every one-dof coordinate; floating base
+            // [p; quat] (+) [dw; dp] = [p + R^T dp; quat + 1/2 quat (x) (0, dw)] with R the rotation of
+            // quaternionToRotationMatrix(quat). The reference test leaves implicit clusters out (its TODO at
+            // testRigidBodyDynamicsAlgosDerivatives.cpp:166); here their spanning coordinates move along the
+            // constraint manifold, dq_span = G(q) dy, the derivative with respect to the independent coordinates.
+            // ---------------------------------------------------------------------------------
+            std::vector<std::vector<std::pair<int, Sym>>> positionTangentMap()
+            {
+                const int nv = m_.getNumDegreesOfFreedom();
+                std::vector<std::vector<std::pair<int, Sym>>> T(nv); // per direction: (position index, d q / d dq_j)
+                for (const ClusterTreeNode &c : m_.clusters())
+                {
+                    const ClusterDesc &d = c.joint_;
+                    const int pi = c.position_index_, vi = c.velocity_index_, n = d.num_velocities;
+                    if (d.type == ClusterType::FreeQuaternion)
+                    {
+                        const Sym e0 = Sym::input(IN_Q, pi + 3), e1 = Sym::input(IN_Q, pi + 4), e2 = Sym::input(IN_Q, pi + 5),
+                                  e3 = Sym::input(IN_Q, pi + 6);
+                        const M3 E = quaternionToRotationMatrix(e0, e1, e2, e3);
+                        const Sym h(0.5);
+                        // 1/2 quat (x) (0, w): [-qv . w; e0 w + qv x w] / 2, columns = unit vectors w
+                        const Sym dq4[4][3] = {{-(h * e1), -(h * e2), -(h * e3)},
+                                               {h * e0, -(h * e3), h * e2},
+                                               {h * e3, h * e0, -(h * e1)},
+                                               {-(h * e2), h * e1, h * e0}};
+                        for (int k = 0; k < 3; k++)
+                        {
+                            for (int r = 0; r < 4; r++)
+                                T[vi + k].push_back({pi + 3 + r, dq4[r][k]});
+                            for (int r = 0; r < 3; r++)
+                                T[vi + 3 + k].push_back({pi + r, E(k, r)}); // (E^T)_{r k}
+                        }
+                    }
+                    else if (d.type == ClusterType::FreeRollPitchYaw || d.type == ClusterType::Explicit)
+                        for (int k = 0; k < n; k++)
+                            T[vi + k].push_back({pi + k, Sym(1.0)});
+                    else
+                    {
+                        const ClusterKin ck = clusterConstraint(c, false);
+                        for (int k = 0; k < n; k++)
+                            for (int i = 0; i < d.num_bodies; i++)
+                                T[vi + k].push_back({pi + i, ck.G[i * n + k]});
+                    }
+                }
+                return T;
+            }
+            void inverseDynamicsDerivatives(std::vector<Sym> &dtau_dq, std::vector<Sym> &dtau_dyd)
+            {
+                const int nv = m_.getNumDegreesOfFreedom();
+                const std::vector<Sym> tau = inverseDynamics(); // ydd = inAux(): inputs, or placeholders (below)
+                const auto T = positionTangentMap();
+                dtau_dq.assign(nv * nv, Sym(0.0));
+                dtau_dyd.assign(nv * nv, Sym(0.0));
+                for (int j = 0; j < nv; j++)
+                {
+                    std::unordered_map<int32_t, Sym> seed;
+                    for (auto &kv : T[j])
+                        seed[Sym::input(IN_Q, kv.first).id] = kv.second;
+                    const std::vector<Sym> col = tangentSweep(tau, seed);
+                    for (int i = 0; i < nv; i++)
+                        dtau_dq[i * nv + j] = col[i];
+                    seed.clear();
+                    seed[inYd(j).id] = Sym(1.0);
+                    const std::vector<Sym> col_v = tangentSweep(tau, seed);
+                    for (int i = 0; i < nv; i++)
+                        dtau_dyd[i * nv + j] = col_v[i];
+                }
+            }
+
+            // Derivatives of the forward dynamics by the implicit function theorem, tau = ID(q, yd, ydd):
+            //   d ydd / d x = -H^-1 (d ID / d x) at ydd = FD(q, yd, tau),   d ydd / d tau = H^-1.
+            // (The reference differentiates the forward dynamics the same way it does everything: CasADi's
+            // jacobian() of the symbolic program, testRigidBodyDynamicsAlgosDerivatives.cpp:141-151 - there named
+            // `inverseDynamics(tau)` but bound to the argument of forwardDynamics in the test's finite differences.)
+            // The partial derivatives of ID are taken with placeholder accelerations (input array 3), which are then
+            // replaced by the forward-dynamics expressions; every H^-1 column solve shares the one factorisation.
+            void forwardDynamicsDerivatives(std::vector<Sym> &dydd_dq, std::vector<Sym> &dydd_dyd, std::vector<Sym> &dydd_dtau)
+            {
+                const int nv = m_.getNumDegreesOfFreedom();
+                std::vector<Sym> placeholder(nv);
+                for (int i = 0; i < nv; i++)
+                    placeholder[i] = Sym::input(3, i);
+                std::vector<Sym> d_q, d_yd;
+                aux_override_ = &placeholder;
+                inverseDynamicsDerivatives(d_q, d_yd);
+                aux_override_ = nullptr;
+                const std::vector<Sym> ydd = forwardDynamicsLTL();
+                std::unordered_map<int32_t, Sym> values;
+                for (int i = 0; i < nv; i++)
+                    values[placeholder[i].id] = ydd[i];
+                std::vector<Sym> all = d_q;
+                all.insert(all.end(), d_yd.begin(), d_yd.end());
+                all = substituteInputs(all, values);
+                dydd_dq.assign(nv * nv, Sym(0.0));
+                dydd_dyd.assign(nv * nv, Sym(0.0));
+                dydd_dtau.assign(nv * nv, Sym(0.0));
+                for (int j = 0; j < nv; j++)
+                {
+                    std::vector<Sym> bq(nv), bv(nv), e(nv, Sym(0.0));
+                    for (int i = 0; i < nv; i++)
+                        bq[i] = -all[i * nv + j], bv[i] = -all[nv * nv + i * nv + j];
+                    e[j] = Sym(1.0);
+                    const std::vector<Sym> xq = solveMassMatrix(bq), xv = solveMassMatrix(bv), xe = solveMassMatrix(e);
+                    for (int i = 0; i < nv; i++)
+                        dydd_dq[i * nv + j] = xq[i], dydd_dyd[i * nv + j] = xv[i], dydd_dtau[i * nv + j] = xe[i];
+                }
             }
 
             // ---------------------------------------------------------------------------------

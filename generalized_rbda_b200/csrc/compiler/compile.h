@@ -29,14 +29,18 @@ namespace grbda
             ALGO_CONTACT_JAC = 9,  // in: q              out: J[n_cp][6][nv] (world frame, [angular; linear])
             ALGO_TEST_FORCE = 10,  // in: q, f[3 n_cp]   out: dstate[n_cp][nv], lambda_inv[n_cp]
             ALGO_OSIM = 11,        // in: q              out: Lambda^-1 [6 n_ee][6 n_ee]
-            PROGRAM_COUNT = 12
+            // derivatives (compiled at run time when first used): row-major [i][j] = d out_i / d x_j,
+            // dq = tangent-space perturbation of the positions (ModelCompiler::positionTangentMap)
+            ALGO_ID_DERIV = 12,    // in: q, yd, ydd     out: dtau/ddq [nv nv], dtau/dyd [nv nv]
+            ALGO_FD_DERIV = 13,    // in: q, yd, tau     out: dydd/ddq [nv nv], dydd/dyd [nv nv], dydd/dtau = H^-1 [nv nv]
+            PROGRAM_COUNT = 14
         };
         // registry slot a program belongs to
         inline int algoOfProgram(int program) { return program == PROGRAM_FD_LTL ? ALGO_FD : program; }
         inline const char *algoName(int a)
         {
             static const char *names[] = {"id", "fd", "fk", "h", "phi", "gfa", "gfs", "fd_ltl", "contact_kin", "contact_jac",
-                                          "test_force", "osim"};
+                                          "test_force", "osim", "id_deriv", "fd_deriv"};
             return names[a];
         }
 
@@ -98,6 +102,12 @@ namespace grbda
                 break;
             case ALGO_OSIM:
                 n_out[0] = 36 * model.getNumEndEffectors() * model.getNumEndEffectors();
+                break;
+            case ALGO_ID_DERIV:
+                n_in[1] = n_in[2] = nv, n_out[0] = n_out[1] = nv * nv;
+                break;
+            case ALGO_FD_DERIV:
+                n_in[1] = n_in[2] = nv, n_out[0] = n_out[1] = n_out[2] = nv * nv;
                 break;
             default:
                 throw std::runtime_error("algoSizes: unknown program");
@@ -191,6 +201,22 @@ namespace grbda
                 p.n_in[0] = nq;
                 p.outputs.push_back(mc.inverseOperationalSpaceInertiaMatrix());
                 break;
+            case ALGO_ID_DERIV:
+            {
+                p.n_in[0] = nq, p.n_in[1] = nv, p.n_in[2] = nv;
+                std::vector<sym::Sym> dq, dyd;
+                mc.inverseDynamicsDerivatives(dq, dyd);
+                p.outputs = {dq, dyd};
+                break;
+            }
+            case ALGO_FD_DERIV:
+            {
+                p.n_in[0] = nq, p.n_in[1] = nv, p.n_in[2] = nv;
+                std::vector<sym::Sym> dq, dyd, dtau;
+                mc.forwardDynamicsDerivatives(dq, dyd, dtau);
+                p.outputs = {dq, dyd, dtau};
+                break;
+            }
             default:
                 throw std::runtime_error("compileAlgo: unknown algorithm");
             }
@@ -199,7 +225,7 @@ namespace grbda
 
         inline CompiledAlgo compileAlgo(const ClusterTreeModel &model, int algo, bool want_body = true,
                                         int sync_every = 0, ConstTable *consts = nullptr, int out_chunk = 0,
-                                        bool park = false)
+                                        bool park = false, bool allow_vector_stores = true)
         {
             sym::Graph graph;
             sym::GraphScope scope(graph);
@@ -222,7 +248,9 @@ namespace grbda
                 if (const char *gap = std::getenv("GRBDA_PARK_GAP")) // tuning experiments
                     pc.min_gap = std::atoi(gap);
                 out.parked = park && sync_every == 0;
-                const bool vec = !(std::getenv("GRBDA_NO_VECTOR_STORES") && std::getenv("GRBDA_NO_VECTOR_STORES")[0] == '1');
+                // (vector-store bodies need CTAs of four warps: the caller says whether its launch shape has them)
+                const bool vec = allow_vector_stores &&
+                                 !(std::getenv("GRBDA_NO_VECTOR_STORES") && std::getenv("GRBDA_NO_VECTOR_STORES")[0] == '1');
                 out.body = em.cudaBody(sync_every, out_chunk, out.parked ? &pc : nullptr, vec);
                 out.num_parked = em.numParked();
                 out.stage_buffers = em.stageBuffers();
@@ -269,7 +297,8 @@ namespace grbda
                   "*__restrict__ in0, const real *__restrict__ in1,\n        const real *__restrict__ in2)\n    {\n"
                   "#define KC(x) ((real)(x))\n#define IN0(i) in0[i]\n#define IN1(i) in1[i]\n#define IN2(i) in2[i]\n"
                   "        return " << c.range_check << ";\n#undef KC\n#undef IN0\n#undef IN1\n#undef IN2\n    }\n";
-            os << "    template <typename real, bool FAST>\n";
+            // vector-store bodies: W = alignment class of the warp (state mod 4), kernels/batched_kernel.cuh runBody
+            os << "    template <typename real, bool FAST" << (c.vector_stores ? ", int W" : "") << ">\n";
             if (c.parked)
                 // the thread's rows are read AND written (parking): no __restrict__, one pointer per row
                 os << "    static __device__ __forceinline__ void run(const real *in0, const real *in1, const real *in2,\n"
@@ -290,8 +319,8 @@ namespace grbda
             os << "#define KC(x) ((real)(x))\n#define KT(i) kc_table<real>(i)\n"
                   "#define OUT1(i, x) out1[i] = (x)\n#define OUT2(i, x) out2[i] = (x)\n"
                   "#define GRBDA_ALIGN() __syncwarp()\n#define GRBDA_PIN(x, late) GRBDA_PIN_IMPL(x, late, stage.zero)\n"
-                  "#define STGV4(k, m, base, a, b, c, d) if (stage.cls[k] == (m)) storeRow4(out##k + (base), a, b, c, d)\n"
-                  "#define STGV1(k, m, base, a) if (stage.cls[k] == (m)) storeRow1(out##k + (base), a)\n"
+                  "#define STGV4(k, m, base, a, b, c, d) if (((W * N_OUT##k) & 3) == (m) && stage.store) storeRow4(out##k + (base), a, b, c, d)\n"
+                  "#define STGV1(k, m, base, a) if (((W * N_OUT##k) & 3) == (m) && stage.store) storeRow1(out##k + (base), a)\n"
                   "#define STG_PUT(j, x) stage.lane[j] = (x)\n"
                   "#define STG_PUTK(k, j, x) stage.lane[(k) * stage.buf_stride + (j)] = (x)\n"
                   "#define STG_FLUSHI0(base, count) flushChunk<real, N_OUT0, count>(stage.g[0], base, stage.warp, stage.valid)\n"

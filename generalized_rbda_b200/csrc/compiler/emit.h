@@ -366,11 +366,11 @@ namespace grbda
                     int n_chunked = 0;
                     for (size_t arr = 0; arr < n_arr; arr++)
                         n_chunked += chunked[arr];
-                    // only for arrays whose elements appear in ascending order (forward kinematics): a quad then waits
+                    // only for programs with arrays whose elements appear in ascending order (forward kinematics): a quad then waits
                     // for at most three values. The mass matrix fills its rows out of order (H_ij and H_ji in different
                     // rows, ancestors last): holding its quads costs registers (measured 0.53 against 0.28 ms per 2^18
                     // Tello states), it keeps the chunk staging.
-                    vector_stores_ = vector_stores && n_chunked > 0 && n_imm == n_chunked;
+                    vector_stores_ = vector_stores && n_chunked > 0 && n_imm > 0;
                     if (vector_stores_)
                         stage_buffers_ = 0; // no staging buffers at all
                 }

@@ -311,9 +311,9 @@ namespace grbda_kernels
         int valid;    // number of states of this warp that exist (tail of the batch)
         int zero;     // 0 at run time, unknown at compile time (see pinAfter)
         int buf_stride; // elements between the staging buffers of consecutive output arrays (Body::STAGE_BUFFERS > 1)
-        // Body::VECTOR_STORES: position of this thread's row of output k inside the 32-byte sector grid,
-        // (state N_OUTk) mod 4 - warp-uniform by the state mapping of the shells - or -1 for a thread without a state
-        int cls[3];
+        // Body::VECTOR_STORES: this thread has a state of its own (tail threads of the last tile replay the last
+        // state with another warp's alignment class: they must not store)
+        int store;
     };
     // 256-bit store of one whole sector of the thread's own output row (SASS STG.E.256), evict-first
     __device__ __forceinline__ void storeRow4(double *p, double a, double b, double c, double d)
@@ -331,16 +331,47 @@ namespace grbda_kernels
     }
     template <typename real>
     __device__ __forceinline__ void storeRow1(real *p, real a) { __stcs(p, a); }
-    // state (row of the tile) a thread works on. Vector-store bodies: warp w takes the states w, w + 4, w + 8, ...
+    // state (row of the tile) a thread works on. Vector-store bodies: warp w takes the states w, w + 4, w + 8, ... of
+    // its group of 128, so that the position of a thread's output rows inside the 32-byte sector grid,
+    // (state N_OUTk) mod 4, is the same for the whole warp: (w N_OUTk) mod 4.
     template <typename Body, int BLOCK>
     __device__ __forceinline__ int threadState(int tid)
     {
-        // (CTAs that are not a multiple of four warps keep the identity: the class is then a per-thread value and the
-        // conditional stores diverge - correct, slower; no shipped shape does that for a vector-store body)
-        if constexpr (Body::VECTOR_STORES && BLOCK % 128 == 0)
+        if constexpr (Body::VECTOR_STORES)
+        {
+            static_assert(BLOCK % 128 == 0, "vector-store bodies need CTAs of four warps (one per alignment class)");
             return (tid & 127) / 32 + (tid & 31) * 4 + (tid & ~127);
+        }
         else
             return tid;
+    }
+    // The body of a vector-store program exists once per alignment class W = warp mod 4 (template parameter: which
+    // four consecutive values form a sector is then a compile-time fact, every instance is straight-line code
+    // without predicates and its values are computed straight into the register quads the 256-bit stores take).
+    template <typename Body, typename real, bool FAST>
+    __device__ __forceinline__ void runBody(const real *i0, const real *i1, const real *i2, real *o0, real *o1, real *o2,
+                                            const OutStage<real> &stage)
+    {
+        if constexpr (Body::VECTOR_STORES)
+        {
+            switch ((threadIdx.x >> 5) & 3)
+            {
+            case 0:
+                Body::template run<real, FAST, 0>(i0, i1, i2, o0, o1, o2, stage);
+                break;
+            case 1:
+                Body::template run<real, FAST, 1>(i0, i1, i2, o0, o1, o2, stage);
+                break;
+            case 2:
+                Body::template run<real, FAST, 2>(i0, i1, i2, o0, o1, o2, stage);
+                break;
+            default:
+                Body::template run<real, FAST, 3>(i0, i1, i2, o0, o1, o2, stage);
+                break;
+            }
+        }
+        else
+            Body::template run<real, FAST>(i0, i1, i2, o0, o1, o2, stage);
     }
     // Flush of one staged chunk: 32 states x COUNT values, COUNT * sizeof(real) contiguous bytes per
     // state. FK / H bodies flush 40-70 chunks. Two things were measured on the way: fully unrolled
@@ -419,10 +450,7 @@ namespace grbda_kernels
                                                            int ts = 0)
     {
         OutStage<real> o;
-        // ts = state of the tile this thread works on (threadState); tiles start at multiples of four states
-        o.cls[0] = ts < rows ? (ts * Body::N_OUT0) & 3 : -1;
-        o.cls[1] = ts < rows ? (ts * Body::N_OUT1) & 3 : -1;
-        o.cls[2] = ts < rows ? (ts * Body::N_OUT2) & 3 : -1;
+        o.store = ts < rows; // ts = state of the tile this thread works on (threadState)
         o.zero = (int)((uint64_t)batch >> 62); // batch < 2^62: always 0, but the compiler cannot know
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         real *buf = reinterpret_cast<real *>(stage_base) + (size_t)warp * 32 * (OUT_CHUNK + 1);
@@ -528,7 +556,7 @@ namespace grbda_kernels
                     real *o1 = Body::N_OUT1 ? out1 + state * Body::N_OUT1 : nullptr;
                     real *o2 = Body::N_OUT2 ? out2 + state * Body::N_OUT2 : nullptr;
                     if (!Body::PARKED || has_state) // parked rows are private: no tail replicas
-                        Body::template run<real, FAST>(i0, i1, i2, o0, o1, o2, stage);
+                        runBody<Body, real, FAST>(i0, i1, i2, o0, o1, o2, stage);
                     if (L::STAGE_OUT0)
                     {
                         __syncthreads();
@@ -549,8 +577,8 @@ namespace grbda_kernels
                         flags[tile] = ok ? 0 : 1;
                 }
                 if (ok)
-                    Body::template run<real, FAST>(i0, i1, i2, out0 + state * Body::N_OUT0,
-                                                   out1 + state * Body::N_OUT1, out2 + state * Body::N_OUT2, stage);
+                    runBody<Body, real, FAST>(i0, i1, i2, out0 + state * Body::N_OUT0, out1 + state * Body::N_OUT1,
+                                              out2 + state * Body::N_OUT2, stage);
             }
             if (!FAST)
                 __syncthreads(); // the shared-memory tiles are reused by the next flagged tile
@@ -799,7 +827,7 @@ namespace grbda_kernels
                 return; // CTA-uniform: the second pass recomputes this tile
         }
         if (!Body::PARKED || has_state) // parked rows are private: no tail replicas
-            Body::template run<real, true>(i0, i1, i2, o0, o1, o2, stage);
+            runBody<Body, real, true>(i0, i1, i2, o0, o1, o2, stage);
 
         if (L::STAGE_OUT0)
         {

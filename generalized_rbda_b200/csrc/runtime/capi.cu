@@ -872,7 +872,7 @@ extern "C"
             m->model.setContactPoints(pts);
             std::lock_guard<std::mutex> lock(m->jit_ext_mutex);
             if (m->jit_ext)
-                for (int a = compiler::ALGO_CONTACT_KIN; a < compiler::PROGRAM_COUNT; a++)
+                for (int a = compiler::ALGO_CONTACT_KIN; a <= compiler::ALGO_OSIM; a++)
                     for (int p = 0; p < 2; p++)
                     {
                         if (m->jit_ext->algo[a][p].library)
@@ -904,6 +904,18 @@ extern "C"
         if (m && m->model.contactPoints().empty())
             return fail(GRBDA_ERR_INVALID_ARGUMENT, "the model has no contact points (grbda_cuda_set_contact_points)");
         return launchAlgo(m, compiler::ALGO_TEST_FORCE, false, q, force, nullptr, dstate, lambda_inv, nullptr, batch, stream);
+    }
+    grbda_status grbda_cuda_inverse_dynamics_derivatives_f64(const grbda_model *m, const double *q, const double *yd,
+                                                             const double *ydd, double *dtau_dq, double *dtau_dyd,
+                                                             int64_t batch, void *stream)
+    {
+        return launchAlgo(m, compiler::ALGO_ID_DERIV, false, q, yd, ydd, dtau_dq, dtau_dyd, nullptr, batch, stream);
+    }
+    grbda_status grbda_cuda_forward_dynamics_derivatives_f64(const grbda_model *m, const double *q, const double *yd,
+                                                             const double *tau, double *dydd_dq, double *dydd_dyd,
+                                                             double *dydd_dtau, int64_t batch, void *stream)
+    {
+        return launchAlgo(m, compiler::ALGO_FD_DERIV, false, q, yd, tau, dydd_dq, dydd_dyd, dydd_dtau, batch, stream);
     }
     grbda_status grbda_cuda_inverse_osim_f64(const grbda_model *m, const double *q, double *lambda_inv, int64_t batch,
                                              void *stream)

@@ -206,10 +206,14 @@ int main(int argc, char **argv)
                     if (v.park && grbda_kernels::shapeTileBytes(n_in, n_out, 3, v.block, 8) > grbda_kernels::SLOW_PASS_STAGED_LIMIT)
                         v.park = false;
             }
+            // vector-store bodies (large outputs) need CTAs of four warps: only if every variant has them
+            bool vec_ok = true;
+            for (auto &v : variants)
+                vec_ok = vec_ok && v.block % 128 == 0;
             auto programOf = [&](const Variant &v) { return v.program >= 0 ? v.program : a; };
             auto bodyKey = [&](const Variant &v) { return (v.sync * 2 + (v.park ? 1 : 0)) * 16 + programOf(v); };
             const CompiledAlgo c = compileAlgo(model, programOf(variants[0]), true, variants[0].sync, &consts, out_chunk,
-                                               variants[0].park);
+                                               variants[0].park, vec_ok);
             std::map<int, CompiledAlgo> by_sync; // distinct (alignment period, program) bodies
             // FP32 kernels do not spill (half the register footprint) and are faster without parking
             // (measured: forward dynamics 0.386 against 0.414 ms): their launchers use the unparked body
@@ -222,10 +226,10 @@ int main(int argc, char **argv)
             for (auto &v : variants)
             {
                 if (!by_sync.count(bodyKey(v)))
-                    by_sync[bodyKey(v)] = compileAlgo(model, programOf(v), true, v.sync, &consts, out_chunk, v.park);
+                    by_sync[bodyKey(v)] = compileAlgo(model, programOf(v), true, v.sync, &consts, out_chunk, v.park, vec_ok);
                 const Variant u = f32Variant(v);
                 if (!by_sync.count(bodyKey(u))) // also the body of the direct-I/O fallback
-                    by_sync[bodyKey(u)] = compileAlgo(model, programOf(u), true, u.sync, &consts, out_chunk, false);
+                    by_sync[bodyKey(u)] = compileAlgo(model, programOf(u), true, u.sync, &consts, out_chunk, false, vec_ok);
             }
             if (a == ALGO_PHI && c.n_out[0] == 0)
                 continue; // no implicit clusters

@@ -237,6 +237,23 @@ grbda_status grbda_cuda_apply_test_force_f64(const grbda_model *m, const double 
 grbda_status grbda_cuda_inverse_osim_f64(const grbda_model *m, const double *q, double *lambda_inv, int64_t batch,
                                          void *stream);
 
+/* Derivatives of the dynamics. The reference has no closed-form derivative algorithm: it takes
+ * CasADi's jacobian() of its symbolic model with respect to a tangent-space perturbation dq of the positions, the
+ * velocities and the third argument (UnitTests/testRigidBodyDynamicsAlgosDerivatives.cpp:126-155, 339-383;
+ * q (+) dq = UnitTests/testHelpers.hpp:50-112: q + dq per one-dof coordinate, floating base
+ * [p + R^T dp; quat + 1/2 quat (x) (0, dw)] with dq = [dw; dp]; clusters with an implicit loop constraint move along
+ * the constraint manifold, dq_span = G dy). These entry points evaluate the same Jacobians, generated by
+ * differentiating the model's compiled program; all matrices are nv x nv, row-major, [i][j] = d out_i / d x_j.
+ * The programs are compiled at run time when first used.
+ *   inverse dynamics: dtau_dq, dtau_dyd  (d tau / d ydd is grbda_cuda_mass_matrix_f64)
+ *   forward dynamics: dydd_dq, dydd_dyd, dydd_dtau (= H^-1) */
+grbda_status grbda_cuda_inverse_dynamics_derivatives_f64(const grbda_model *m, const double *q, const double *yd,
+                                                         const double *ydd, double *dtau_dq, double *dtau_dyd,
+                                                         int64_t batch, void *stream);
+grbda_status grbda_cuda_forward_dynamics_derivatives_f64(const grbda_model *m, const double *q, const double *yd,
+                                                         const double *tau, double *dydd_dq, double *dydd_dyd,
+                                                         double *dydd_dtau, int64_t batch, void *stream);
+
 /* Integration step (semi-implicit Euler): yd_out = yd + dt ydd, q_out = q advanced with yd_out -
  * revolute coordinates q + dt yd; free base p + dt R v_body and ori::integrateQuat(quat, R omega_body,
  * dt) (include/grbda/Utils/OrientationTools.h:387-413); clusters with an implicit loop constraint

@@ -119,6 +119,15 @@ class OracleModel:
         _check(lib().oracle_forward_dynamics(self._h, _P(q), _P(yd), _P(tau), _P(ydd), C.c_int64(q.shape[0]), threads))
         return ydd
 
+    def dynamics_derivatives(self, q, yd, in3, forward, threads=0):
+        """Jacobians of inverse (forward=False: in3 = ydd) or forward dynamics (in3 = tau) with respect to the
+        tangent-space perturbation dq, yd and (forward only) tau; each [batch, nv, nv], [b, i, j] = d out_i / d x_j."""
+        B = q.shape[0]
+        outs = [np.zeros((B, self.nv, self.nv)) for _ in range(3 if forward else 2)]
+        _check(lib().oracle_dynamics_derivatives(self._h, int(bool(forward)), _P(q), _P(yd), _P(in3), _P(outs[0]), _P(outs[1]),
+                                                 _P(outs[2]) if forward else None, C.c_int64(B), threads))
+        return tuple(outs)
+
     def dynamics_with_external_forces(self, q, yd, in3, f_ext, forward, threads=0):
         out = np.zeros_like(in3)
         _check(lib().oracle_dynamics_with_external_forces(self._h, _P(q), _P(yd), _P(in3),

@@ -6,12 +6,14 @@
 // assembled body by body / cluster by cluster through oracle_builder_* (the same calls the
 // reference's registerBody / appendRegisteredBodiesAsCluster make), which is how the tests hand
 // URDF-derived models to the oracle.
+#include <atomic>
 #include <cstring>
 #include <ctime>
 #include <sstream>
 #include <thread>
 #include "grbda_oracle/robots.h"
 #include "grbda_oracle/rng.h"
+#include "grbda_oracle/dual.h"
 
 using namespace grbda_oracle;
 
@@ -293,8 +295,14 @@ namespace
         }
     };
 
+    inline uint64_t nextUid()
+    {
+        static std::atomic<uint64_t> n{1};
+        return n++;
+    }
     struct Handle
     {
+        uint64_t uid = nextUid(); // identity for per-thread caches (a freed handle's address may be reused)
         ModelSpec spec;
         std::unique_ptr<ClusterTreeModel<double>> model; // instance 0 (sizes, introspection)
         std::vector<std::unique_ptr<ClusterTreeModel<double>>> workers;
@@ -830,6 +838,78 @@ extern "C"
             OpCounts c = op_counts();
             out[0] = c.add_all; out[1] = c.mul_all; out[2] = c.div_all; out[3] = c.sqrt_all; out[4] = c.trig_all;
             out[5] = c.add_alg; out[6] = c.mul_alg; out[7] = c.div_alg; out[8] = c.sqrt_alg; out[9] = c.trig_alg; });
+    }
+
+    // ---- derivatives (test infrastructure for grbda_cuda_{inverse,forward}_dynamics_derivatives_f64) -------
+    // The reference test's Jacobians (testRigidBodyDynamicsAlgosDerivatives.cpp:126-155): derivative of the third
+    // argument's counterpart with respect to a tangent-space perturbation dq (testHelpers.hpp:50-112 `plus`), the
+    // velocities and (forward dynamics) tau, by forward-mode dual arithmetic through the restated algorithms.
+    // mode 0: out0 = d ID / d dq, out1 = d ID / d yd               (in3 = ydd)
+    // mode 1: out0 = d FD / d dq, out1 = d FD / d yd, out2 = d FD / d tau   (in3 = tau)
+    // all nv x nv row-major, [i][j] = d out_i / d x_j. Clusters with an implicit constraint move along the
+    // constraint manifold (dq_span = G dy; the reference test leaves them out).
+    int oracle_dynamics_derivatives(void *hv, int mode, const double *q, const double *yd, const double *in3, double *out0,
+                                    double *out1, double *out2, int64_t batch, int threads)
+    {
+        Handle *h = (Handle *)hv;
+        const int nq = h->model->getNumPositions(), nv = h->model->getNumDegreesOfFreedom();
+        return runBatch(h, batch, threads, [&](ClusterTreeModel<double> &m, int64_t b)
+                        {
+            static thread_local std::unique_ptr<ClusterTreeModel<Dual>> md;
+            static thread_local uint64_t owner = 0;
+            if (owner != h->uid)
+            {
+                md.reset(new ClusterTreeModel<Dual>(h->spec.instantiate<Dual>()));
+                owner = h->uid;
+            }
+            const double *qb = q + b * nq, *ydb = yd + b * nv, *xb = in3 + b * nv;
+            // tangent map T (nq x nv) at this state
+            m.setState(toVec(qb, nq), toVec(ydb, nv));
+            m.forwardKinematics();
+            std::vector<double> T((size_t)nq * nv, 0.0);
+            for (auto &n : m.nodes)
+            {
+                const int pi = n->position_index, vi = n->velocity_index;
+                if (std::string(n->joint->typeName()) == "Free" && n->num_positions == 7)
+                {
+                    Mat<double> quat(4, 1);
+                    for (int i = 0; i < 4; i++) quat[i] = qb[pi + 3 + i];
+                    const Mat<double> R = quaternionToRotationMatrix(quat);
+                    for (int k = 0; k < 3; k++)
+                    {
+                        const double w[4] = {0.0, k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0};
+                        const double qq[4] = {quat[0], quat[1], quat[2], quat[3]};
+                        double prod[4];
+                        quatProduct(qq, w, prod);
+                        for (int r = 0; r < 4; r++) T[(size_t)(pi + 3 + r) * nv + vi + k] = 0.5 * prod[r];
+                        for (int r = 0; r < 3; r++) T[(size_t)(pi + r) * nv + vi + 3 + k] = R(k, r); // R^T e_k
+                    }
+                }
+                else if (n->joint->loop_constraint->isImplicit())
+                {
+                    const Mat<double> &G = n->joint->G();
+                    for (int i = 0; i < n->num_positions; i++)
+                        for (int k = 0; k < n->num_velocities; k++)
+                            T[(size_t)(pi + i) * nv + vi + k] = G(i, k);
+                }
+                else
+                    for (int k = 0; k < n->num_velocities; k++)
+                        T[(size_t)(pi + k) * nv + vi + k] = 1.0;
+            }
+            Mat<Dual> qd(nq, 1), ydd(nv, 1), xd(nv, 1);
+            const int n_kinds = mode == 0 ? 2 : 3;
+            double *outs[3] = {out0, out1, out2};
+            for (int kind = 0; kind < n_kinds; kind++)
+                for (int j = 0; j < nv; j++)
+                {
+                    for (int i = 0; i < nq; i++) qd[i] = Dual(qb[i], kind == 0 ? T[(size_t)i * nv + j] : 0.0);
+                    for (int i = 0; i < nv; i++) ydd[i] = Dual(ydb[i], kind == 1 && i == j ? 1.0 : 0.0);
+                    for (int i = 0; i < nv; i++) xd[i] = Dual(xb[i], kind == 2 && i == j ? 1.0 : 0.0);
+                    md->setState(qd, ydd);
+                    const Mat<Dual> r = mode == 0 ? md->inverseDynamics(xd) : md->forwardDynamics(xd);
+                    for (int i = 0; i < nv; i++)
+                        outs[kind][(size_t)b * nv * nv + (size_t)i * nv + j] = r[i].d;
+                } });
     }
 
     int oracle_max_threads() { return resolveThreads(0); }
