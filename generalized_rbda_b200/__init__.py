@@ -532,7 +532,7 @@ class ClusterTreeModel:
         dv = torch.empty_like(dq)
         _check(_lib.grbda_cuda_inverse_dynamics_derivatives_f64(self._h, _ptr(q), _ptr(yd), _ptr(ydd), _ptr(dq), _ptr(dv),
                                                                 q.shape[0], _stream()))
-        return dq, dv
+        return dq.transpose(1, 2), dv.transpose(1, 2)  # the library writes column-major matrices
 
     def forwardDynamicsDerivatives(self, q, yd, tau):
         """(dydd_dq, dydd_dyd, dydd_dtau), each [batch, nv, nv]; dydd_dtau = H^-1."""
@@ -543,7 +543,7 @@ class ClusterTreeModel:
         dv, dt = torch.empty_like(dq), torch.empty_like(dq)
         _check(_lib.grbda_cuda_forward_dynamics_derivatives_f64(self._h, _ptr(q), _ptr(yd), _ptr(tau), _ptr(dq), _ptr(dv),
                                                                 _ptr(dt), q.shape[0], _stream()))
-        return dq, dv, dt
+        return dq.transpose(1, 2), dv.transpose(1, 2), dt.transpose(1, 2)
 
     def integrate(self, q, yd, ydd, dt, out=None):
         """(q', yd', flags): semi-implicit Euler step, quaternion base by ori::integrateQuat, implicit clusters

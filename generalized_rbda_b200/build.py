@@ -136,7 +136,13 @@ def build(verbose=True, jobs=None, models=None):
 
     # 2. generate
     gen_sources = []
+    # experiments: GRBDA_VARIANTS="fk=T,128,2;T,256,1|h=..." replaces the variant lists of the named entry points
+    override = dict(seg.split("=", 1) for seg in os.environ.get("GRBDA_VARIANTS", "").split("|") if "=" in seg)
     for name, (algos, variants, f32) in models.items():
+        if override:
+            segs = dict(seg.split("=", 1) for seg in variants.split("|"))
+            segs.update(override)
+            variants = "|".join("%s=%s" % kv for kv in segs.items())
         cmd = [modelc, "--model", name, "--urdf-dir", URDF_DIR, "--out", GEN, "--algos", algos,
                "--variants", variants, "--sync-every", str(SYNC_EVERY)]
         if not f32:

@@ -756,7 +756,9 @@ namespace grbda
 
             // ---------------------------------------------------------------------------------
             // derivatives of the inverse dynamics: d tau / d dq and d tau / d yd, both nv x nv,
-            // row-major [i][j] = d tau_i / d x_j. (d tau / d ydd is the mass matrix.)
+            // COLUMN-major (as Eigen and CasADi store the reference's Jacobians): element [j * nv + i] = d tau_i / d x_j;
+            // a column is one tangent sweep, so the outputs of the program complete column by column.
+            // (d tau / d ydd is the mass matrix.)
             // dq is the tangent-space perturbation of the reference's derivative test
             // (UnitTests/testHelpers.hpp:50-112, `plus`): q + dq for every one-dof coordinate; floating base
             // [p; quat] (+) [dw; dp] = [p + R^T dp; quat + 1/2 quat (x) (0, dw)] with R the rotation of
@@ -818,12 +820,12 @@ namespace grbda
                         seed[Sym::input(IN_Q, kv.first).id] = kv.second;
                     const std::vector<Sym> col = tangentSweep(tau, seed);
                     for (int i = 0; i < nv; i++)
-                        dtau_dq[i * nv + j] = col[i];
+                        dtau_dq[j * nv + i] = col[i];
                     seed.clear();
                     seed[inYd(j).id] = Sym(1.0);
                     const std::vector<Sym> col_v = tangentSweep(tau, seed);
                     for (int i = 0; i < nv; i++)
-                        dtau_dyd[i * nv + j] = col_v[i];
+                        dtau_dyd[j * nv + i] = col_v[i];
                 }
             }
 
@@ -858,11 +860,11 @@ namespace grbda
                 {
                     std::vector<Sym> bq(nv), bv(nv), e(nv, Sym(0.0));
                     for (int i = 0; i < nv; i++)
-                        bq[i] = -all[i * nv + j], bv[i] = -all[nv * nv + i * nv + j];
+                        bq[i] = -all[j * nv + i], bv[i] = -all[nv * nv + j * nv + i];
                     e[j] = Sym(1.0);
                     const std::vector<Sym> xq = solveMassMatrix(bq), xv = solveMassMatrix(bv), xe = solveMassMatrix(e);
                     for (int i = 0; i < nv; i++)
-                        dydd_dq[i * nv + j] = xq[i], dydd_dyd[i * nv + j] = xv[i], dydd_dtau[i * nv + j] = xe[i];
+                        dydd_dq[j * nv + i] = xq[i], dydd_dyd[j * nv + i] = xv[i], dydd_dtau[j * nv + i] = xe[i];
                 }
             }
 

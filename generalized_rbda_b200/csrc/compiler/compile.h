@@ -29,7 +29,7 @@ namespace grbda
             ALGO_CONTACT_JAC = 9,  // in: q              out: J[n_cp][6][nv] (world frame, [angular; linear])
             ALGO_TEST_FORCE = 10,  // in: q, f[3 n_cp]   out: dstate[n_cp][nv], lambda_inv[n_cp]
             ALGO_OSIM = 11,        // in: q              out: Lambda^-1 [6 n_ee][6 n_ee]
-            // derivatives (compiled at run time when first used): row-major [i][j] = d out_i / d x_j,
+            // derivatives (compiled at run time when first used): column-major, [j nv + i] = d out_i / d x_j,
             // dq = tangent-space perturbation of the positions (ModelCompiler::positionTangentMap)
             ALGO_ID_DERIV = 12,    // in: q, yd, ydd     out: dtau/ddq [nv nv], dtau/dyd [nv nv]
             ALGO_FD_DERIV = 13,    // in: q, yd, tau     out: dydd/ddq [nv nv], dydd/dyd [nv nv], dydd/dtau = H^-1 [nv nv]
@@ -297,8 +297,7 @@ namespace grbda
                   "*__restrict__ in0, const real *__restrict__ in1,\n        const real *__restrict__ in2)\n    {\n"
                   "#define KC(x) ((real)(x))\n#define IN0(i) in0[i]\n#define IN1(i) in1[i]\n#define IN2(i) in2[i]\n"
                   "        return " << c.range_check << ";\n#undef KC\n#undef IN0\n#undef IN1\n#undef IN2\n    }\n";
-            // vector-store bodies: W = alignment class of the warp (state mod 4), kernels/batched_kernel.cuh runBody
-            os << "    template <typename real, bool FAST" << (c.vector_stores ? ", int W" : "") << ">\n";
+            os << "    template <typename real, bool FAST>\n";
             if (c.parked)
                 // the thread's rows are read AND written (parking): no __restrict__, one pointer per row
                 os << "    static __device__ __forceinline__ void run(const real *in0, const real *in1, const real *in2,\n"
@@ -318,9 +317,9 @@ namespace grbda
                       "#define PARK_ST(t, i, x)\n#define PARK_LD(t, i) KC(0.0)\n";
             os << "#define KC(x) ((real)(x))\n#define KT(i) kc_table<real>(i)\n"
                   "#define OUT1(i, x) out1[i] = (x)\n#define OUT2(i, x) out2[i] = (x)\n"
-                  "#define GRBDA_ALIGN() __syncwarp()\n#define GRBDA_PIN(x, late) GRBDA_PIN_IMPL(x, late, stage.zero)\n"
-                  "#define STGV4(k, m, base, a, b, c, d) if (((W * N_OUT##k) & 3) == (m) && stage.store) storeRow4(out##k + (base), a, b, c, d)\n"
-                  "#define STGV1(k, m, base, a) if (((W * N_OUT##k) & 3) == (m) && stage.store) storeRow1(out##k + (base), a)\n"
+                  "#define GRBDA_ALIGN() " << (std::getenv("GRBDA_ALIGN_CTA") ? "__syncthreads()" : "__syncwarp()") << "\n#define GRBDA_PIN(x, late) GRBDA_PIN_IMPL(x, late, stage.zero)\n"
+                  "#define STGV4(k, m, base, a, b, c, d) if (stage.cls[k] == (m)) storeRow4(out##k + (base), a, b, c, d)\n"
+                  "#define STGV1(k, m, base, a) if (stage.cls[k] == (m)) storeRow1(out##k + (base), a)\n"
                   "#define STG_PUT(j, x) stage.lane[j] = (x)\n"
                   "#define STG_PUTK(k, j, x) stage.lane[(k) * stage.buf_stride + (j)] = (x)\n"
                   "#define STG_FLUSHI0(base, count) flushChunk<real, N_OUT0, count>(stage.g[0], base, stage.warp, stage.valid)\n"

@@ -30,6 +30,7 @@ namespace grbda_std
 }
 #else
 #include <algorithm>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <type_traits>
@@ -298,6 +299,44 @@ namespace grbda_kernels
         }
     }
 
+    // ---- programmatic dependent launch ------------------------------------------------------------
+    // Every call is two launches (fast kernel + flagged-tile pass) and calls follow each other on one stream
+    // (forward dynamics, then inverse dynamics ...). The kernels are launched with the programmatic stream
+    // serialization attribute: a kernel's launch (CTA scheduling, parameter set-up) overlaps the tail of its
+    // predecessor instead of waiting for its completion. Every kernel waits (griddepcontrol.wait: predecessor
+    // complete and its memory visible) before it touches global memory, and releases its successor once its
+    // compute is done (griddepcontrol.launch_dependents; an exiting CTA counts as released). A predecessor that is
+    // not one of these kernels never releases early: plain stream order. GRBDA_NO_PDL=1 turns the attribute off.
+    __device__ __forceinline__ void gridDependencyWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+    __device__ __forceinline__ void gridLaunchDependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifndef __CUDACC_RTC__
+    inline bool usePdl()
+    {
+        static const bool on = !(std::getenv("GRBDA_NO_PDL") && std::getenv("GRBDA_NO_PDL")[0] == '1');
+        return on;
+    }
+    inline void pdlConfig(cudaLaunchConfig_t &cfg, cudaLaunchAttribute &attr, unsigned grid, unsigned block, size_t smem,
+                          cudaStream_t stream)
+    {
+        cfg = cudaLaunchConfig_t();
+        cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = usePdl() ? 1 : 0;
+    }
+    template <typename real>
+    cudaError_t launchShell(void (*kernel)(const real *, const real *, const real *, real *, real *, real *, int64_t, unsigned char *),
+                            unsigned grid, unsigned block, size_t smem, cudaStream_t stream, const real *in0, const real *in1,
+                            const real *in2, real *out0, real *out1, real *out2, int64_t batch, unsigned char *flags)
+    {
+        cudaLaunchConfig_t cfg;
+        cudaLaunchAttribute attr;
+        pdlConfig(cfg, attr, grid, block, smem, stream);
+        return cudaLaunchKernelEx(&cfg, kernel, in0, in1, in2, out0, out1, out2, batch, flags);
+    }
+#endif
+
     // ---- chunked output staging (kernels with large outputs: FK, H) ------------------------------
     // The generated body hands over `COUNT` consecutive elements of one output array for the 32
     // states of the warp through the warp's staging buffer; this writes them with coalesced stores
@@ -311,9 +350,10 @@ namespace grbda_kernels
         int valid;    // number of states of this warp that exist (tail of the batch)
         int zero;     // 0 at run time, unknown at compile time (see pinAfter)
         int buf_stride; // elements between the staging buffers of consecutive output arrays (Body::STAGE_BUFFERS > 1)
-        // Body::VECTOR_STORES: this thread has a state of its own (tail threads of the last tile replay the last
-        // state with another warp's alignment class: they must not store)
-        int store;
+        // Body::VECTOR_STORES: position of this thread's row of output k inside the 32-byte sector grid,
+        // (state N_OUTk) mod 4 - warp-uniform by the state mapping of the shells (threadState) - or -1 for a thread
+        // without a state of its own (tail of the last tile)
+        int cls[3];
     };
     // 256-bit store of one whole sector of the thread's own output row (SASS STG.E.256), evict-first
     __device__ __forceinline__ void storeRow4(double *p, double a, double b, double c, double d)
@@ -345,33 +385,14 @@ namespace grbda_kernels
         else
             return tid;
     }
-    // The body of a vector-store program exists once per alignment class W = warp mod 4 (template parameter: which
-    // four consecutive values form a sector is then a compile-time fact, every instance is straight-line code
-    // without predicates and its values are computed straight into the register quads the 256-bit stores take).
+    // (Measured alternative, profiles/README.md: one instance of the body per alignment class - template parameter,
+    // no predicates, a quarter of the store instructions per warp - is SLOWER: the four instruction streams of a CTA
+    // quadruple the instruction-cache footprint of a kernel that is bound by instruction fetch.)
     template <typename Body, typename real, bool FAST>
     __device__ __forceinline__ void runBody(const real *i0, const real *i1, const real *i2, real *o0, real *o1, real *o2,
                                             const OutStage<real> &stage)
     {
-        if constexpr (Body::VECTOR_STORES)
-        {
-            switch ((threadIdx.x >> 5) & 3)
-            {
-            case 0:
-                Body::template run<real, FAST, 0>(i0, i1, i2, o0, o1, o2, stage);
-                break;
-            case 1:
-                Body::template run<real, FAST, 1>(i0, i1, i2, o0, o1, o2, stage);
-                break;
-            case 2:
-                Body::template run<real, FAST, 2>(i0, i1, i2, o0, o1, o2, stage);
-                break;
-            default:
-                Body::template run<real, FAST, 3>(i0, i1, i2, o0, o1, o2, stage);
-                break;
-            }
-        }
-        else
-            Body::template run<real, FAST>(i0, i1, i2, o0, o1, o2, stage);
+        Body::template run<real, FAST>(i0, i1, i2, o0, o1, o2, stage);
     }
     // Flush of one staged chunk: 32 states x COUNT values, COUNT * sizeof(real) contiguous bytes per
     // state. FK / H bodies flush 40-70 chunks. Two things were measured on the way: fully unrolled
@@ -450,7 +471,10 @@ namespace grbda_kernels
                                                            int ts = 0)
     {
         OutStage<real> o;
-        o.store = ts < rows; // ts = state of the tile this thread works on (threadState)
+        // ts = state of the tile this thread works on (threadState); tiles start at multiples of four states
+        o.cls[0] = ts < rows ? (ts * Body::N_OUT0) & 3 : -1;
+        o.cls[1] = ts < rows ? (ts * Body::N_OUT1) & 3 : -1;
+        o.cls[2] = ts < rows ? (ts * Body::N_OUT2) & 3 : -1;
         o.zero = (int)((uint64_t)batch >> 62); // batch < 2^62: always 0, but the compiler cannot know
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         real *buf = reinterpret_cast<real *>(stage_base) + (size_t)warp * 32 * (OUT_CHUNK + 1);
@@ -498,6 +522,7 @@ namespace grbda_kernels
     {
         using L = TileLayout<Body, real, BLOCK>;
         extern __shared__ __align__(16) unsigned char smem_raw[];
+        gridDependencyWait();
         const int64_t num_tiles = (batch + BLOCK - 1) / BLOCK;
         // FAST: one tile per CTA (grid = number of tiles). !FAST: a few CTAs scan the flags the FAST
         // kernel left and recompute the flagged tiles with the library forms.
@@ -584,6 +609,7 @@ namespace grbda_kernels
                 __syncthreads(); // the shared-memory tiles are reused by the next flagged tile
             tile++;
         } while (!FAST && tile < tile_end);
+        gridLaunchDependents();
     }
 
 #ifndef __CUDACC_RTC__
@@ -619,12 +645,12 @@ namespace grbda_kernels
                 return e;
         }
         const int64_t grid = (tiles + BLOCK - 1) / BLOCK;
-        kernel<<<(unsigned)grid, BLOCK, SMEM, a.stream>>>(
-            (const real *)a.in[0], (const real *)a.in[1], (const real *)a.in[2], (real *)a.out[0],
-            (real *)a.out[1], (real *)a.out[2], a.batch, flags);
+        const cudaError_t e = launchShell<real>(kernel, (unsigned)grid, BLOCK, SMEM, a.stream, (const real *)a.in[0],
+                                                (const real *)a.in[1], (const real *)a.in[2], (real *)a.out[0],
+                                                (real *)a.out[1], (real *)a.out[2], a.batch, flags);
         if (a.launched)
             ++*a.launched;
-        return cudaGetLastError();
+        return e;
     }
 
     template <typename real, typename Body, int BLOCK, int MIN_BLOCKS, bool STAGED>
@@ -647,10 +673,8 @@ namespace grbda_kernels
         cudaError_t e = acquireFlags<Body>(a, grid, &flags);
         if (e != cudaSuccess)
             return e;
-        kernel<<<(unsigned)grid, BLOCK, smem, a.stream>>>(
-            (const real *)a.in[0], (const real *)a.in[1], (const real *)a.in[2], (real *)a.out[0],
-            (real *)a.out[1], (real *)a.out[2], a.batch, flags);
-        e = cudaGetLastError();
+        e = launchShell<real>(kernel, (unsigned)grid, BLOCK, smem, a.stream, (const real *)a.in[0], (const real *)a.in[1],
+                              (const real *)a.in[2], (real *)a.out[0], (real *)a.out[1], (real *)a.out[2], a.batch, flags);
         if (a.launched)
             ++*a.launched;
         const cudaError_t e2 = launchSlowPass<real, Body, BLOCK, MIN_BLOCKS>(a, grid, flags);
@@ -797,6 +821,7 @@ namespace grbda_kernels
         if (tid == 0)
             mbarInit(bar, BLOCK);
         __syncthreads();
+        gridDependencyWait();
         {
             const real *g0 = in0 + first * Body::N_IN0, *g1 = in1 + first * Body::N_IN1, *g2 = in2 + first * Body::N_IN2;
             const uint32_t bytes = tmaTileBytes<real, Body::N_IN0>(tid, rows) + tmaTileBytes<real, Body::N_IN1>(tid, rows) +
@@ -828,6 +853,7 @@ namespace grbda_kernels
         }
         if (!Body::PARKED || has_state) // parked rows are private: no tail replicas
             runBody<Body, real, true>(i0, i1, i2, o0, o1, o2, stage);
+        gridLaunchDependents();
 
         if (L::STAGE_OUT0)
         {
@@ -881,10 +907,8 @@ namespace grbda_kernels
         cudaError_t e = acquireFlags<Body>(a, grid, &flags);
         if (e != cudaSuccess)
             return e;
-        kernel<<<(unsigned)grid, BLOCK, L::BYTES, a.stream>>>(
-            (const real *)a.in[0], (const real *)a.in[1], (const real *)a.in[2], (real *)a.out[0],
-            (real *)a.out[1], (real *)a.out[2], a.batch, flags);
-        e = cudaGetLastError();
+        e = launchShell<real>(kernel, (unsigned)grid, BLOCK, L::BYTES, a.stream, (const real *)a.in[0], (const real *)a.in[1],
+                              (const real *)a.in[2], (real *)a.out[0], (real *)a.out[1], (real *)a.out[2], a.batch, flags);
         if (a.launched)
             ++*a.launched;
         const cudaError_t e2 = launchSlowPass<real, Body, BLOCK, MIN_BLOCKS>(a, grid, flags);

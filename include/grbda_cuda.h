@@ -243,7 +243,8 @@ grbda_status grbda_cuda_inverse_osim_f64(const grbda_model *m, const double *q, 
  * q (+) dq = UnitTests/testHelpers.hpp:50-112: q + dq per one-dof coordinate, floating base
  * [p + R^T dp; quat + 1/2 quat (x) (0, dw)] with dq = [dw; dp]; clusters with an implicit loop constraint move along
  * the constraint manifold, dq_span = G dy). These entry points evaluate the same Jacobians, generated by
- * differentiating the model's compiled program; all matrices are nv x nv, row-major, [i][j] = d out_i / d x_j.
+ * differentiating the model's compiled program; all matrices are nv x nv, COLUMN-major as Eigen / CasADi store
+ * them: element [j * nv + i] = d out_i / d x_j (one contiguous column per perturbed coordinate).
  * The programs are compiled at run time when first used.
  *   inverse dynamics: dtau_dq, dtau_dyd  (d tau / d ydd is grbda_cuda_mass_matrix_f64)
  *   forward dynamics: dydd_dq, dydd_dyd, dydd_dtau (= H^-1) */

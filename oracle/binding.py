@@ -248,6 +248,12 @@ class OracleBuilder:
         lib().oracle_builder_append_generic_loops(self._h, name.encode(), (C.c_int * len(axes))(*axes),
                                                   (C.c_int * len(axes))(*[int(x) for x in independent]))
 
+    def append_four_bar(self, name, axes, path1, path2, offset, independent_coordinate):
+        """ClusterJoints::FourBar with the analytic LoopConstraint::FourBar (FourBarJoint.cpp:7-199)."""
+        p1, p2, off = (np.ascontiguousarray(x, dtype=np.float64) for x in (path1, path2, offset))
+        lib().oracle_builder_append_four_bar(self._h, name.encode(), (C.c_int * len(axes))(*axes), _P(p1), len(p1),
+                                             _P(p2), len(p2), _P(off), int(independent_coordinate))
+
     def append_generic_phi(self, name, axes, independent, ops, outputs):
         """ops: structured array with fields op, a, b, val (generalized_rbda_b200.PHI_OP_DTYPE)"""
         ci = lambda x: np.ascontiguousarray(x, dtype=np.int32)

@@ -182,6 +182,143 @@ namespace grbda_oracle
         }
     };
 
+    // reference: FourBarJoint.cpp:7-199 (LoopConstraint::FourBar): planar four-bar linkage, spanning coordinates
+    // {path-1 joint 0, path-2 joint 0, path-1 joint 1}. The reference codes K, G, k and g in closed form; they are
+    // restated the same way (NOT through the Taylor arithmetic of GenericImplicit), so a model built on this
+    // constraint checks the generic loop machinery independently.
+    template <typename T>
+    struct FourBarConstraint : LoopConstraintBase<T>
+    {
+        std::vector<T> l1, l2; // path link lengths (two links on path 1, one on path 2)
+        T off[2];
+        int independent_coordinate;
+        Mat<T> map;    // indepenent_coordinate_map_ (FourBarJoint.cpp:57-77)
+        Mat<T> Kd_mat; // dependent columns of K at the last updateJacobians()
+
+        FourBarConstraint(const std::vector<T> &path1, const std::vector<T> &path2, T off_x, T off_y, int ind)
+            : l1(path1), l2(path2), independent_coordinate(ind), map(3, 3)
+        {
+            if (l1.size() + l2.size() != 3 || l1.size() != 2)
+                throw std::runtime_error("FourBar: Must contain 3 links");
+            off[0] = off_x, off[1] = off_y;
+            this->G = Mat<T>(3, 1);
+            this->g = Mat<T>(3, 1);
+            this->K = Mat<T>(2, 3);
+            this->k = Mat<T>(2, 1);
+            const int rows[3][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}}; // row r of the map has its 1 in column rows[ind][r]
+            if (ind < 0 || ind > 2)
+                throw std::runtime_error("FourBar: Invalid independent coordinate");
+            for (int r = 0; r < 3; r++)
+                map(r, rows[ind][r]) = T(1.0);
+        }
+        bool isImplicit() const override { return true; }
+        Mat<T> gamma(const Mat<T> &) const override { throw std::runtime_error("FourBar::gamma() not implemented"); }
+        // FourBarJoint.cpp:22-50
+        Mat<T> phi(const Mat<T> &q) const override
+        {
+            const T q1[2] = {q[0], q[2]}, q2[1] = {q[1]};
+            T a(0.0), p1x(0.0), p1y(0.0);
+            for (int i = 0; i < 2; i++)
+            {
+                a = a + q1[i];
+                p1x = p1x + l1[i] * cos(a);
+                p1y = p1y + l1[i] * sin(a);
+            }
+            a = T(0.0);
+            T p2x = off[0], p2y = off[1];
+            for (int i = 0; i < 1; i++)
+            {
+                a = a + q2[i];
+                p2x = p2x + l2[i] * cos(a);
+                p2y = p2y + l2[i] * sin(a);
+            }
+            Mat<T> out(2, 1);
+            out[0] = p1x - p2x, out[1] = p1y - p2y;
+            return out;
+        }
+        // FourBarJoint.cpp:81-146
+        void updateJacobians(const Mat<T> &q) override
+        {
+            const T q1[2] = {q[0], q[2]}, q2[1] = {q[1]};
+            Mat<T> K1(2, 2), K2(2, 1);
+            T a(0.0);
+            for (int i = 0; i < 2; i++)
+            {
+                a = a + q1[i];
+                for (int j = 0; j <= i; j++)
+                {
+                    K1(0, j) = K1(0, j) - l1[i] * sin(a);
+                    K1(1, j) = K1(1, j) + l1[i] * cos(a);
+                }
+            }
+            a = T(0.0);
+            for (int i = 0; i < 1; i++)
+            {
+                a = a + q2[i];
+                for (int j = 0; j <= i; j++)
+                {
+                    K2(0, j) = K2(0, j) + l2[i] * sin(a);
+                    K2(1, j) = K2(1, j) - l2[i] * cos(a);
+                }
+            }
+            for (int r = 0; r < 2; r++)
+                this->K(r, 0) = K1(r, 0), this->K(r, 1) = K2(r, 0), this->K(r, 2) = K1(r, 1);
+            Mat<T> Ki(2, 1);
+            Kd_mat = Mat<T>(2, 2);
+            int dep = 0;
+            for (int i = 0; i < 3; i++)
+            {
+                if (i == independent_coordinate)
+                    Ki(0, 0) = this->K(0, i), Ki(1, 0) = this->K(1, i);
+                else
+                {
+                    Kd_mat(0, dep) = this->K(0, i), Kd_mat(1, dep) = this->K(1, i);
+                    dep++;
+                }
+            }
+            const Mat<T> Gd = -solve(Kd_mat, Ki);
+            Mat<T> Gt(3, 1);
+            Gt[0] = T(1.0), Gt[1] = Gd[0], Gt[2] = Gd[1];
+            this->G = map * Gt;
+        }
+        // FourBarJoint.cpp:148-199
+        void updateBiases(const Mat<T> &q, const Mat<T> &qd) override
+        {
+            const T q1[2] = {q[0], q[2]}, q2[1] = {q[1]}, qd1[2] = {qd[0], qd[2]}, qd2[1] = {qd[1]};
+            Mat<T> Kd1(2, 2), Kd2(2, 1);
+            T a(0.0), w(0.0);
+            for (int i = 0; i < 2; i++)
+            {
+                a = a + q1[i];
+                w = w + qd1[i];
+                for (int j = 0; j <= i; j++)
+                {
+                    Kd1(0, j) = Kd1(0, j) - l1[i] * w * cos(a);
+                    Kd1(1, j) = Kd1(1, j) - l1[i] * w * sin(a);
+                }
+            }
+            a = T(0.0), w = T(0.0);
+            for (int i = 0; i < 1; i++)
+            {
+                a = a + q2[i];
+                w = w + qd2[i];
+                for (int j = 0; j <= i; j++)
+                {
+                    Kd2(0, j) = Kd2(0, j) + l2[i] * w * cos(a);
+                    Kd2(1, j) = Kd2(1, j) + l2[i] * w * sin(a);
+                }
+            }
+            Mat<T> Kdot(2, 3);
+            for (int r = 0; r < 2; r++)
+                Kdot(r, 0) = Kd1(r, 0), Kdot(r, 1) = Kd2(r, 0), Kdot(r, 2) = Kd1(r, 1);
+            this->k = -(Kdot * qd);
+            const Mat<T> gd = solve(Kd_mat, this->k);
+            Mat<T> gt(3, 1);
+            gt[0] = T(0.0), gt[1] = gd[0], gt[2] = gd[1];
+            this->g = map * gt;
+        }
+    };
+
     ////////////////////////////////////////////////////////////////////////////////////////////
     // Single joints  (reference: include/grbda/Dynamics/Joints/Joint.h:43-102)
     ////////////////////////////////////////////////////////////////////////////////////////////

@@ -487,6 +487,73 @@ namespace grbda_oracle
     ////////////////////////////////////////////////////////////////////////////////////////////
     // Uniform serial chains (RevoluteChainWithRotor.cpp:45-109, RevolutePairChainWithRotor.cpp:62-128)
     ////////////////////////////////////////////////////////////////////////////////////////////
+    ////////////////////////////////////////////////////////////////////////////////////////////
+    // MIT_Humanoid_Leg (src/Robots/MIT_Humanoid_Leg.cpp:6-164): one leg of the MIT humanoid on a fixed base,
+    // with the raw (unsigned) constants of MIT_Humanoid.hpp:19-65,74-143 and MASSLESS rotors (:25,52,77,104,117).
+    // The reference compares it with robot-models/mit_humanoid_leg.urdf (UnitTests/testClusterTreeModel.cpp:100-113).
+    ////////////////////////////////////////////////////////////////////////////////////////////
+    template <typename T>
+    ClusterTreeModel<T> buildMitHumanoidLeg()
+    {
+        ClusterTreeModel<T> model;
+        const Mat<T> I3 = Mat<T>::Identity(3);
+        Mat<T> hipRzRotI = mat3<T>({0.0015373, 0.0000011, 0.0005578, 0.0000011, 0.0014252,
+                                   0.0000024, 0.0005578, 0.0000024, 0.0012028});
+        Mat<T> hipRxRotI = mat3<T>({0.0017535, -0.0000063, -0.000080, -0.0000063, 0.003338,
+                                   -0.000013, -0.000080, -0.000013, 0.0019927});
+        Mat<T> hipRyRotI = mat3<T>({0.0243761, 0.0000996, 0.0006548, 0.0000996, 0.0259015,
+                                   0.0026713, 0.0006548, 0.0026713, 0.0038929});
+        Mat<T> kneeRotI = mat3<T>({0.003051, 0.000000, 0.0000873, 0.000000, 0.003033, 0.0000393,
+                                  0.0000873, 0.0000393, 0.0002529});
+        Mat<T> ankleRotI = mat3<T>({0.0000842, 0.000000, -0.0000488, 0.000000, 0.0007959,
+                                   -0.000000, -0.0000488, -0.000000, 0.0007681});
+        Mat<T> largeRotorZ = mat3<T>({3.443e-4, 0, 0, 0, 3.443e-4, 0, 0, 0, 5.548e-4});
+        Mat<T> smallRotorZ = mat3<T>({1.084e-4, 0, 0, 0, 1.084e-4, 0, 0, 0, 1.6841e-4});
+        Mat<T> RY = coordinateRotation<T>(Axis::Y, T(M_PI / 2));
+        Mat<T> RX = coordinateRotation<T>(Axis::X, T(-M_PI / 2));
+        Mat<T> smallRotorX = RY.transpose() * smallRotorZ * RY;
+        Mat<T> smallRotorY = RX.transpose() * smallRotorZ * RX;
+        Mat<T> largeRotorY = RX.transpose() * largeRotorZ * RX;
+        Mat<T> zero3 = V3<T>(0, 0, 0);
+        const double hipRzPitch = -0.174533, hipRxPitch = 0.436332;
+        const double hipRyPitch = -(hipRxPitch + hipRzPitch);
+
+        Mat<T> Xrot_HipZ = coordinateRotation<T>(Axis::Y, T(hipRzPitch));
+        appendRevoluteWithRotor<T>(model, "hip_rz", "hip_rz_link", "hip_rz_rotor", "ground",
+                                   spatialInertia<T>(T(0.84563), V3<T>(-0.064842, -0.000036, -0.063090), hipRzRotI),
+                                   spatialInertia<T>(T(0.0), zero3, smallRotorZ),
+                                   Transform<T>(Xrot_HipZ, V3<T>(-0.00565, -0.082, -0.05735)),
+                                   Transform<T>(Xrot_HipZ, V3<T>(-0.00842837, -0.082, -0.041593)), Axis::Z, Axis::Z, 6.0);
+        Mat<T> Xrot_HipX = coordinateRotation<T>(Axis::Y, T(hipRxPitch));
+        appendRevoluteWithRotor<T>(model, "hip_rx", "hip_rx_link", "hip_rx_rotor", "hip_rz_link",
+                                   spatialInertia<T>(T(1.20868), V3<T>(0.067232, -0.013018, 0.0001831), hipRxRotI),
+                                   spatialInertia<T>(T(0.0), zero3, smallRotorX),
+                                   Transform<T>(Xrot_HipX, V3<T>(-0.06435, 0.0, -.07499)),
+                                   Transform<T>(Xrot_HipX, V3<T>(-0.0827, 0.0, -0.066436)), Axis::X, Axis::X, 6.0);
+        Mat<T> Xrot_HipY = coordinateRotation<T>(Axis::Y, T(hipRyPitch));
+        appendRevoluteWithRotor<T>(model, "hip_ry", "hip_ry_link", "hip_ry_rotor", "hip_rx_link",
+                                   spatialInertia<T>(T(2.64093), V3<T>(0.0132054, 0.0269864, -0.096021), hipRyRotI),
+                                   spatialInertia<T>(T(0.0), zero3, largeRotorY),
+                                   Transform<T>(Xrot_HipY, V3<T>(0.071, 0.0018375, 0.0)),
+                                   Transform<T>(Xrot_HipY, V3<T>(0.071, 0.024, 0.0)), Axis::Y, Axis::Y, 6.0);
+        // knee + ankle: registration order knee_link, ankle_rotor, knee_rotor, ankle_link (:134-141)
+        Body<T> knee_link = model.registerBody(
+            "knee_link", spatialInertia<T>(T(0.35435), V3<T>(0.00528, 0.0014762, -0.13201), kneeRotI), "hip_ry_link",
+            Transform<T>(I3, V3<T>(0.0, 0.0, -0.267)));
+        Body<T> ankle_rotor = model.registerBody("ankle_rotor", spatialInertia<T>(T(0.0), zero3, smallRotorY), "hip_ry_link",
+                                                 Transform<T>(I3, V3<T>(.01563, -.0454, -.13354)));
+        Body<T> knee_rotor = model.registerBody("knee_rotor", spatialInertia<T>(T(0.0), zero3, largeRotorY), "hip_ry_link",
+                                                Transform<T>(I3, V3<T>(0.013, -0.0497, -0.0178)));
+        Body<T> ankle_link = model.registerBody(
+            "ankle_link", spatialInertia<T>(T(0.280951), V3<T>(0.022623, 0.0, -0.012826), ankleRotI), "knee_link",
+            Transform<T>(I3, V3<T>(0.0, 0.0, -0.2785)));
+        ParallelBeltTransmissionModule<T> knee_module{knee_link, knee_rotor, Axis::Y, Axis::Y, T(6.0), {T(2.0)}};
+        ParallelBeltTransmissionModule<T> ankle_module{ankle_link, ankle_rotor, Axis::Y, Axis::Y, T(6.0), {T(2.0), T(1.0)}};
+        model.appendRegisteredBodiesAsCluster("knee_and_ankle",
+                                              std::make_shared<RevolutePairWithRotorCluster<T>>(knee_module, ankle_module));
+        return model;
+    }
+
     template <typename T>
     ClusterTreeModel<T> buildRevoluteChainWithRotor(int N)
     {

@@ -97,6 +97,8 @@ namespace
                     return buildMitHumanoid<T>(true);
                 if (named == "mit_humanoid_rpy")
                     return buildMitHumanoid<T>(false);
+                if (named == "mit_humanoid_leg")
+                    return buildMitHumanoidLeg<T>();
                 const std::string a = "revolute_chain_with_rotor_", b = "revolute_pair_chain_with_rotor_";
                 if (named.compare(0, a.size(), a) == 0)
                     return buildRevoluteChainWithRotor<T>(std::stoi(named.substr(a.size())));
@@ -198,6 +200,21 @@ namespace
                     };
                     joint = std::make_shared<GenericCluster<T>>(
                         bodies, joints, std::make_shared<GenericImplicitConstraint<T>>(ind, phi));
+                    break;
+                }
+                case 10:
+                {
+                    // ClusterJoints::FourBar (FourBarJoint.h): three revolute joints + LoopConstraint::FourBar;
+                    // belt1 = path-1 link lengths, belt2 = path-2 link lengths, belt3 = offset, gear[0] = independent coordinate
+                    JointVec<T> joints;
+                    for (int i = 0; i < N; i++)
+                        joints.push_back(std::make_shared<SingleRevolute<T>>((Axis)c.axes[i]));
+                    std::vector<T> p1, p2;
+                    for (double x : c.belt1) p1.push_back(T(x));
+                    for (double x : c.belt2) p2.push_back(T(x));
+                    joint = std::make_shared<GenericCluster<T>>(
+                        bodies, joints,
+                        std::make_shared<FourBarConstraint<T>>(p1, p2, T(c.belt3[0]), T(c.belt3[1]), (int)c.gear[0]));
                     break;
                 }
                 case 8:
@@ -499,6 +516,23 @@ extern "C"
         c.kind = 5;
         c.axes.assign(axes, axes + N);
         c.independent.assign(independent, independent + N);
+        h->spec.clusters.push_back(c);
+        h->spec.pending = ClusterCmd();
+    }
+    // ClusterJoints::FourBar: the reference's manual builders (src/Robots/PlanarLegLinkage.cpp:66-83)
+    void oracle_builder_append_four_bar(void *hv, const char *name, const int *axes, const double *path1, int n1,
+                                        const double *path2, int n2, const double *offset, int independent_coordinate)
+    {
+        Handle *h = (Handle *)hv;
+        ClusterCmd &c = h->spec.pending;
+        const int N = (int)c.bodies.size();
+        c.name = name;
+        c.kind = 10;
+        c.axes.assign(axes, axes + N);
+        c.belt1.assign(path1, path1 + n1);
+        c.belt2.assign(path2, path2 + n2);
+        c.belt3.assign(offset, offset + 2);
+        c.gear[0] = independent_coordinate;
         h->spec.clusters.push_back(c);
         h->spec.pending = ClusterCmd();
     }

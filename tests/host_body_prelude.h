@@ -29,7 +29,7 @@ namespace host_body
         int valid;
         int zero;
         int buf_stride;
-        int store; // vector-store bodies: the thread has a state of its own
+        int cls[3]; // vector-store bodies: alignment class of the thread's output rows (state N_OUTk mod 4)
     };
     template <typename real>
     inline void storeRow4(real *p, real a, real b, real c, real d) { p[0] = a, p[1] = b, p[2] = c, p[3] = d; }

@@ -337,25 +337,6 @@ using namespace host_body;
 #include "body.inc"
 #include <cstdio>
 #include <vector>
-// a vector-store body exists once per alignment class (warp mod 4 on the device): state b plays a thread of warp
-// b % 4, so all four instances are exercised
-template <typename B>
-void runAny(int w, const double *r0, const double *r1, const double *r2, double *p0, double *p1, double *p2,
-            const OutStage<double> &st)
-{
-    if constexpr (B::VECTOR_STORES)
-    {
-        switch (w)
-        {
-        case 0: B::template run<double, true, 0>(r0, r1, r2, p0, p1, p2, st); break;
-        case 1: B::template run<double, true, 1>(r0, r1, r2, p0, p1, p2, st); break;
-        case 2: B::template run<double, true, 2>(r0, r1, r2, p0, p1, p2, st); break;
-        default: B::template run<double, true, 3>(r0, r1, r2, p0, p1, p2, st); break;
-        }
-    }
-    else
-        B::template run<double, true>(r0, r1, r2, p0, p1, p2, st);
-}
 int main(int argc, char **argv)
 {
     FILE *f = std::fopen(argv[1], "rb");
@@ -382,10 +363,10 @@ int main(int argc, char **argv)
         st.lane = st.warp = stg;
         st.g[0] = &out0[b * M0], st.g[1] = &out1[b * M1], st.g[2] = &out2[b * M2];
         st.valid = 1, st.zero = 0, st.buf_stride = OUT_CHUNK + 1;
-        st.store = 1;
+        // vector-store bodies: state b plays a thread of warp b % 4, so all four store schedules are exercised
+        st.cls[0] = (int)((b % 4) * M0) & 3, st.cls[1] = (int)((b % 4) * M1) & 3, st.cls[2] = (int)((b % 4) * M2) & 3;
         const bool staged_out = M0 <= 64;
-        double *p0 = staged_out ? o0 : &out0[b * M0], *p1 = &out1[b * M1], *p2 = &out2[b * M2];
-        runAny<Body>((int)(b % 4), r0, r1, r2, p0, p1, p2, st);
+        Body::run<double, true>(r0, r1, r2, staged_out ? o0 : &out0[b * M0], &out1[b * M1], &out2[b * M2], st);
         if (staged_out)
             for (int i = 0; i < M0; i++) out0[b * M0 + i] = o0[i];
     }

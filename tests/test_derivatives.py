@@ -102,7 +102,7 @@ def test_derivative_programs_match_oracle(grbda, oracle, robot, tmp_path):
         want = o.dynamics_derivatives(q, yd, aux, forward)
         assert len(outs) == len(want)
         for got, w in zip(outs, want):
-            assert rel(got, w) < TOL
+            assert rel(got.reshape(w.shape).transpose(0, 2, 1), w) < TOL  # the programs write column-major matrices
         # sparsity is exploited: far fewer operations than 2 nv dense tangent sweeps of the program
         base = m.dump_program(grbda.ALGO_ID)["flops"]
         if not forward and o.nv >= 18:
