@@ -107,6 +107,19 @@ def _headers():
     return sorted(out)
 
 
+def source_digest():
+    """Digest of everything the library is built from (csrc/ minus generated code, the C header, this file's model
+    table): written next to the library as libgrbda_cuda.stamp; tests/conftest.py refuses a library whose stamp does
+    not match the sources in the tree."""
+    paths = list(_headers())
+    for root, _, files in os.walk(CSRC):
+        if root.startswith(os.path.join(CSRC, "generated")):
+            continue
+        paths += [os.path.join(root, f) for f in files if f.endswith((".cpp", ".cu"))]
+    paths.append(os.path.abspath(__file__))
+    return _digest(sorted(set(os.path.abspath(p) for p in paths)))
+
+
 def _compile_cached(src, obj_dir, compiler_cmd, dep_digest, log):
     """Compile src -> object named by content hash; returns object path."""
     key = _digest([src], dep_digest + " ".join(compiler_cmd))
@@ -192,6 +205,8 @@ def build(verbose=True, jobs=None, models=None):
         p = os.path.join(BUILD, f)
         if p not in keep and f.endswith(".o"):
             os.remove(p)
+    with open(os.path.splitext(LIB)[0] + ".stamp", "w") as f:
+        f.write(source_digest() + "\n")
     log("  linked %s" % os.path.relpath(LIB, os.path.join(HERE, "..")))
     return LIB
 
