@@ -125,12 +125,14 @@ def run_reference(args):
 def ncu_traffic(kernel, states):
     """DRAM bytes of one launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu
     --set full capture of this round, scaled to `states`; None when no capture is on file."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_roofline_traffic.json")
-    try:
-        rec = json.load(open(path))[kernel]
-        return rec["dram_bytes_per_launch"] * states / rec["states"]
-    except (OSError, KeyError, ValueError):
-        return None
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles")
+    for name in ("r2_roofline_traffic.json", "r1_roofline_traffic.json"):  # newest capture on file
+        try:
+            rec = json.load(open(os.path.join(here, name)))[kernel]
+            return rec["dram_bytes_per_launch"] * states / rec["states"]
+        except (OSError, KeyError, ValueError):
+            continue
+    return None
 
 
 _RESULT_FD = None

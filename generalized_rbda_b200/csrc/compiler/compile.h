@@ -55,6 +55,7 @@ namespace grbda
             int num_parked = 0;
             int stage_buffers = 1;   // chunked outputs: staging buffers per warp (1, or one per output array)
             bool vector_stores = false; // large outputs leave as 256-bit stores of the thread's own row (emit.h)
+            bool ring_stores = false;   // ... assembled in per-thread shared-memory rings (emit.h, row_stores = 2)
             ProgramStats stats;
             Tape tape;
         };
@@ -248,13 +249,22 @@ namespace grbda
                 if (const char *gap = std::getenv("GRBDA_PARK_GAP")) // tuning experiments
                     pc.min_gap = std::atoi(gap);
                 out.parked = park && sync_every == 0;
-                // (vector-store bodies need CTAs of four warps: the caller says whether its launch shape has them)
-                const bool vec = allow_vector_stores &&
-                                 !(std::getenv("GRBDA_NO_VECTOR_STORES") && std::getenv("GRBDA_NO_VECTOR_STORES")[0] == '1');
-                out.body = em.cudaBody(sync_every, out_chunk, out.parked ? &pc : nullptr, vec);
+                // how large in-order outputs (forward kinematics) leave: rings (default), predicated register quads
+                // ("pred": needs CTAs of four warps - the caller says whether its launch shape has them) or the chunk
+                // staging every other large output uses ("chunk"); GRBDA_ROW_STORES selects, for A/B timing
+                const char *rs = std::getenv("GRBDA_ROW_STORES");
+                int row_stores = 2;
+                if (rs && std::string(rs) == "pred")
+                    row_stores = allow_vector_stores ? 1 : 0;
+                else if (rs && std::string(rs) == "chunk")
+                    row_stores = 0;
+                if (std::getenv("GRBDA_NO_VECTOR_STORES") && std::getenv("GRBDA_NO_VECTOR_STORES")[0] == '1')
+                    row_stores = 0;
+                out.body = em.cudaBody(sync_every, out_chunk, out.parked ? &pc : nullptr, row_stores);
                 out.num_parked = em.numParked();
                 out.stage_buffers = em.stageBuffers();
                 out.vector_stores = em.vectorStores();
+                out.ring_stores = em.ringStores();
                 out.range_check = em.cudaRangeCheck();
             }
             return out;
@@ -291,6 +301,7 @@ namespace grbda
             os << "    static constexpr bool RANGE_CHECKED = " << (c.range_check == "true" ? "false" : "true") << ";\n";
             os << "    static constexpr int STAGE_BUFFERS = " << c.stage_buffers << ";\n";
             os << "    static constexpr bool VECTOR_STORES = " << (c.vector_stores ? "true" : "false") << ";\n";
+            os << "    static constexpr bool RING_STORES = " << (c.ring_stores ? "true" : "false") << ";\n";
             os << "    static constexpr bool PARKED = " << (c.parked ? "true" : "false") << "; // " << c.num_parked
                << " values parked in the thread's tile row\n";
             os << "    template <typename real>\n    static __device__ __forceinline__ bool inRange(const real "
@@ -320,6 +331,10 @@ namespace grbda
                   "#define GRBDA_ALIGN() " << (std::getenv("GRBDA_ALIGN_CTA") ? "__syncthreads()" : "__syncwarp()") << "\n#define GRBDA_PIN(x, late) GRBDA_PIN_IMPL(x, late, stage.zero)\n"
                   "#define STGV4(k, m, base, a, b, c, d) if (stage.cls[k] == (m)) storeRow4(out##k + (base), a, b, c, d)\n"
                   "#define STGV1(k, m, base, a) if (stage.cls[k] == (m)) storeRow1(out##k + (base), a)\n"
+                  "#define RING_PUT(k, e, x) ringPut<e>(stage.ring[k], x)\n"
+                  "#define RING_HEAD(k) ringHead<real>(stage.ring[k], out##k)\n"
+                  "#define RING_FLUSH(k, n) ringFlush<real, n>(stage.ring[k], out##k)\n"
+                  "#define RING_TAIL(k) ringTail<real, N_OUT##k>(stage.ring[k], out##k)\n"
                   "#define STG_PUT(j, x) stage.lane[j] = (x)\n"
                   "#define STG_PUTK(k, j, x) stage.lane[(k) * stage.buf_stride + (j)] = (x)\n"
                   "#define STG_FLUSHI0(base, count) flushChunk<real, N_OUT0, count>(stage.g[0], base, stage.warp, stage.valid)\n"
@@ -329,7 +344,7 @@ namespace grbda
                   "#define STG_FLUSH1(base, count) flushChunk<real, N_OUT1, count>(stage.g[1], base, stage.warp, stage.valid)\n"
                   "#define STG_FLUSH2(base, count) flushChunk<real, N_OUT2, count>(stage.g[2], base, stage.warp, stage.valid)\n";
             os << c.body;
-            os << "#undef KC\n#undef KT\n#undef IN0\n#undef IN1\n#undef IN2\n#undef OUT0\n#undef OUT1\n#undef OUT2\n#undef GRBDA_ALIGN\n#undef GRBDA_PIN\n#undef PARK_ST\n#undef PARK_LD\n#undef STGV4\n#undef STGV1\n#undef STG_PUT\n#undef STG_PUTK\n#undef STG_FLUSHI0\n#undef STG_FLUSHI1\n#undef STG_FLUSHI2\n#undef STG_FLUSH0\n#undef STG_FLUSH1\n#undef STG_FLUSH2\n";
+            os << "#undef KC\n#undef KT\n#undef IN0\n#undef IN1\n#undef IN2\n#undef OUT0\n#undef OUT1\n#undef OUT2\n#undef GRBDA_ALIGN\n#undef GRBDA_PIN\n#undef PARK_ST\n#undef PARK_LD\n#undef STGV4\n#undef STGV1\n#undef RING_PUT\n#undef RING_HEAD\n#undef RING_FLUSH\n#undef RING_TAIL\n#undef STG_PUT\n#undef STG_PUTK\n#undef STG_FLUSHI0\n#undef STG_FLUSHI1\n#undef STG_FLUSHI2\n#undef STG_FLUSH0\n#undef STG_FLUSH1\n#undef STG_FLUSH2\n";
             os << "    }\n};\n";
         }
 

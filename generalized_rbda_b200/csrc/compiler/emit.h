@@ -136,6 +136,7 @@ namespace grbda
             int numParked() const { return num_parked_; }       // after cudaBody(..., park)
             int stageBuffers() const { return stage_buffers_; } // after cudaBody: staging buffers per warp
             bool vectorStores() const { return vector_stores_; } // after cudaBody: outputs leave as 256-bit row stores
+            bool ringStores() const { return ring_stores_; }     // after cudaBody: ... through per-thread shared-memory rings
 
             Tape tape() const
             {
@@ -295,9 +296,18 @@ namespace grbda
             // ("class" m = (warp N) mod 4), and every thread writes its own row with 256-bit stores of whole sectors
             // (STGV4; the one or two ragged quads at the row ends go out as 64-bit stores, STGV1). A quad of a class
             // is stored as soon as its last element exists: about one conditional store per element.
+            // row_stores = 2 (rings): the same sector-aligned 256-bit stores without alignment classes in the code. A thread
+            // writes the elements of a row, in order, into a ring of 8 slots of its own in shared memory at slot
+            // (e + m) mod 8, m = (state N) mod 4 being its row's offset inside the sector grid (RING_PUT: the offset is
+            // part of the thread's base pointer, so the store address is base + constant); after every fourth element
+            // the quad that is complete for EVERY m is read back with two 128-bit loads and stored as one sector
+            // (RING_FLUSH), the ragged quads at the two ends of the row element by element (RING_HEAD / RING_TAIL).
+            // One instruction stream for all threads, any CTA shape, no values held in registers: 1.75 instructions
+            // per element instead of ~2.5 (chunk staging) or 1 predicated store + register shuffling per class.
             std::string cudaBody(int sync_every = 0, int out_chunk = 0, const ParkConfig *park = nullptr,
-                                 bool vector_stores = false) const
+                                 int row_stores = 0) const
             {
+                const bool vector_stores = row_stores == 1;
                 std::ostringstream os;
                 int since_sync = 0;
                 std::vector<char> done(g_.nodes.size(), 0);
@@ -373,6 +383,38 @@ namespace grbda
                     vector_stores_ = vector_stores && n_chunked > 0 && n_imm > 0;
                     if (vector_stores_)
                         stage_buffers_ = 0; // no staging buffers at all
+                    // rings need the elements of an array (nearly) in order: an element that is ready early waits for its
+                    // turn in a register, one that is late holds up everything behind it
+                    bool in_order = n_chunked > 0;
+                    for (size_t arr = 0; arr < n_arr; arr++)
+                    {
+                        if (!chunked[arr])
+                            continue;
+                        std::vector<int32_t> pos_of; // statement that produces each element (-1: a constant)
+                        for (auto &o : p_.outputs[arr])
+                            pos_of.push_back(basePos(o.id));
+                        // a value that exists before one of its predecessors waits in a register until the ring reaches
+                        // it: sum of those waits (in statements) / program length = values held on average
+                        double held = 0.0;
+                        int32_t high = -1;
+                        for (int32_t pos : pos_of)
+                        {
+                            if (pos >= 0 && pos < high)
+                                held += (double)(high - pos);
+                            high = std::max(high, pos);
+                        }
+                        held /= (double)std::max<size_t>(1, g_.nodes.size());
+                        if (std::getenv("GRBDA_EMIT_TRACE"))
+                            std::fprintf(stderr, "array %d: %d elements, %.2f values wait for their turn on average\n", (int)arr,
+                                         (int)pos_of.size(), held);
+                        // (forward kinematics: 13-19 for the rotation matrices, whose early entries are the rows a joint
+                        // rotation leaves unchanged - alive in their parent's matrix anyway; mass matrix: 45-130)
+                        if (held > 30.0)
+                            in_order = false;
+                    }
+                    ring_stores_ = row_stores == 2 && in_order && n_imm > 0;
+                    if (ring_stores_)
+                        stage_buffers_ = (int)n_arr; // ring k lives in staging buffer k's space
                 }
                 // vector stores: per array and class, the elements each sector-aligned quad still waits for
                 auto classesOf = [](int n) { return n % 4 == 0 ? 1 : (n % 2 == 0 ? 2 : 4); };
@@ -407,6 +449,23 @@ namespace grbda
                                 os << "STGV1(" << arr << ", " << m << ", " << e << ", " << val(e) << ");\n";
                     }
                 };
+                auto drainRing = [&](int arr) {
+                    const int n = (int)p_.outputs[arr].size();
+                    while (drain_next[arr] < n && ready[arr][drain_next[arr]])
+                    {
+                        const int el = drain_next[arr]++;
+                        os << "RING_PUT(" << arr << ", " << el << ", " << ref(p_.outputs[arr][el].id) << ");\n";
+                        if (el % 4 == 3)
+                        {
+                            if (el == 3)
+                                os << "RING_HEAD(" << arr << ");\n";
+                            else
+                                os << "RING_FLUSH(" << arr << ", " << (el - 3) / 4 << ");\n";
+                        }
+                        if (el + 1 == n)
+                            os << "RING_TAIL(" << arr << ");\n";
+                    }
+                };
                 auto drain = [&](int arr) {
                     const int n = (int)p_.outputs[arr].size();
                     while (drain_next[arr] < n && ready[arr][drain_next[arr]])
@@ -431,6 +490,11 @@ namespace grbda
                     if (ready[arr][el])
                         return;
                     ready[arr][el] = 1;
+                    if (ring_stores_)
+                    {
+                        drainRing(arr);
+                        return;
+                    }
                     if (vector_stores_)
                     {
                         vectorStore(arr, el);
@@ -933,6 +997,7 @@ namespace grbda
             mutable int num_parked_ = 0;
             mutable int stage_buffers_ = 1;
             mutable bool vector_stores_ = false;
+            mutable bool ring_stores_ = false;
             std::vector<int> uses_;
             std::vector<int32_t> partner_;
             ProgramStats stats_;

@@ -341,6 +341,24 @@ namespace grbda_kernels
     // The generated body hands over `COUNT` consecutive elements of one output array for the 32
     // states of the warp through the warp's staging buffer; this writes them with coalesced stores
     // (for COUNT = 16 doubles every instruction covers two states x 128 contiguous bytes).
+    // Row rings (Body::RING_STORES, compiler/emit.h row_stores = 2): a thread assembles the sectors of its own output
+    // row in 8 shared-memory slots. m = (state N) mod 4 is the position of the row's first element inside the 32-byte
+    // sector grid (FP32: the 16-byte grid); element e lives in slot (e + m) mod 8, so quad n of the GLOBAL sector grid
+    // is slots 4 (n mod 2) .. + 3 and leaves as one aligned 256-bit store to ga + 4 n, ga = row - m.
+    template <typename real>
+    struct RowRing
+    {
+        real *slots;   // 8 slots (16-byte aligned; rows of different threads 80 / 48 bytes apart)
+        real *put;     // slots + m: elements with (e mod 8) < 5 are stored at put[e mod 8]
+        real *wrap[3]; // slot of the elements with e mod 8 = 5, 6, 7 (they may wrap around the ring)
+        real *ga;      // global address of the sector that holds the row's first element (row - m)
+        int m;
+    };
+    template <typename real>
+    struct RingStride
+    {
+        static constexpr int value = sizeof(real) == 8 ? 10 : 12; // elements: 128-bit loads stay aligned, few bank conflicts
+    };
     template <typename real>
     struct OutStage
     {
@@ -354,6 +372,7 @@ namespace grbda_kernels
         // (state N_OUTk) mod 4 - warp-uniform by the state mapping of the shells (threadState) - or -1 for a thread
         // without a state of its own (tail of the last tile)
         int cls[3];
+        RowRing<real> ring[3]; // Body::RING_STORES
     };
     // 256-bit store of one whole sector of the thread's own output row (SASS STG.E.256), evict-first
     __device__ __forceinline__ void storeRow4(double *p, double a, double b, double c, double d)
@@ -371,6 +390,55 @@ namespace grbda_kernels
     }
     template <typename real>
     __device__ __forceinline__ void storeRow1(real *p, real a) { __stcs(p, a); }
+    template <int E, typename real>
+    __device__ __forceinline__ void ringPut(const RowRing<real> &r, real x)
+    {
+        if constexpr ((E & 7) < 5)
+            r.put[E & 7] = x;
+        else
+            *r.wrap[(E & 7) - 5] = x;
+    }
+    __device__ __forceinline__ void ringStoreQuad(double *g, const double *s)
+    {
+        const double2 lo = *reinterpret_cast<const double2 *>(s), hi = *reinterpret_cast<const double2 *>(s + 2);
+        storeRow4(g, lo.x, lo.y, hi.x, hi.y);
+    }
+    __device__ __forceinline__ void ringStoreQuad(float *g, const float *s)
+    {
+        const float4 v = *reinterpret_cast<const float4 *>(s);
+        storeRow4(g, v.x, v.y, v.z, v.w);
+    }
+    // quad N0 of the sector grid; emitted after element 4 N0 + 3: complete whatever m is
+    template <typename real, int N0>
+    __device__ __forceinline__ void ringFlush(const RowRing<real> &r, real *)
+    {
+        ringStoreQuad(r.ga + 4 * N0, r.slots + ((4 * N0) & 7));
+    }
+    // first quad (after element 3): whole when the row starts on a sector boundary, else its m leading values belong
+    // to the previous state's row
+    template <typename real>
+    __device__ __forceinline__ void ringHead(const RowRing<real> &r, real *)
+    {
+        if (r.m == 0)
+            ringStoreQuad(r.ga, r.slots);
+        else
+        {
+#pragma unroll
+            for (int p = 1; p < 4; p++)
+                if (p >= r.m)
+                    __stcs(r.ga + p, r.slots[p]);
+        }
+    }
+    // after the last element: positions 4 floor(N / 4) .. m + N - 1 (at most six values) did not form a quad for every m
+    template <typename real, int N>
+    __device__ __forceinline__ void ringTail(const RowRing<real> &r, real *)
+    {
+        constexpr int P0 = 4 * (N / 4);
+#pragma unroll
+        for (int p = P0; p < P0 + 6; p++)
+            if (p < r.m + N)
+                __stcs(r.ga + p, r.slots[p & 7]);
+    }
     // state (row of the tile) a thread works on. Vector-store bodies: warp w takes the states w, w + 4, w + 8, ... of
     // its group of 128, so that the position of a thread's output rows inside the 32-byte sector grid,
     // (state N_OUTk) mod 4, is the same for the whole warp: (w N_OUTk) mod 4.
@@ -487,6 +555,25 @@ namespace grbda_kernels
         o.g[2] = out2 ? out2 + s0 * Body::N_OUT2 : nullptr;
         const int v = rows - 32 * warp;
         o.valid = v < 0 ? 0 : (v > 32 ? 32 : v);
+        if constexpr (Body::RING_STORES)
+        {
+            // (tail threads of the last tile replay the last state: same slots' values to the same addresses)
+            const int64_t state = first + (ts < rows ? ts : rows - 1);
+            real *outs[3] = {out0, out1, out2};
+            const int n[3] = {Body::N_OUT0, Body::N_OUT1, Body::N_OUT2};
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+            {
+                RowRing<real> &r = o.ring[k];
+                r.slots = reinterpret_cast<real *>(stage_base) + ((size_t)k * blockDim.x + threadIdx.x) * RingStride<real>::value;
+                r.m = (int)((state * n[k]) & 3);
+                r.put = r.slots + r.m;
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+                    r.wrap[j] = r.slots + ((5 + j + r.m) & 7);
+                r.ga = outs[k] ? outs[k] + state * n[k] - r.m : nullptr;
+            }
+        }
         return o;
     }
 

@@ -30,7 +30,46 @@ namespace host_body
         int zero;
         int buf_stride;
         int cls[3]; // vector-store bodies: alignment class of the thread's output rows (state N_OUTk mod 4)
+        struct Ring
+        {
+            real slots[8];
+            real *put, *wrap[3], *ga;
+            int m;
+            void init(real *row, int m_)
+            {
+                m = m_, put = slots + m, ga = row - m;
+                for (int j = 0; j < 3; j++)
+                    wrap[j] = slots + ((5 + j + m) & 7);
+            }
+        };
+        mutable Ring ring[3]; // ring-store bodies (the device keeps the slots in shared memory)
     };
+    template <int E, typename R, typename real>
+    inline void ringPut(R &r, real x)
+    {
+        if ((E & 7) < 5)
+            r.put[E & 7] = x;
+        else
+            *r.wrap[(E & 7) - 5] = x;
+    }
+    template <typename real, int N0, typename R>
+    inline void ringFlush(R &r, real *)
+    {
+        for (int i = 0; i < 4; i++)
+            r.ga[4 * N0 + i] = r.slots[((4 * N0) & 7) + i];
+    }
+    template <typename real, typename R>
+    inline void ringHead(R &r, real *)
+    {
+        for (int p = r.m; p < 4; p++)
+            r.ga[p] = r.slots[p];
+    }
+    template <typename real, int N, typename R>
+    inline void ringTail(R &r, real *)
+    {
+        for (int p = 4 * (N / 4); p < r.m + N; p++)
+            r.ga[p] = r.slots[p & 7];
+    }
     template <typename real>
     inline void storeRow4(real *p, real a, real b, real c, real d) { p[0] = a, p[1] = b, p[2] = c, p[3] = d; }
     template <typename real>

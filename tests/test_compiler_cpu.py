@@ -365,6 +365,9 @@ int main(int argc, char **argv)
         st.valid = 1, st.zero = 0, st.buf_stride = OUT_CHUNK + 1;
         // vector-store bodies: state b plays a thread of warp b % 4, so all four store schedules are exercised
         st.cls[0] = (int)((b % 4) * M0) & 3, st.cls[1] = (int)((b % 4) * M1) & 3, st.cls[2] = (int)((b % 4) * M2) & 3;
+        // ring-store bodies: the row of state b starts (b M) mod 4 values into its sector
+        st.ring[0].init(&out0[b * M0], (int)((b * M0) & 3)), st.ring[1].init(&out1[b * M1], (int)((b * M1) & 3));
+        st.ring[2].init(&out2[b * M2], (int)((b * M2) & 3));
         const bool staged_out = M0 <= 64;
         Body::run<double, true>(r0, r1, r2, staged_out ? o0 : &out0[b * M0], &out1[b * M1], &out2[b * M2], st);
         if (staged_out)
@@ -428,21 +431,24 @@ def test_emitted_cuda_text_on_the_host(grbda, oracle, robot, tmp_path, monkeypat
         assert in_range == q.shape[0]
         if park and robot == "tello_with_arms":
             assert "PARKED = true" in text and text.count("PARK_ST(") >= (50 if program == LTL else 5)
-    # forward kinematics: three large output arrays written with 256-bit row stores (the host run plays all four
-    # alignment classes), and the chunk-staged form they replace (GRBDA_NO_VECTOR_STORES=1, kept for A/B timing)
+    # forward kinematics: three large in-order output arrays. Default: sector-aligned 256-bit stores assembled in
+    # per-thread shared-memory rings (the host run covers all four row alignments); kept for A/B timing: predicated
+    # register quads per alignment class (GRBDA_ROW_STORES=pred) and the chunk staging (=chunk)
     p, R, v = o.forward_kinematics(q, yd)
-    for tag, legacy in (("fk", False), ("fk_chunks", True)):
-        if legacy:
-            monkeypatch.setenv("GRBDA_NO_VECTOR_STORES", "1")
+    for tag, mode in (("fk", None), ("fk_pred", "pred"), ("fk_chunks", "chunk")):
+        if mode:
+            monkeypatch.setenv("GRBDA_ROW_STORES", mode)
         outs, in_range, text = run_emitted_source(m, 2, False, [q, yd], tmp_path, tag)
-        monkeypatch.delenv("GRBDA_NO_VECTOR_STORES", raising=False)
+        monkeypatch.delenv("GRBDA_ROW_STORES", raising=False)
         assert rel(outs[0].reshape(p.shape), p) < TOL and rel(outs[1].reshape(R.shape), R) < TOL
         assert rel(outs[2].reshape(v.shape), v) < TOL
         if robot == "tello_with_arms":
-            if legacy:
+            if mode == "chunk":
                 assert "STAGE_BUFFERS = 3" in text and "STG_PUTK(" in text
-            else:
+            elif mode == "pred":
                 assert "VECTOR_STORES = true" in text and text.count("STGV4(") > 300
+            else:
+                assert "RING_STORES = true" in text and text.count("\nRING_FLUSH(") > 150 and text.count("\nRING_TAIL(") == 3
     # the mass matrix fills its rows out of order and keeps the chunk staging (emit.h)
     outs, _, text = run_emitted_source(m, 3, False, [q], tmp_path, "h_chunks")
     assert rel(outs[0].reshape(-1, o.nv, o.nv), o.mass_matrix(q)) < TOL
