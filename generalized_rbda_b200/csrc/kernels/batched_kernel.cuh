@@ -349,8 +349,7 @@ namespace grbda_kernels
     struct RowRing
     {
         real *slots;   // 8 slots (16-byte aligned; rows of different threads 80 / 48 bytes apart)
-        real *put;     // slots + m: elements with (e mod 8) < 5 are stored at put[e mod 8]
-        real *wrap[3]; // slot of the elements with e mod 8 = 5, 6, 7 (they may wrap around the ring)
+        real *put;     // slots + m: elements with (e mod 8) < 5 are stored at put[e mod 8] (no wrap-around)
         real *ga;      // global address of the sector that holds the row's first element (row - m)
         int m;
     };
@@ -395,8 +394,8 @@ namespace grbda_kernels
     {
         if constexpr ((E & 7) < 5)
             r.put[E & 7] = x;
-        else
-            *r.wrap[(E & 7) - 5] = x;
+        else // may wrap around the ring (three elements in eight): two integer instructions instead of a third pointer
+            r.slots[((E & 7) + r.m) & 7] = x;
     }
     __device__ __forceinline__ void ringStoreQuad(double *g, const double *s)
     {
@@ -568,9 +567,6 @@ namespace grbda_kernels
                 r.slots = reinterpret_cast<real *>(stage_base) + ((size_t)k * blockDim.x + threadIdx.x) * RingStride<real>::value;
                 r.m = (int)((state * n[k]) & 3);
                 r.put = r.slots + r.m;
-#pragma unroll
-                for (int j = 0; j < 3; j++)
-                    r.wrap[j] = r.slots + ((5 + j + r.m) & 7);
                 r.ga = outs[k] ? outs[k] + state * n[k] - r.m : nullptr;
             }
         }

