@@ -72,7 +72,9 @@ MODELS = {
 
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-CXXFLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-variable", "-Wno-sign-compare"]
+# (-D switches of GRBDA_EXTRA_NVCCFLAGS reach the host compiler too: kernels/shapes.h is shared by both sides)
+CXXFLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-variable", "-Wno-sign-compare"] + \
+    [f for f in os.environ.get("GRBDA_EXTRA_NVCCFLAGS", "").split() if f.startswith("-D")]
 NVCCFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
              "-Xcompiler", "-fPIC", "-I", CSRC, "-ccbin", CXX,
              "-DGRBDA_DEFAULT_URDF_DIR=\"%s\"" % URDF_DIR] + os.environ.get("GRBDA_EXTRA_NVCCFLAGS", "").split()
