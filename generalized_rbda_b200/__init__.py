@@ -45,7 +45,9 @@ for _n in ("num_positions", "num_degrees_of_freedom", "num_bodies", "num_cluster
     getattr(_lib, "grbda_cuda_" + _n).argtypes = [_vp]
 _lib.grbda_cuda_model_create_from_robot.argtypes = [C.c_char_p, C.c_int, C.POINTER(_vp)]
 _lib.grbda_cuda_model_create_from_urdf.argtypes = [C.c_char_p, C.c_int, C.POINTER(_vp)]
+_lib.grbda_cuda_model_create_from_urdfs.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(_vp)]
 _lib.grbda_cuda_model_create.argtypes = [_vp, C.c_int, C.POINTER(_vp)]
+_lib.grbda_cuda_describe_urdf.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, _i64, C.POINTER(_i64)]
 _lib.grbda_cuda_model_destroy.argtypes = [_vp]
 _lib.grbda_cuda_cluster_info.argtypes = [_vp, C.c_int, _vp, _vp]
 _lib.grbda_cuda_body_info.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]
@@ -88,7 +90,7 @@ _lib.grbda_cuda_measure_fma_peak.argtypes = [C.c_int, C.c_int, C.c_double, C.POI
 
 EXPORTED_SYMBOLS = [
     "grbda_cuda_last_error_string", "grbda_cuda_version", "grbda_cuda_model_create",
-    "grbda_cuda_model_create_from_urdf", "grbda_cuda_model_create_from_robot", "grbda_cuda_model_destroy",
+    "grbda_cuda_model_create_from_urdf", "grbda_cuda_model_create_from_urdfs", "grbda_cuda_describe_urdf", "grbda_cuda_model_create_from_robot", "grbda_cuda_model_destroy",
     "grbda_cuda_num_positions", "grbda_cuda_num_degrees_of_freedom", "grbda_cuda_num_bodies",
     "grbda_cuda_num_clusters", "grbda_cuda_model_hash", "grbda_cuda_cluster_info", "grbda_cuda_body_info",
     "grbda_cuda_cluster_G", "grbda_cuda_model_gravity", "grbda_cuda_cluster_phi", "grbda_cuda_dump_program", "grbda_cuda_kernel_counts", "grbda_cuda_emit_source",
@@ -204,6 +206,20 @@ def _stream():
     return _vp(torch.cuda.current_stream().cuda_stream)
 
 
+def describe_urdf(paths):
+    """The URDF+ front end's reading of one file or of several files that make one robot (dict: link_order, links
+    with parent / children / loop_links / supporting_chain / cluster, clusters)."""
+    import json
+    if not isinstance(paths, (list, tuple)):
+        paths = [paths]
+    arr = (C.c_char_p * len(paths))(*[os.fspath(p).encode() for p in paths])
+    need = _i64(0)
+    _check(_lib.grbda_cuda_describe_urdf(arr, len(paths), None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    _check(_lib.grbda_cuda_describe_urdf(arr, len(paths), buf, need.value, None))
+    return json.loads(buf.value.decode())
+
+
 class ClusterTreeModel:
     """Batched counterpart of grbda::ClusterTreeModel.
 
@@ -223,8 +239,14 @@ class ClusterTreeModel:
 
     @classmethod
     def from_urdf(cls, path, device=0):
+        """path: one URDF+ file, or a list of files that together describe one robot (ClusterTreeModel.h:41-53)."""
         h = _vp()
-        _check(_lib.grbda_cuda_model_create_from_urdf(path.encode(), -1 if device is None else device, C.byref(h)))
+        dev = -1 if device is None else device
+        if isinstance(path, (list, tuple)):
+            paths = (C.c_char_p * len(path))(*[os.fspath(p).encode() for p in path])
+            _check(_lib.grbda_cuda_model_create_from_urdfs(paths, len(path), dev, C.byref(h)))
+        else:
+            _check(_lib.grbda_cuda_model_create_from_urdf(os.fspath(path).encode(), dev, C.byref(h)))
         return cls(h, device)
 
     @classmethod

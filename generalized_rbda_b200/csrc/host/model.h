@@ -397,7 +397,17 @@ namespace grbda
             buildModelFromURDF(urdf_filename);
         }
 
-        void buildModelFromURDF(const std::string &urdf_filename); // host/urdf.cpp
+        // reference: ClusterTreeModel.h:48-53
+        explicit ClusterTreeModel(const std::vector<std::string> &urdf_filenames) : ClusterTreeModel()
+        {
+            buildModelFromURDF(urdf_filenames);
+        }
+
+        void buildModelFromURDF(const std::string &urdf_filename);                // host/urdf.cpp
+        void buildModelFromURDF(const std::vector<std::string> &urdf_filenames); // several files, one model
+        // the parse as JSON (link order, parents, children, loop links, supporting chains, clusters): what the
+        // reference's parser tests check of the urdfdom fork's ModelInterface
+        static std::string describeURDF(const std::vector<std::string> &urdf_filenames);
 
         // reference: ClusterTreeModel.cpp:9-32
         Body registerBody(const std::string &name, const SpatialInertia &inertia,

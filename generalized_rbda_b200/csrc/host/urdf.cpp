@@ -249,7 +249,12 @@ namespace grbda
             return chain;
         }
 
-        UModel parseUrdf(const std::string &path)
+        // The <link> / <joint> / <loop> / <coupling> elements of one file, added to `m`. Several files make one model
+        // (the fork's parseURDFFiles, ClusterTreeModel.h:48-53; UnitTests/testUrdfParser.cpp:398-445 splits Mini
+        // Cheetah into a base and four legs): every file names the links it attaches to as empty <link/> stubs, so
+        // a link may be declared more than once as long as at most one declaration carries an <inertial>; joints
+        // and constraints must be unique.
+        void readRobotElements(const std::string &path, UModel &m)
         {
             std::ifstream f(path);
             if (!f)
@@ -262,7 +267,6 @@ namespace grbda
             if (!robot)
                 throw std::runtime_error("Could not parse URDF file: no <robot> element in " + path);
 
-            UModel m;
             for (const XmlNode &n : robot->children)
             {
                 if (n.name == "link")
@@ -282,9 +286,15 @@ namespace grbda
                                          g("ixz"), g("iyz"), g("izz")};
                         }
                     }
-                    if (m.links.count(l.name))
+                    const auto seen = m.links.find(l.name);
+                    if (seen == m.links.end())
+                        m.links[l.name] = l;
+                    else if (!l.has_inertial)
+                        ; // a stub for a link another declaration defines
+                    else if (!seen->second.has_inertial)
+                        seen->second = l;
+                    else
                         throw std::runtime_error("URDF: link '" + l.name + "' is not unique");
-                    m.links[l.name] = l;
                 }
                 else if (n.name == "joint")
                 {
@@ -309,6 +319,8 @@ namespace grbda
                         const auto a = numbers(ax->get("xyz"), 3, {1, 0, 0});
                         j.axis = {a[0], a[1], a[2]};
                     }
+                    if (m.joints.count(j.name))
+                        throw std::runtime_error("URDF: joint '" + j.name + "' is not unique");
                     m.joints[j.name] = j;
                 }
                 else if (n.name == "loop" || n.name == "coupling")
@@ -325,9 +337,21 @@ namespace grbda
                     c.succ_origin = parsePose(s->child("origin"));
                     if (const XmlNode *r = n.child("ratio"))
                         c.ratio = numbers(r->get("value"), 1, {1})[0];
+                    for (const UConstraint &other : m.constraints)
+                        if (other.name == c.name)
+                            throw std::runtime_error("URDF: constraint '" + c.name + "' is not unique");
                     m.constraints.push_back(c);
                 }
             }
+        }
+
+        UModel parseUrdf(const std::vector<std::string> &paths)
+        {
+            if (paths.empty())
+                throw std::runtime_error("Could not parse URDF file: no file given");
+            UModel m;
+            for (const std::string &path : paths)
+                readRobotElements(path, m);
             // tree (urdfdom initTree: joints_ is a name-keyed map, so children follow joint-name order)
             for (auto &kv : m.joints)
             {
@@ -505,11 +529,68 @@ namespace grbda
         }
     } // namespace
 
+    // What the front end made of the files, as JSON: the quantities the reference's parser tests pin
+    // (UnitTests/testUrdfParser.cpp:39-396: link order, parents, children in order, supporting chains, neighbours =
+    // children followed by loop links, clusters with parent / child clusters).
+    std::string ClusterTreeModel::describeURDF(const std::vector<std::string> &urdf_filenames)
+    {
+        const UModel um = parseUrdf(urdf_filenames);
+        auto quote = [](const std::string &x) { return "\"" + x + "\""; };
+        auto list = [&](const std::vector<std::string> &v)
+        {
+            std::string o = "[";
+            for (size_t i = 0; i < v.size(); i++)
+                o += (i ? ", " : "") + quote(v[i]);
+            return o + "]";
+        };
+        std::ostringstream os;
+        // link order = the order buildModelFromURDF registers the bodies in: clusters depth first, child clusters in
+        // their stored order, the links of a cluster in theirs
+        std::vector<std::string> order;
+        std::function<void(int)> visit = [&](int ci)
+        {
+            for (const std::string &l : um.clusters[ci].links)
+                order.push_back(l);
+            for (int ch : um.clusters[ci].children)
+                visit(ch);
+        };
+        visit(um.containing_cluster.at(um.root));
+        os << "{\"root\": " << quote(um.root) << ", \"link_order\": " << list(order) << ", \"links\": {";
+        bool first = true;
+        for (const auto &kv : um.links)
+        {
+            const ULink &l = kv.second;
+            std::vector<std::string> chain = chainToRoot(um, l.name); // link ... root
+            chain.pop_back();
+            std::reverse(chain.begin(), chain.end());
+            os << (first ? "" : ", ") << quote(l.name) << ": {\"parent\": " << (l.parent.empty() ? "null" : quote(l.parent))
+               << ", \"children\": " << list(l.child_links) << ", \"loop_links\": " << list(l.loop_links)
+               << ", \"supporting_chain\": " << list(chain) << ", \"cluster\": " << um.containing_cluster.at(l.name) << "}";
+            first = false;
+        }
+        os << "}, \"clusters\": [";
+        for (size_t c = 0; c < um.clusters.size(); c++)
+        {
+            const UCluster &uc = um.clusters[c];
+            os << (c ? ", " : "") << "{\"links\": " << list(uc.links) << ", \"parent\": " << uc.parent << ", \"children\": [";
+            for (size_t i = 0; i < uc.children.size(); i++)
+                os << (i ? ", " : "") << uc.children[i];
+            os << "]}";
+        }
+        os << "], \"num_joints\": " << um.joints.size() << ", \"num_constraints\": " << um.constraints.size() << "}";
+        return os.str();
+    }
+
     // reference: ClusterTreeModel.h:41-46 + ClusterTreeParsing.cpp:5-43
     void ClusterTreeModel::buildModelFromURDF(const std::string &urdf_filename)
     {
+        buildModelFromURDF(std::vector<std::string>{urdf_filename});
+    }
+    // reference: ClusterTreeModel.h:48-53 (several files, one model)
+    void ClusterTreeModel::buildModelFromURDF(const std::vector<std::string> &urdf_filenames)
+    {
         using namespace ClusterJoints;
-        const UModel um = parseUrdf(urdf_filename);
+        const UModel um = parseUrdf(urdf_filenames);
         // the root link is the ground (ClusterTreeParsing.cpp:13-19)
         body_name_to_body_index_[um.root] = -1;
         const UCluster &root_cluster = um.clusters[um.containing_cluster.at(um.root)];

@@ -309,6 +309,35 @@ extern "C"
             return fail(GRBDA_ERR_INVALID_ARGUMENT, "null argument");
         return guarded([&] { return finishCreate(ClusterTreeModel(std::string(urdf_path)), device, out); });
     }
+    grbda_status grbda_cuda_model_create_from_urdfs(const char *const *urdf_paths, int num_paths, int device, grbda_model **out)
+    {
+        if (!urdf_paths || num_paths <= 0 || !out)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "null argument");
+        for (int i = 0; i < num_paths; i++)
+            if (!urdf_paths[i])
+                return fail(GRBDA_ERR_INVALID_ARGUMENT, "null path");
+        return guarded([&] {
+            return finishCreate(ClusterTreeModel(std::vector<std::string>(urdf_paths, urdf_paths + num_paths)), device, out);
+        });
+    }
+    grbda_status grbda_cuda_describe_urdf(const char *const *urdf_paths, int num_paths, char *json, int64_t capacity,
+                                          int64_t *needed)
+    {
+        if (!urdf_paths || num_paths <= 0)
+            return fail(GRBDA_ERR_INVALID_ARGUMENT, "null argument");
+        return guarded([&] {
+            const std::string text = ClusterTreeModel::describeURDF(std::vector<std::string>(urdf_paths, urdf_paths + num_paths));
+            if (needed)
+                *needed = (int64_t)text.size() + 1;
+            if (json && capacity > 0)
+            {
+                const size_t n = std::min((size_t)capacity - 1, text.size());
+                std::memcpy(json, text.data(), n);
+                json[n] = 0;
+            }
+            return GRBDA_OK;
+        });
+    }
     grbda_status grbda_cuda_model_create_from_robot(const char *name, int device, grbda_model **out)
     {
         if (!name || !out)

@@ -118,6 +118,16 @@ grbda_status grbda_cuda_model_create(const grbda_schedule *schedule, int device,
 /* From a URDF+ file. Replaces ClusterTreeModel(const std::string &urdf_filename),
  * include/grbda/Dynamics/ClusterTreeModel.h:33-46 + src/Dynamics/ClusterTreeParsing.cpp. */
 grbda_status grbda_cuda_model_create_from_urdf(const char *urdf_path, int device, grbda_model **out);
+/* From several URDF+ files that together describe one robot (every file names the links it attaches to as empty
+ * <link/> stubs). Replaces buildModelFromURDF(const std::vector<std::string> &urdf_filenames),
+ * include/grbda/Dynamics/ClusterTreeModel.h:48-53 (UnitTests/testUrdfParser.cpp:398-445). */
+grbda_status grbda_cuda_model_create_from_urdfs(const char *const *urdf_paths, int num_paths, int device,
+                                                grbda_model **out);
+/* The front end's reading of the file(s) as JSON text: link order, parent / children / loop links / supporting chain
+ * of every link, clusters with parent and child clusters - the quantities UnitTests/testUrdfParser.cpp:39-396 checks
+ * of the parser. Call with json = NULL to get the size in *needed. No GPU involved. */
+grbda_status grbda_cuda_describe_urdf(const char *const *urdf_paths, int num_paths, char *json, int64_t capacity,
+                                      int64_t *needed);
 /* From one of the reference's robot classes (include/grbda/Robots): "tello", "tello_with_arms",
  * "mini_cheetah", "mit_humanoid", "revolute_chain_with_rotor_<N>",
  * "revolute_pair_chain_with_rotor_<N>", or a URDF name from robot-models ("four_bar", ...). */
