@@ -412,8 +412,9 @@ class ClusterTreeModel:
         return out
 
     def emit_source(self, program, path, park=False):
-        """Write the CUDA source the model compiler emits for `program` (constant table + struct Body)."""
-        _check(_lib.grbda_cuda_emit_source(self._h, program, int(bool(park)), path.encode()))
+        """Write the CUDA source the model compiler emits for `program` (constant table + struct Body). park: False,
+        True (values parked in the tile rows) or 1 + n (and in a park area of n slots per thread)."""
+        _check(_lib.grbda_cuda_emit_source(self._h, program, int(park), path.encode()))
 
     def kernel_counts(self, algo):
         """Operation counts of the program the default compiled kernel of `algo` runs per state."""

@@ -38,10 +38,12 @@ LIB = os.path.join(_OUT, "libgrbda_cuda.so")
 # shared-memory tile row instead of being spilled (T and S only); 'f32aba' = the FP32 kernel of the variant runs the
 # articulated-body sweep. Measured on B200 (profiles/README.md): T,128,2 is the fastest
 # and the most device-independent shape for every entry point.
-DEFAULT_VARIANTS = "id=T,128,2;S,128,2|fd=T,128,2,auto,park;T,128,2,ltl,park;T,128,2;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2"
+# 'park' on the mass matrix: its results wait in registers for their 16-value chunk (91 spilled doubles on TelloWithArms);
+# the body parks them in the park area - the shared memory its single input row leaves unused (kernels/shapes.h)
+DEFAULT_VARIANTS = "id=T,128,2;S,128,2|fd=T,128,2,auto,park;T,128,2,ltl,park;T,128,2;S,128,2|fk=T,128,2;S,128,2|h=T,128,2,park;T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2"
 SYNC_EVERY = int(os.environ.get("GRBDA_SYNC_EVERY", "0"))  # alignment barriers measured useless (profiles/)
 MODELS = {
-    "tello_with_arms": ("id,fd,fk,h,phi,gfa,gfs,gen", "id=T,128,2;S,128,2|fd=T,128,2,ltl,park;T,128,2,ltl;S,128,2,ltl,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2", True),
+    "tello_with_arms": ("id,fd,fk,h,phi,gfa,gfs,gen", "id=T,128,2;S,128,2|fd=T,128,2,ltl,park;T,128,2,ltl;S,128,2,ltl,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2,park;T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2", True),
     "tello": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
     "mini_cheetah": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "mit_humanoid": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
@@ -52,7 +54,7 @@ MODELS = {
     # 58 bodies: the tile rows of a 128-thread CTA take 163 KB (one CTA per SM); 64-thread CTAs fit twice.
     # Both dynamics kernels spill and are parked (ID 1.01 -> 0.86 ms, FD 3.3-4.2 ms per 2^20 states, L2 dependent)
     "jvrc1_humanoid": ("id,fd,fk,h,phi,gfa,gfs,gen",
-                       "id=T,64,2,park;T,128,2,park;S,128,2|fd=T,64,2,ltl,park;T,128,2,ltl,park;T,64,2,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2", True),
+                       "id=T,64,2,park;T,128,2,park;S,128,2|fd=T,64,2,ltl,park;T,128,2,ltl,park;T,64,2,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2,park;T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2", True),
     "revolute_rotor_chain": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_2": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_4": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),

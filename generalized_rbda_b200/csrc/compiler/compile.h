@@ -53,6 +53,7 @@ namespace grbda
             std::string range_check; // expression: may the fast sin/cos forms be used for this state
             bool parked = false;     // body parks long-lived values in the thread's shared-memory row
             int num_parked = 0;
+            int park_extra = 0;      // slots per thread of the park area behind the tiles (parked bodies)
             int stage_buffers = 1;   // chunked outputs: staging buffers per warp (1, or one per output array)
             bool vector_stores = false; // large outputs leave as 256-bit stores of the thread's own row (emit.h)
             bool ring_stores = false;   // ... assembled in per-thread shared-memory rings (emit.h, row_stores = 2)
@@ -226,7 +227,7 @@ namespace grbda
 
         inline CompiledAlgo compileAlgo(const ClusterTreeModel &model, int algo, bool want_body = true,
                                         int sync_every = 0, ConstTable *consts = nullptr, int out_chunk = 0,
-                                        bool park = false, bool allow_vector_stores = true)
+                                        bool park = false, bool allow_vector_stores = true, int park_extra = 0)
         {
             sym::Graph graph;
             sym::GraphScope scope(graph);
@@ -246,6 +247,13 @@ namespace grbda
                 for (int i = 0; i < 3; i++)
                     pc.n_slots[i] = p.n_in[i];
                 pc.n_slots[3] = out.n_out[0] <= 64 ? out.n_out[0] : 0; // the shells stage output 0 when it is small
+                pc.n_slots[4] = park_extra;                            // park area behind the tiles
+                // Programs with large outputs (mass matrix) hold their results until a 16-value chunk is complete: many
+                // values that wait a few hundred statements each, not a few that wait for half the program. Measured
+                // on B200 (TelloWithArms / MIT humanoid mass matrix, 2^18 states, unparked 0.278 / 0.279 ms): gap 300 ->
+                // 0.263 / 0.265, 100 -> 0.247 / 0.256, 50 -> 0.248 / 0.259, 20 -> 0.260 / 0.276 ms
+                if (grbda_kernels::shapeChunkStageBytes(out.n_out, 1, 32, 8) > 0)
+                    pc.min_gap = 100;
                 if (const char *gap = std::getenv("GRBDA_PARK_GAP")) // tuning experiments
                     pc.min_gap = std::atoi(gap);
                 out.parked = park && sync_every == 0;
@@ -262,6 +270,7 @@ namespace grbda
                     row_stores = 0;
                 out.body = em.cudaBody(sync_every, out_chunk, out.parked ? &pc : nullptr, row_stores);
                 out.num_parked = em.numParked();
+                out.park_extra = out.parked ? park_extra : 0;
                 out.stage_buffers = em.stageBuffers();
                 out.vector_stores = em.vectorStores();
                 out.ring_stores = em.ringStores();
@@ -304,6 +313,7 @@ namespace grbda
             os << "    static constexpr bool RING_STORES = " << (c.ring_stores ? "true" : "false") << ";\n";
             os << "    static constexpr bool PARKED = " << (c.parked ? "true" : "false") << "; // " << c.num_parked
                << " values parked in the thread's tile row\n";
+            os << "    static constexpr int PARK_EXTRA = " << c.park_extra << ";\n";
             os << "    template <typename real>\n    static __device__ __forceinline__ bool inRange(const real "
                   "*__restrict__ in0, const real *__restrict__ in1,\n        const real *__restrict__ in2)\n    {\n"
                   "#define KC(x) ((real)(x))\n#define IN0(i) in0[i]\n#define IN1(i) in1[i]\n#define IN2(i) in2[i]\n"
@@ -314,7 +324,7 @@ namespace grbda
                 os << "    static __device__ __forceinline__ void run(const real *in0, const real *in1, const real *in2,\n"
                       "        real *out0, real *out1, real *out2, const OutStage<real> &stage)\n    {\n"
                       "        real *const row0 = const_cast<real *>(in0), *const row1 = const_cast<real *>(in1),\n"
-                      "                   *const row2 = const_cast<real *>(in2), *const row3 = out0;\n"
+                      "                   *const row2 = const_cast<real *>(in2), *const row3 = out0, *const row4 = stage.park;\n"
                       "#define IN0(i) row0[i]\n#define IN1(i) row1[i]\n#define IN2(i) row2[i]\n#define OUT0(i, x) row3[i] = (x)\n"
                       // volatile: otherwise the compiler forwards the stored value to the load and keeps (spills) it itself
                       "#define PARK_ST(t, i, x) *(volatile real *)(row##t + (i)) = (x)\n"

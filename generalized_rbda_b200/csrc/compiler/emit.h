@@ -115,7 +115,8 @@ namespace grbda
         // values there (PARK_ST / PARK_LD) instead.
         struct ParkConfig
         {
-            int n_slots[4] = {0, 0, 0, 0}; // usable elements of the in0 / in1 / in2 / out0 rows (0: row not staged)
+            // usable elements of the in0 / in1 / in2 / out0 rows (0: row not staged) and of the park area behind the tiles
+            int n_slots[5] = {0, 0, 0, 0, 0};
             // park only across gaps of at least this fraction of the program (in graph nodes). Measured on
             // B200 (TelloWithArms forward dynamics, 8.9 k nodes): 0.09 -> 0.763 ms, 0.13 -> 0.770, 0.20 -> 0.741,
             // 0.28 -> 0.729, 0.39 -> 0.766, 0.56 -> 0.782, 0.78 -> 0.841, no parking 0.986 ms
@@ -659,7 +660,8 @@ namespace grbda
                 bool any_chunked = false;
                 for (size_t arr = 0; arr < n_arr; arr++)
                     any_chunked = any_chunked || chunked[arr];
-                if (park && !any_chunked)
+                // (register quads of the predicated vector stores read their values at per-class positions: not planned)
+                if (park && !(any_chunked && vector_stores_))
                 {
                     const int32_t N = (int32_t)g_.nodes.size();
                     const int32_t min_gap = park->min_gap > 0 ? park->min_gap
@@ -701,6 +703,47 @@ namespace grbda
                                     access[x].push_back(pos);
                             }
                     }
+                    // Large outputs are not stored where they are defined: an element of a chunk-staged array is read
+                    // when the LAST element of its 16-value chunk exists (flushChunk), an element of an in-order array
+                    // (rings, immediate staging) when every element before it exists. Those reads are accesses too -
+                    // the values that wait for them are what the mass matrix spills.
+                    for (size_t arr = 0; arr < n_arr; arr++)
+                    {
+                        if (!chunked[arr])
+                            continue;
+                        const int n = (int)p_.outputs[arr].size();
+                        std::vector<int32_t> ready_at(n, -1); // statement after which the element exists (-1: constant)
+                        for (int e = 0; e < n; e++)
+                        {
+                            const int32_t b = base(p_.outputs[arr][e].id);
+                            if (g_.nodes[b].op != sym::OP_CONST)
+                                ready_at[e] = b; // (a negated output leaves with its operand)
+                        }
+                        const bool in_order_drain = ring_stores_ || immediate[arr];
+                        std::vector<int32_t> read_at(n, -1);
+                        if (in_order_drain)
+                        {
+                            int32_t high = -1;
+                            for (int e = 0; e < n; e++)
+                                read_at[e] = high = std::max(high, ready_at[e]);
+                        }
+                        else
+                            for (int c0 = 0; c0 < n; c0 += out_chunk)
+                            {
+                                int32_t last = -1;
+                                for (int e = c0; e < std::min(n, c0 + out_chunk); e++)
+                                    last = std::max(last, ready_at[e]);
+                                for (int e = c0; e < std::min(n, c0 + out_chunk); e++)
+                                    read_at[e] = last;
+                            }
+                        for (int e = 0; e < n; e++)
+                        {
+                            const int32_t b = base(p_.outputs[arr][e].id);
+                            if (g_.nodes[b].op == sym::OP_CONST || g_.nodes[b].op == sym::OP_INPUT || read_at[e] <= b)
+                                continue;
+                            access[b].push_back(read_at[e]);
+                        }
+                    }
                     // slot availability: [free_from, free_until)
                     std::vector<Slot> slots;
                     for (int t = 0; t < 3; t++)
@@ -721,6 +764,8 @@ namespace grbda
                                 continue;
                             slots.push_back(Slot{3, k, 0, b, {}});
                         }
+                    for (int k = 0; k < park->n_slots[4]; k++)
+                        slots.push_back(Slot{4, k, 0, N, {}});
                     // candidates: the longest gap between consecutive accesses of a value
                     std::vector<Cand> cands;
                     for (int32_t x = 0; x < N; x++)

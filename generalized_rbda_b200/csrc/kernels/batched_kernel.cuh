@@ -372,6 +372,7 @@ namespace grbda_kernels
         // without a state of its own (tail of the last tile)
         int cls[3];
         RowRing<real> ring[3]; // Body::RING_STORES
+        real *park;            // Body::PARK_EXTRA > 0: this thread's slots of the park area
     };
     // 256-bit store of one whole sector of the thread's own output row (SASS STG.E.256), evict-first
     __device__ __forceinline__ void storeRow4(double *p, double a, double b, double c, double d)
@@ -528,9 +529,15 @@ namespace grbda_kernels
         return Body::N_OUT0 > 64 || Body::N_OUT1 > OUT_CHUNK || Body::N_OUT2 > OUT_CHUNK; // = Emitter's rule
     }
     template <typename Body, typename real, int BLOCK>
-    __host__ __device__ constexpr size_t stageBytes()
+    __host__ __device__ constexpr size_t chunkStageBytes()
     {
         return bodyChunked<Body>() ? (size_t)Body::STAGE_BUFFERS * BLOCK * (OUT_CHUNK + 1) * sizeof(real) : 0;
+    }
+    // chunk staging buffers / rings, then the park area of a parked body (Body::PARK_EXTRA slots per thread)
+    template <typename Body, typename real, int BLOCK>
+    __host__ __device__ constexpr size_t stageBytes()
+    {
+        return chunkStageBytes<Body, real, BLOCK>() + shapeParkBytes(Body::PARK_EXTRA, BLOCK, (int)sizeof(real));
     }
     template <typename Body, typename real>
     __device__ __forceinline__ OutStage<real> makeOutStage(unsigned char *stage_base, real *out0, real *out1,
@@ -554,6 +561,9 @@ namespace grbda_kernels
         o.g[2] = out2 ? out2 + s0 * Body::N_OUT2 : nullptr;
         const int v = rows - 32 * warp;
         o.valid = v < 0 ? 0 : (v > 32 ? 32 : v);
+        if constexpr (Body::PARK_EXTRA > 0)
+            o.park = reinterpret_cast<real *>(stage_base + (bodyChunked<Body>() ? (size_t)Body::STAGE_BUFFERS * blockDim.x * (OUT_CHUNK + 1) * sizeof(real) : 0)) +
+                     (size_t)threadIdx.x * oddStride(Body::PARK_EXTRA);
         if constexpr (Body::RING_STORES)
         {
             // (tail threads of the last tile replay the last state: same slots' values to the same addresses)
@@ -571,6 +581,23 @@ namespace grbda_kernels
             }
         }
         return o;
+    }
+
+    // A parked body keeps values in its tile rows, so the threads behind the end of the batch (last tile) cannot share
+    // the row of the last valid state the way the replicas of an unparked body do. They normally sit the body out -
+    // unless its large outputs leave through chunk staging, where flushChunk is a warp-cooperative copy that needs
+    // every lane: then each of them gets a private copy of the last valid row (and its stores are masked by `valid`).
+    template <typename Body>
+    __host__ __device__ constexpr bool parkedCooperative()
+    {
+        return Body::PARKED && bodyChunked<Body>() && !Body::RING_STORES && !Body::VECTOR_STORES;
+    }
+    template <typename real, int N>
+    __device__ __forceinline__ void replicateRow(real *mine, const real *last)
+    {
+#pragma unroll 1
+        for (int i = 0; i < N; i++)
+            mine[i] = last[i];
     }
 
     // Shared-memory budget of one CTA: all input tiles plus the tile of output array 0 when it is
@@ -650,7 +677,18 @@ namespace grbda_kernels
                     stage_in<real, Body::N_IN2 ? Body::N_IN2 : 1, BLOCK>(in2 + first * Body::N_IN2,
                                                                         smem + L::OFF2, rows);
                 __syncthreads();
-                const real *i0 = smem + t * L::S0, *i1 = smem + L::OFF1 + t * L::S1, *i2 = smem + L::OFF2 + t * L::S2;
+                const int tr = parkedCooperative<Body>() ? ts : t; // row this thread works in
+                if (parkedCooperative<Body>() && rows < BLOCK)     // (CTA-uniform)
+                {
+                    if (!has_state)
+                    {
+                        replicateRow<real, Body::N_IN0>(smem + tr * L::S0, smem + t * L::S0);
+                        replicateRow<real, Body::N_IN1>(smem + L::OFF1 + tr * L::S1, smem + L::OFF1 + t * L::S1);
+                        replicateRow<real, Body::N_IN2>(smem + L::OFF2 + tr * L::S2, smem + L::OFF2 + t * L::S2);
+                    }
+                    __syncthreads();
+                }
+                const real *i0 = smem + tr * L::S0, *i1 = smem + L::OFF1 + tr * L::S1, *i2 = smem + L::OFF2 + tr * L::S2;
                 bool ok = true;
                 if (FAST && GRBDA_RANGE_CHECKED(Body))
                 {
@@ -660,10 +698,10 @@ namespace grbda_kernels
                 }
                 if (ok)
                 {
-                    real *o0 = L::STAGE_OUT0 ? smem + L::OFFO + t * L::SO : out0 + state * Body::N_OUT0;
+                    real *o0 = L::STAGE_OUT0 ? smem + L::OFFO + tr * L::SO : out0 + state * Body::N_OUT0;
                     real *o1 = Body::N_OUT1 ? out1 + state * Body::N_OUT1 : nullptr;
                     real *o2 = Body::N_OUT2 ? out2 + state * Body::N_OUT2 : nullptr;
-                    if (!Body::PARKED || has_state) // parked rows are private: no tail replicas
+                    if (!Body::PARKED || has_state || parkedCooperative<Body>()) // parked rows are private: no tail replicas
                         runBody<Body, real, FAST>(i0, i1, i2, o0, o1, o2, stage);
                     if (L::STAGE_OUT0)
                     {
@@ -876,8 +914,8 @@ namespace grbda_kernels
     __host__ __device__ constexpr bool shapeMirrorsAgree()
     {
         const int n_in[3] = {Body::N_IN0, Body::N_IN1, Body::N_IN2}, n_out[3] = {Body::N_OUT0, Body::N_OUT1, Body::N_OUT2};
-        return shapeTileBytes(n_in, n_out, Body::STAGE_BUFFERS, BLOCK, (int)sizeof(real)) == TileLayout<Body, real, BLOCK>::BYTES &&
-               shapeTmaBytes(n_in, n_out, Body::STAGE_BUFFERS, BLOCK, (int)sizeof(real)) == TmaLayout<Body, real, BLOCK>::BYTES;
+        return shapeTileBytes(n_in, n_out, Body::STAGE_BUFFERS, BLOCK, (int)sizeof(real), Body::PARK_EXTRA) == TileLayout<Body, real, BLOCK>::BYTES &&
+               shapeTmaBytes(n_in, n_out, Body::STAGE_BUFFERS, BLOCK, (int)sizeof(real), Body::PARK_EXTRA) == TmaLayout<Body, real, BLOCK>::BYTES;
     }
 
     template <typename real, typename Body, int BLOCK, int MIN_BLOCKS>
@@ -921,11 +959,22 @@ namespace grbda_kernels
         const bool has_state = ts < rows;
         const int t = min(ts, rows - 1);
         const int64_t state = first + t;
-        real *o0 = L::STAGE_OUT0 ? so + t * L::SO : out0 + state * Body::N_OUT0;
+        const int tr = parkedCooperative<Body>() ? ts : t; // row this thread works in
+        if (parkedCooperative<Body>() && rows < BLOCK)     // (CTA-uniform)
+        {
+            if (!has_state)
+            {
+                replicateRow<real, Body::N_IN0>(s0 + tr * L::S0, s0 + t * L::S0);
+                replicateRow<real, Body::N_IN1>(s1 + tr * L::S1, s1 + t * L::S1);
+                replicateRow<real, Body::N_IN2>(s2 + tr * L::S2, s2 + t * L::S2);
+            }
+            __syncthreads();
+        }
+        real *o0 = L::STAGE_OUT0 ? so + tr * L::SO : out0 + state * Body::N_OUT0;
         real *o1 = Body::N_OUT1 ? out1 + state * Body::N_OUT1 : nullptr;
         real *o2 = Body::N_OUT2 ? out2 + state * Body::N_OUT2 : nullptr;
         const OutStage<real> stage = makeOutStage<Body, real>(smem_raw + L::TILE_BYTES, out0, out1, out2, first, rows, batch, ts);
-        const real *i0 = s0 + t * L::S0, *i1 = s1 + t * L::S1, *i2 = s2 + t * L::S2;
+        const real *i0 = s0 + tr * L::S0, *i1 = s1 + tr * L::S1, *i2 = s2 + tr * L::S2;
         if (GRBDA_RANGE_CHECKED(Body))
         {
             const bool ok = __syncthreads_and(Body::template inRange<real>(i0, i1, i2));
@@ -934,7 +983,7 @@ namespace grbda_kernels
             if (!ok)
                 return; // CTA-uniform: the second pass recomputes this tile
         }
-        if (!Body::PARKED || has_state) // parked rows are private: no tail replicas
+        if (!Body::PARKED || has_state || parkedCooperative<Body>()) // parked rows are private: no tail replicas
             runBody<Body, real, true>(i0, i1, i2, o0, o1, o2, stage);
         gridLaunchDependents();
 

@@ -32,33 +32,45 @@ namespace grbda_kernels
 
     // elem = sizeof(real); the static_asserts in the kernels keep these in step with TileLayout / TmaLayout
     GRBDA_HD constexpr size_t shapeAlign16(size_t x) { return (x + 15) & ~(size_t)15; }
-    GRBDA_HD constexpr size_t shapeStageBytes(const int *n_out, int stage_buffers, int block, int elem)
+    GRBDA_HD constexpr size_t shapeChunkStageBytes(const int *n_out, int stage_buffers, int block, int elem)
     {
         return (n_out[0] > 64 || n_out[1] > OUT_CHUNK || n_out[2] > OUT_CHUNK)
                    ? (size_t)stage_buffers * block * (OUT_CHUNK + 1) * elem
                    : 0;
     }
+    // A parked body may own `park_extra` more slots per thread than its tile rows offer (kernels whose tiles leave
+    // shared memory unused: the mass matrix has one input row and holds its results until their chunk is
+    // complete). Odd stride: conflict-free for 4- and 8-byte elements.
+    GRBDA_HD constexpr size_t shapeParkBytes(int park_extra, int block, int elem)
+    {
+        return park_extra > 0 ? (size_t)block * oddStride(park_extra) * elem : 0;
+    }
+    // everything behind the tiles: chunk staging buffers / rings, then the park area
+    GRBDA_HD constexpr size_t shapeStageBytes(const int *n_out, int stage_buffers, int block, int elem, int park_extra = 0)
+    {
+        return shapeChunkStageBytes(n_out, stage_buffers, block, elem) + shapeParkBytes(park_extra, block, elem);
+    }
     GRBDA_HD constexpr size_t shapeTileBytes(const int *n_in, const int *n_out, int stage_buffers, int block,
-                                                        int elem)
+                                                        int elem, int park_extra = 0)
     {
         size_t elems = 0;
         for (int i = 0; i < 3; i++)
             elems += n_in[i] ? (size_t)oddStride(n_in[i]) * block : 0;
         elems += n_out[0] <= 64 ? (size_t)oddStride(n_out[0]) * block : 0;
-        return shapeAlign16(elems * elem) + shapeStageBytes(n_out, stage_buffers, block, elem);
+        return shapeAlign16(elems * elem) + shapeStageBytes(n_out, stage_buffers, block, elem, park_extra);
     }
     GRBDA_HD constexpr int shapeTmaStride(int n, int elem)
     {
         return (n >= 12 && (n * elem) % 16 == 0) ? n + 16 / elem : n;
     }
     GRBDA_HD constexpr size_t shapeTmaBytes(const int *n_in, const int *n_out, int stage_buffers, int block,
-                                                       int elem)
+                                                       int elem, int park_extra = 0)
     {
         size_t off = 16;
         for (int i = 0; i < 3; i++)
             off = shapeAlign16(off + (size_t)shapeTmaStride(n_in[i], elem) * block * elem);
         off = shapeAlign16(off + (n_out[0] <= 64 ? (size_t)shapeTmaStride(n_out[0], elem) * block * elem : 0));
-        return off + shapeStageBytes(n_out, stage_buffers, block, elem);
+        return off + shapeStageBytes(n_out, stage_buffers, block, elem, park_extra);
     }
 } // namespace grbda_kernels
 #endif // GRBDA_KERNELS_SHAPES_H

@@ -479,7 +479,7 @@ extern "C"
         return guarded([&]
                        {
             compiler::ConstTable consts;
-            const compiler::CompiledAlgo c = compiler::compileAlgo(m->model, program, true, 0, &consts, 16, park != 0);
+            const compiler::CompiledAlgo c = compiler::compileAlgo(m->model, program, true, 0, &consts, 16, park != 0, true, park > 1 ? park - 1 : 0);
             std::ofstream f(path);
             if (!f)
                 return fail(GRBDA_ERR_IO, std::string("cannot write ") + path);

@@ -205,6 +205,14 @@ int main(int argc, char **argv)
                 for (auto &v : variants)
                     if (v.park && grbda_kernels::shapeTileBytes(n_in, n_out, 3, v.block, 8) > grbda_kernels::SLOW_PASS_STAGED_LIMIT)
                         v.park = false;
+                // Programs with large outputs (mass matrix): parking pays where the unparked body spills the results
+                // that wait for their chunk. Measured on B200 (profiles/README.md, per 2^20 states, unparked -> parked):
+                // nv = 24: 1.126 -> 1.014 ms (TelloWithArms), 1.127 -> 1.025 (MIT humanoid); nv = 38: 6.20 -> 5.80 (JVRC1);
+                // nv = 18: 0.533 -> 0.531 (Mini Cheetah); nv = 16: 0.442 -> 0.467 (Tello); nv = 8: 0.104 -> 0.132.
+                if (grbda_kernels::shapeChunkStageBytes(n_out, 1, 32, 8) > 0 && std::max(n_out[0], std::max(n_out[1], n_out[2])) < 400 &&
+                    !std::getenv("GRBDA_PARK_SMALL_OUTPUTS"))
+                    for (auto &v : variants)
+                        v.park = false;
             }
             // vector-store bodies (large outputs) need CTAs of four warps: only if every variant has them
             bool vec_ok = true;
@@ -212,8 +220,38 @@ int main(int argc, char **argv)
                 vec_ok = vec_ok && v.block % 128 == 0;
             auto programOf = [&](const Variant &v) { return v.program >= 0 ? v.program : a; };
             auto bodyKey = [&](const Variant &v) { return (v.sync * 2 + (v.park ? 1 : 0)) * 16 + programOf(v); };
-            const CompiledAlgo c = compileAlgo(model, programOf(variants[0]), true, variants[0].sync, &consts, out_chunk,
-                                               variants[0].park, vec_ok);
+            CompiledAlgo c = compileAlgo(model, programOf(variants[0]), true, variants[0].sync, &consts, out_chunk,
+                                         variants[0].park, vec_ok);
+            // Park area: a parked body of a program with large outputs (mass matrix: one input row, results held until
+            // their chunk is complete) gets the shared memory its tiles leave unused, as extra parking slots per
+            // thread - as many as every parked variant of the entry point (and its flagged-tile pass) can hold.
+            int park_extra = 0;
+            if (grbda_kernels::shapeChunkStageBytes(c.n_out, 1, 32, 8) > 0 || std::getenv("GRBDA_PARK_EXTRA_ALL"))
+            {
+                long slots = 96;
+                bool any = false;
+                for (auto &v : variants)
+                {
+                    if (!v.park)
+                        continue;
+                    any = true;
+                    const size_t tiles = v.kind == 'T' ? grbda_kernels::shapeTmaBytes(c.n_in, c.n_out, c.stage_buffers, v.block, 8)
+                                                       : grbda_kernels::shapeTileBytes(c.n_in, c.n_out, c.stage_buffers, v.block, 8);
+                    long per_cta = (long)(grbda_kernels::SM_SHARED_BYTES / v.min_blocks) - 1024 - (long)tiles;
+                    if (per_cta < 0) // the variant does not reach its CTA count anyway: what one CTA per SM leaves
+                        per_cta = (long)grbda_kernels::SM_SHARED_BYTES - 1024 - (long)tiles;
+                    const long slow = (long)grbda_kernels::SLOW_PASS_STAGED_LIMIT -
+                                      (long)grbda_kernels::shapeTileBytes(c.n_in, c.n_out, c.stage_buffers, v.block, 8);
+                    slots = std::min(slots, std::min(per_cta, slow) / (long)(v.block * 8));
+                }
+                if (const char *e = std::getenv("GRBDA_PARK_EXTRA")) // tuning experiments
+                    slots = std::min<long>(slots, std::atol(e));
+                if (any && slots >= 3)
+                    park_extra = (int)(slots % 2 ? slots : slots - 1); // odd: the stride of the area is the slot count
+                if (park_extra > 0 && variants[0].park)
+                    c = compileAlgo(model, programOf(variants[0]), true, variants[0].sync, &consts, out_chunk, true, vec_ok,
+                                    park_extra);
+            }
             std::map<int, CompiledAlgo> by_sync; // distinct (alignment period, program) bodies
             // FP32 kernels do not spill (half the register footprint) and are faster without parking
             // (measured: forward dynamics 0.386 against 0.414 ms): their launchers use the unparked body
@@ -226,7 +264,8 @@ int main(int argc, char **argv)
             for (auto &v : variants)
             {
                 if (!by_sync.count(bodyKey(v)))
-                    by_sync[bodyKey(v)] = compileAlgo(model, programOf(v), true, v.sync, &consts, out_chunk, v.park, vec_ok);
+                    by_sync[bodyKey(v)] = compileAlgo(model, programOf(v), true, v.sync, &consts, out_chunk, v.park, vec_ok,
+                                                      v.park ? park_extra : 0);
                 const Variant u = f32Variant(v);
                 if (!by_sync.count(bodyKey(u))) // also the body of the direct-I/O fallback
                     by_sync[bodyKey(u)] = compileAlgo(model, programOf(u), true, u.sync, &consts, out_chunk, false, vec_ok);
@@ -248,8 +287,9 @@ int main(int argc, char **argv)
                 if (v.kind == 'T' || v.kind == 'S')
                 {
                     const int elem = std::string(real) == "float" ? 4 : 8;
-                    const size_t bytes = v.kind == 'T' ? grbda_kernels::shapeTmaBytes(c.n_in, c.n_out, c.stage_buffers, v.block, elem)
-                                                       : grbda_kernels::shapeTileBytes(c.n_in, c.n_out, c.stage_buffers, v.block, elem);
+                    const int extra = v.park ? park_extra : 0;
+                    const size_t bytes = v.kind == 'T' ? grbda_kernels::shapeTmaBytes(c.n_in, c.n_out, c.stage_buffers, v.block, elem, extra)
+                                                       : grbda_kernels::shapeTileBytes(c.n_in, c.n_out, c.stage_buffers, v.block, elem, extra);
                     if (bytes + 1024 > grbda_kernels::SM_SHARED_BYTES) // not even one CTA per SM
                     {
                         v.kind = 'D';

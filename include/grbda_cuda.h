@@ -162,7 +162,8 @@ grbda_status grbda_cuda_dump_program(const grbda_model *m, int algo, const char 
 /* The CUDA source the model compiler emits for one program (0 ID, 1 FD, 2 FK, 3 H, 4 phi, 5/6 external-force programs, 7 FD/LTDL):
  * constant table + `struct Body` (sizes, generated range check, run<real, FAST>()), exactly what
  * build.py feeds to nvcc, written to `path`. park != 0: the variant that parks long-lived values in the
- * thread's shared-memory tile row. Used by the emitter self test, which compiles this text for the
+ * thread's shared-memory tile row; park = 1 + n: with a park area of n more slots per thread behind the tiles
+ * (kernels/shapes.h shapeParkBytes). Used by the emitter self test, which compiles this text for the
  * host with the kernel-side helpers stubbed (tests/host_body_prelude.h) and compares with the oracle. */
 grbda_status grbda_cuda_emit_source(const grbda_model *m, int program, int park, const char *path);
 

@@ -43,6 +43,7 @@ namespace host_body
             }
         };
         mutable Ring ring[3]; // ring-store bodies (the device keeps the slots in shared memory)
+        real *park = nullptr; // park area of a parked body (Body::PARK_EXTRA slots)
     };
     template <int E, typename R, typename real>
     inline void ringPut(R &r, real x)

@@ -368,6 +368,8 @@ int main(int argc, char **argv)
         // ring-store bodies: the row of state b starts (b M) mod 4 values into its sector
         st.ring[0].init(&out0[b * M0], (int)((b * M0) & 3)), st.ring[1].init(&out1[b * M1], (int)((b * M1) & 3));
         st.ring[2].init(&out2[b * M2], (int)((b * M2) & 3));
+        double park_area[Body::PARK_EXTRA + 1];
+        st.park = park_area;
         const bool staged_out = M0 <= 64;
         Body::run<double, true>(r0, r1, r2, staged_out ? o0 : &out0[b * M0], &out1[b * M1], &out2[b * M2], st);
         if (staged_out)
@@ -389,7 +391,7 @@ def run_emitted_source(m, program, park, ins, tmp_path, tag):
     import subprocess
     d = tmp_path / tag
     d.mkdir()
-    m.emit_source(program, str(d / "body.inc"), park=park)
+    m.emit_source(program, str(d / "body.inc"), park=int(park))
     (d / "main.cpp").write_text(HOST_MAIN)
     exe = str(d / "run")
     subprocess.run(["/usr/bin/g++", "-O0", "-std=c++17", "-I", os.path.dirname(os.path.abspath(__file__)), "-I", str(d), "-o", exe, str(d / "main.cpp")],
@@ -454,6 +456,16 @@ def test_emitted_cuda_text_on_the_host(grbda, oracle, robot, tmp_path, monkeypat
     assert rel(outs[0].reshape(-1, o.nv, o.nv), o.mass_matrix(q)) < TOL
     if robot == "tello_with_arms":
         assert "VECTOR_STORES = false" in text and "STG_FLUSH0(" in text
+    # ... and parks the results that wait for their chunk: in the dead slots of its input row and in the park area
+    # behind the tiles (park = 1 + 41 slots); forward kinematics with a park area (in-order drain through the rings)
+    outs, _, text = run_emitted_source(m, 3, 42, [q], tmp_path, "h_parked")
+    assert rel(outs[0].reshape(-1, o.nv, o.nv), o.mass_matrix(q)) < TOL
+    if robot == "tello_with_arms":
+        assert "PARKED = true" in text and "PARK_EXTRA = 41" in text and "STG_FLUSH0(" in text
+        assert text.count("PARK_ST(4, ") > 30 and text.count("PARK_ST(0, ") > 10
+    outs, _, text = run_emitted_source(m, 2, 12, [q, yd], tmp_path, "fk_parked")
+    assert rel(outs[0].reshape(p.shape), p) < TOL and rel(outs[1].reshape(R.shape), R) < TOL
+    assert rel(outs[2].reshape(v.shape), v) < TOL
     # the generated range check rejects a joint angle beyond the fast sin/cos range
     q_far = q.copy()
     q_far[3, m.clusters()[-1]["position_index"]] = 3.0e13
