@@ -209,8 +209,9 @@ int main(int argc, char **argv)
                 // that wait for their chunk. Measured on B200 (profiles/README.md, per 2^20 states, unparked -> parked):
                 // nv = 24: 1.126 -> 1.014 ms (TelloWithArms), 1.127 -> 1.025 (MIT humanoid); nv = 38: 6.20 -> 5.80 (JVRC1);
                 // nv = 18: 0.533 -> 0.531 (Mini Cheetah); nv = 16: 0.442 -> 0.467 (Tello); nv = 8: 0.104 -> 0.132.
-                if (grbda_kernels::shapeChunkStageBytes(n_out, 1, 32, 8) > 0 && std::max(n_out[0], std::max(n_out[1], n_out[2])) < 400 &&
-                    !std::getenv("GRBDA_PARK_SMALL_OUTPUTS"))
+                // (a mass matrix of up to 64 values is staged as a row and never held: 0.104 -> 0.136 ms parked, nv = 8)
+                if ((a == ALGO_H || grbda_kernels::shapeChunkStageBytes(n_out, 1, 32, 8) > 0) &&
+                    std::max(n_out[0], std::max(n_out[1], n_out[2])) < 400 && !std::getenv("GRBDA_PARK_SMALL_OUTPUTS"))
                     for (auto &v : variants)
                         v.park = false;
             }
