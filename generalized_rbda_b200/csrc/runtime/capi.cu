@@ -714,11 +714,35 @@ extern "C"
             pending[s].nb = 0;
             return de;
         };
-        int k = 0;
-        for (int64_t b0 = 0; b0 < batch && rs == GRBDA_OK; b0 += chunk, k++)
+        // Chunk sizes. The first chunk's upload and the last chunk's download overlap with nothing, so the pipeline
+        // opens and closes with short chunks (1/8, 1/4, 1/2 of the steady-state size) - uniformly short chunks are
+        // slower (tools/e2e_sweep.py). Measured: 14.47 -> 14.37 ms per 2^20 Tello states at 128 k chunks, 15.18 -> 14.66 ms
+        // at 256 k: the call sits on the duplex host link (H2D 47 GB/s while D2H runs), not on fill and drain.
+        // GRBDA_HOST_RAMP=0: uniform chunks.
+        std::vector<int64_t> sizes;
         {
-            const int64_t nb = std::min(chunk, batch - b0);
-            const int s = k % grbda_model::NSTREAM;
+            static const bool ramp = !(std::getenv("GRBDA_HOST_RAMP") && std::getenv("GRBDA_HOST_RAMP")[0] == '0');
+            const int64_t edge[3] = {chunk / 8, chunk / 4, chunk / 2};
+            const int64_t edges = edge[0] + edge[1] + edge[2];
+            int64_t left = batch;
+            if (ramp && chunk >= 8192 && batch >= 2 * chunk)
+            {
+                for (int i = 0; i < 3; i++)
+                    sizes.push_back(edge[i]);
+                left -= 2 * edges;
+            }
+            const bool ramped = !sizes.empty();
+            for (; left > 0; left -= chunk)
+                sizes.push_back(std::min(chunk, left));
+            if (ramped)
+                for (int i = 2; i >= 0; i--)
+                    sizes.push_back(edge[i]);
+        }
+        int64_t b0 = 0;
+        for (size_t k = 0; k < sizes.size() && rs == GRBDA_OK; b0 += sizes[k], k++)
+        {
+            const int64_t nb = sizes[k];
+            const int s = (int)(k % grbda_model::NSTREAM);
             cudaStream_t st = m->streams[s];
             double *dq = m->dev_buf[s], *dyd = dq + chunk * nq, *din = dyd + chunk * nv, *dout = din + chunk * nv,
                    *dout2 = dout + chunk * nv;
