@@ -35,7 +35,8 @@ LIB = os.path.join(_OUT, "libgrbda_cuda.so")
 # D = direct global I/O. 'ltl' = forward dynamics as CRBA + bias + sparse LTDL (otherwise the
 # articulated-body sweep), 'auto' = whichever of the two the measured rule picks for the model
 # (compiler/compile.h chooseForwardDynamicsProgram); 'park' = long-lived values parked in dead slots of the thread's
-# shared-memory tile row instead of being spilled (T and S only); 'f32aba' = the FP32 kernel of the variant runs the
+# shared-memory tile row instead of being spilled (T and S only); 'direct' = the (small) output 0 is stored straight to
+# global memory instead of through an output tile (frees shared memory for another CTA); 'f32aba' = the FP32 kernel of the variant runs the
 # articulated-body sweep. Measured on B200 (profiles/README.md): T,128,2 is the fastest
 # and the most device-independent shape for every entry point.
 # 'park' on the mass matrix: its results wait in registers for their 16-value chunk (91 spilled doubles on TelloWithArms);
@@ -52,9 +53,12 @@ MODELS = {
     "planar_leg_linkage": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
     "mit_humanoid_leg": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
     # 58 bodies: the tile rows of a 128-thread CTA take 163 KB (one CTA per SM); 64-thread CTAs fit twice.
-    # Both dynamics kernels spill and are parked (ID 1.01 -> 0.86 ms, FD 3.3-4.2 ms per 2^20 states, L2 dependent)
+    # Both dynamics kernels spill and are parked (ID 1.01 -> 0.86 ms, FD 3.3-4.2 ms per 2^20 states, L2 dependent).
+    # Inverse dynamics: without an output tile ('direct': 38 plain stores per thread) THREE 64-thread CTAs fit, and what
+    # they leave becomes park area: 0.444 -> 0.375 ms per 2^19 states. Forward dynamics loses more parking slots than
+    # the third CTA gives back (1.92 -> 2.17 ms): unchanged.
     "jvrc1_humanoid": ("id,fd,fk,h,phi,gfa,gfs,gen",
-                       "id=T,64,2,park;T,128,2,park;S,128,2|fd=T,64,2,ltl,park;T,128,2,ltl,park;T,64,2,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2,park;T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2", True),
+                       "id=T,64,3,park,direct;T,64,2,park;T,128,2,park;S,128,2|fd=T,64,2,ltl,park;T,128,2,ltl,park;T,64,2,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2,park;T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2", True),
     "revolute_rotor_chain": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_2": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_4": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),

@@ -54,6 +54,7 @@ namespace grbda
             bool parked = false;     // body parks long-lived values in the thread's shared-memory row
             int num_parked = 0;
             int park_extra = 0;      // slots per thread of the park area behind the tiles (parked bodies)
+            bool direct_out = false; // output 0 is stored straight to global memory although it is small (no output tile)
             int stage_buffers = 1;   // chunked outputs: staging buffers per warp (1, or one per output array)
             bool vector_stores = false; // large outputs leave as 256-bit stores of the thread's own row (emit.h)
             bool ring_stores = false;   // ... assembled in per-thread shared-memory rings (emit.h, row_stores = 2)
@@ -227,7 +228,8 @@ namespace grbda
 
         inline CompiledAlgo compileAlgo(const ClusterTreeModel &model, int algo, bool want_body = true,
                                         int sync_every = 0, ConstTable *consts = nullptr, int out_chunk = 0,
-                                        bool park = false, bool allow_vector_stores = true, int park_extra = 0)
+                                        bool park = false, bool allow_vector_stores = true, int park_extra = 0,
+                                        bool direct_out = false)
         {
             sym::Graph graph;
             sym::GraphScope scope(graph);
@@ -246,7 +248,7 @@ namespace grbda
                 ParkConfig pc;
                 for (int i = 0; i < 3; i++)
                     pc.n_slots[i] = p.n_in[i];
-                pc.n_slots[3] = out.n_out[0] <= 64 ? out.n_out[0] : 0; // the shells stage output 0 when it is small
+                pc.n_slots[3] = out.n_out[0] <= 64 && !direct_out ? out.n_out[0] : 0; // the shells stage output 0 when it is small
                 pc.n_slots[4] = park_extra;                            // park area behind the tiles
                 // Programs with large outputs (mass matrix) hold their results until a 16-value chunk is complete: many
                 // values that wait a few hundred statements each, not a few that wait for half the program. Measured
@@ -271,6 +273,7 @@ namespace grbda
                 out.body = em.cudaBody(sync_every, out_chunk, out.parked ? &pc : nullptr, row_stores);
                 out.num_parked = em.numParked();
                 out.park_extra = out.parked ? park_extra : 0;
+                out.direct_out = direct_out && out.n_out[0] <= 64;
                 out.stage_buffers = em.stageBuffers();
                 out.vector_stores = em.vectorStores();
                 out.ring_stores = em.ringStores();
@@ -314,6 +317,7 @@ namespace grbda
             os << "    static constexpr bool PARKED = " << (c.parked ? "true" : "false") << "; // " << c.num_parked
                << " values parked in the thread's tile row\n";
             os << "    static constexpr int PARK_EXTRA = " << c.park_extra << ";\n";
+            os << "    static constexpr bool DIRECT_OUT0 = " << (c.direct_out ? "true" : "false") << ";\n";
             os << "    template <typename real>\n    static __device__ __forceinline__ bool inRange(const real "
                   "*__restrict__ in0, const real *__restrict__ in1,\n        const real *__restrict__ in2)\n    {\n"
                   "#define KC(x) ((real)(x))\n#define IN0(i) in0[i]\n#define IN1(i) in1[i]\n#define IN2(i) in2[i]\n"

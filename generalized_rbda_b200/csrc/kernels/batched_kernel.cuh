@@ -609,7 +609,7 @@ namespace grbda_kernels
         static constexpr int S0 = Body::N_IN0 ? oddStride(Body::N_IN0) : 0;
         static constexpr int S1 = Body::N_IN1 ? oddStride(Body::N_IN1) : 0;
         static constexpr int S2 = Body::N_IN2 ? oddStride(Body::N_IN2) : 0;
-        static constexpr bool STAGE_OUT0 = Body::N_OUT0 <= 64;
+        static constexpr bool STAGE_OUT0 = Body::N_OUT0 <= 64 && !Body::DIRECT_OUT0;
         static constexpr int SO = STAGE_OUT0 ? oddStride(Body::N_OUT0) : 0;
         static constexpr int OFF1 = S0 * BLOCK;
         static constexpr int OFF2 = OFF1 + S1 * BLOCK;
@@ -898,7 +898,7 @@ namespace grbda_kernels
     {
         static constexpr int S0 = tmaStride<real>(Body::N_IN0), S1 = tmaStride<real>(Body::N_IN1),
                              S2 = tmaStride<real>(Body::N_IN2);
-        static constexpr bool STAGE_OUT0 = Body::N_OUT0 <= 64;
+        static constexpr bool STAGE_OUT0 = Body::N_OUT0 <= 64 && !Body::DIRECT_OUT0;
         static constexpr int SO = STAGE_OUT0 ? tmaStride<real>(Body::N_OUT0) : 0;
         // byte offsets; every tile starts on a 16-byte boundary, the first 16 bytes hold the mbarrier
         static constexpr size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -914,8 +914,8 @@ namespace grbda_kernels
     __host__ __device__ constexpr bool shapeMirrorsAgree()
     {
         const int n_in[3] = {Body::N_IN0, Body::N_IN1, Body::N_IN2}, n_out[3] = {Body::N_OUT0, Body::N_OUT1, Body::N_OUT2};
-        return shapeTileBytes(n_in, n_out, Body::STAGE_BUFFERS, BLOCK, (int)sizeof(real), Body::PARK_EXTRA) == TileLayout<Body, real, BLOCK>::BYTES &&
-               shapeTmaBytes(n_in, n_out, Body::STAGE_BUFFERS, BLOCK, (int)sizeof(real), Body::PARK_EXTRA) == TmaLayout<Body, real, BLOCK>::BYTES;
+        return shapeTileBytes(n_in, n_out, Body::STAGE_BUFFERS, BLOCK, (int)sizeof(real), Body::PARK_EXTRA, Body::DIRECT_OUT0) == TileLayout<Body, real, BLOCK>::BYTES &&
+               shapeTmaBytes(n_in, n_out, Body::STAGE_BUFFERS, BLOCK, (int)sizeof(real), Body::PARK_EXTRA, Body::DIRECT_OUT0) == TmaLayout<Body, real, BLOCK>::BYTES;
     }
 
     template <typename real, typename Body, int BLOCK, int MIN_BLOCKS>

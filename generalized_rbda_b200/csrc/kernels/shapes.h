@@ -50,13 +50,15 @@ namespace grbda_kernels
     {
         return shapeChunkStageBytes(n_out, stage_buffers, block, elem) + shapeParkBytes(park_extra, block, elem);
     }
+    // direct_out: the (small) output 0 is not staged as a tile but stored by every thread straight to its own row in
+    // global memory (models whose rows otherwise keep an SM from holding its CTAs: JVRC1)
     GRBDA_HD constexpr size_t shapeTileBytes(const int *n_in, const int *n_out, int stage_buffers, int block,
-                                                        int elem, int park_extra = 0)
+                                                        int elem, int park_extra = 0, bool direct_out = false)
     {
         size_t elems = 0;
         for (int i = 0; i < 3; i++)
             elems += n_in[i] ? (size_t)oddStride(n_in[i]) * block : 0;
-        elems += n_out[0] <= 64 ? (size_t)oddStride(n_out[0]) * block : 0;
+        elems += n_out[0] <= 64 && !direct_out ? (size_t)oddStride(n_out[0]) * block : 0;
         return shapeAlign16(elems * elem) + shapeStageBytes(n_out, stage_buffers, block, elem, park_extra);
     }
     GRBDA_HD constexpr int shapeTmaStride(int n, int elem)
@@ -64,12 +66,12 @@ namespace grbda_kernels
         return (n >= 12 && (n * elem) % 16 == 0) ? n + 16 / elem : n;
     }
     GRBDA_HD constexpr size_t shapeTmaBytes(const int *n_in, const int *n_out, int stage_buffers, int block,
-                                                       int elem, int park_extra = 0)
+                                                       int elem, int park_extra = 0, bool direct_out = false)
     {
         size_t off = 16;
         for (int i = 0; i < 3; i++)
             off = shapeAlign16(off + (size_t)shapeTmaStride(n_in[i], elem) * block * elem);
-        off = shapeAlign16(off + (n_out[0] <= 64 ? (size_t)shapeTmaStride(n_out[0], elem) * block * elem : 0));
+        off = shapeAlign16(off + (n_out[0] <= 64 && !direct_out ? (size_t)shapeTmaStride(n_out[0], elem) * block * elem : 0));
         return off + shapeStageBytes(n_out, stage_buffers, block, elem, park_extra);
     }
 } // namespace grbda_kernels

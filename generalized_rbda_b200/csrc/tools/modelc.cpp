@@ -28,6 +28,7 @@ namespace
         int block, min_blocks;
         int program = -1; // alternative program of the entry point (-1: the entry's own), e.g. PROGRAM_FD_LTL
         bool park = false; // staged shells: long-lived values are parked in dead slots of the thread's tile row
+        bool direct = false; // output 0 goes straight to global memory although it is small (no output tile)
         bool f32_aba = false; // FP32 launcher of this variant runs the articulated-body sweep (deep fixed-base
                               // chains: H^-1 in FP32 loses cond(H) digits, the O(n) recursion does not)
     };
@@ -127,10 +128,10 @@ int main(int argc, char **argv)
         for (auto &v : split(spec, ';'))
         {
             auto p = split(v, ',');
-            if (p.size() < 3 || p.size() > 7 || p[0].size() != 1 ||
+            if (p.size() < 3 || p.size() > 8 || p[0].size() != 1 ||
                 std::string("SDT").find(p[0][0]) == std::string::npos)
                 throw std::runtime_error("bad --variants entry '" + v +
-                                         "' (expected KIND,BLOCK,MINBLOCKS[,SYNC][,ltl][,park][,f32aba])");
+                                         "' (expected KIND,BLOCK,MINBLOCKS[,SYNC][,ltl][,park][,direct][,f32aba])");
             Variant var;
             var.kind = p[0][0];
             var.block = std::atoi(p[1].c_str());
@@ -143,6 +144,8 @@ int main(int argc, char **argv)
                     var.program = -2;
                 else if (p[t] == "park")
                     var.park = var.kind == 'S' || var.kind == 'T';
+                else if (p[t] == "direct")
+                    var.direct = var.kind == 'S' || var.kind == 'T';
                 else if (p[t] == "f32aba")
                     var.f32_aba = true;
                 else
@@ -203,7 +206,7 @@ int main(int argc, char **argv)
                 int n_in[3], n_out[3];
                 algoSizes(model, a, n_in, n_out);
                 for (auto &v : variants)
-                    if (v.park && grbda_kernels::shapeTileBytes(n_in, n_out, 3, v.block, 8) > grbda_kernels::SLOW_PASS_STAGED_LIMIT)
+                    if (v.park && grbda_kernels::shapeTileBytes(n_in, n_out, 3, v.block, 8, 0, v.direct) > grbda_kernels::SLOW_PASS_STAGED_LIMIT)
                         v.park = false;
                 // Programs with large outputs (mass matrix): parking pays where the unparked body spills the results
                 // that wait for their chunk. Measured on B200 (profiles/README.md, per 2^20 states, unparked -> parked):
@@ -220,14 +223,19 @@ int main(int argc, char **argv)
             for (auto &v : variants)
                 vec_ok = vec_ok && v.block % 128 == 0;
             auto programOf = [&](const Variant &v) { return v.program >= 0 ? v.program : a; };
-            auto bodyKey = [&](const Variant &v) { return (v.sync * 2 + (v.park ? 1 : 0)) * 16 + programOf(v); };
+            auto bodyKey = [&](const Variant &v) { return ((v.sync * 2 + (v.park ? 1 : 0)) * 2 + (v.direct ? 1 : 0)) * 16 + programOf(v); };
             CompiledAlgo c = compileAlgo(model, programOf(variants[0]), true, variants[0].sync, &consts, out_chunk,
-                                         variants[0].park, vec_ok);
+                                         variants[0].park, vec_ok, 0, variants[0].direct);
             // Park area: a parked body of a program with large outputs (mass matrix: one input row, results held until
             // their chunk is complete) gets the shared memory its tiles leave unused, as extra parking slots per
             // thread - as many as every parked variant of the entry point (and its flagged-tile pass) can hold.
             int park_extra = 0;
-            if (grbda_kernels::shapeChunkStageBytes(c.n_out, 1, 32, 8) > 0 || std::getenv("GRBDA_PARK_EXTRA_ALL"))
+            // ... and a body whose output tile was given up for a third CTA per SM (`direct`) gets back as park area
+            // what the three CTAs leave (JVRC1 inverse dynamics: 0.444 -> 0.427 ms per 2^19 states without, 0.375 with)
+            bool any_direct = false;
+            for (auto &v : variants)
+                any_direct = any_direct || (v.direct && v.park);
+            if (grbda_kernels::shapeChunkStageBytes(c.n_out, 1, 32, 8) > 0 || any_direct || std::getenv("GRBDA_PARK_EXTRA_ALL"))
             {
                 long slots = 96;
                 bool any = false;
@@ -236,13 +244,13 @@ int main(int argc, char **argv)
                     if (!v.park)
                         continue;
                     any = true;
-                    const size_t tiles = v.kind == 'T' ? grbda_kernels::shapeTmaBytes(c.n_in, c.n_out, c.stage_buffers, v.block, 8)
-                                                       : grbda_kernels::shapeTileBytes(c.n_in, c.n_out, c.stage_buffers, v.block, 8);
+                    const size_t tiles = v.kind == 'T' ? grbda_kernels::shapeTmaBytes(c.n_in, c.n_out, c.stage_buffers, v.block, 8, 0, v.direct)
+                                                       : grbda_kernels::shapeTileBytes(c.n_in, c.n_out, c.stage_buffers, v.block, 8, 0, v.direct);
                     long per_cta = (long)(grbda_kernels::SM_SHARED_BYTES / v.min_blocks) - 1024 - (long)tiles;
                     if (per_cta < 0) // the variant does not reach its CTA count anyway: what one CTA per SM leaves
                         per_cta = (long)grbda_kernels::SM_SHARED_BYTES - 1024 - (long)tiles;
                     const long slow = (long)grbda_kernels::SLOW_PASS_STAGED_LIMIT -
-                                      (long)grbda_kernels::shapeTileBytes(c.n_in, c.n_out, c.stage_buffers, v.block, 8);
+                                      (long)grbda_kernels::shapeTileBytes(c.n_in, c.n_out, c.stage_buffers, v.block, 8, 0, v.direct);
                     slots = std::min(slots, std::min(per_cta, slow) / (long)(v.block * 8));
                 }
                 if (const char *e = std::getenv("GRBDA_PARK_EXTRA")) // tuning experiments
@@ -251,7 +259,7 @@ int main(int argc, char **argv)
                     park_extra = (int)(slots % 2 ? slots : slots - 1); // odd: the stride of the area is the slot count
                 if (park_extra > 0 && variants[0].park)
                     c = compileAlgo(model, programOf(variants[0]), true, variants[0].sync, &consts, out_chunk, true, vec_ok,
-                                    park_extra);
+                                    park_extra, variants[0].direct);
             }
             std::map<int, CompiledAlgo> by_sync; // distinct (alignment period, program) bodies
             // FP32 kernels do not spill (half the register footprint) and are faster without parking
@@ -266,7 +274,7 @@ int main(int argc, char **argv)
             {
                 if (!by_sync.count(bodyKey(v)))
                     by_sync[bodyKey(v)] = compileAlgo(model, programOf(v), true, v.sync, &consts, out_chunk, v.park, vec_ok,
-                                                      v.park ? park_extra : 0);
+                                                      v.park ? park_extra : 0, v.direct);
                 const Variant u = f32Variant(v);
                 if (!by_sync.count(bodyKey(u))) // also the body of the direct-I/O fallback
                     by_sync[bodyKey(u)] = compileAlgo(model, programOf(u), true, u.sync, &consts, out_chunk, false, vec_ok);
@@ -289,8 +297,8 @@ int main(int argc, char **argv)
                 {
                     const int elem = std::string(real) == "float" ? 4 : 8;
                     const int extra = v.park ? park_extra : 0;
-                    const size_t bytes = v.kind == 'T' ? grbda_kernels::shapeTmaBytes(c.n_in, c.n_out, c.stage_buffers, v.block, elem, extra)
-                                                       : grbda_kernels::shapeTileBytes(c.n_in, c.n_out, c.stage_buffers, v.block, elem, extra);
+                    const size_t bytes = v.kind == 'T' ? grbda_kernels::shapeTmaBytes(c.n_in, c.n_out, c.stage_buffers, v.block, elem, extra, v.direct)
+                                                       : grbda_kernels::shapeTileBytes(c.n_in, c.n_out, c.stage_buffers, v.block, elem, extra, v.direct);
                     if (bytes + 1024 > grbda_kernels::SM_SHARED_BYTES) // not even one CTA per SM
                     {
                         v.kind = 'D';
