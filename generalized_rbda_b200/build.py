@@ -42,11 +42,17 @@ LIB = os.path.join(_OUT, "libgrbda_cuda.so")
 # 'park' on the mass matrix: its results wait in registers for their 16-value chunk (91 spilled doubles on TelloWithArms);
 # the body parks them in the park area - the shared memory its single input row leaves unused (kernels/shapes.h)
 DEFAULT_VARIANTS = "id=T,128,2;S,128,2|fd=T,128,2,auto,park;T,128,2,ltl,park;T,128,2;S,128,2|fk=T,128,2;S,128,2|h=T,128,2,park;T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2"
+# Inverse dynamics with THREE 128-thread CTAs per SM: without an output tile ('direct') the rows of the mid-size models
+# fit three times, and their bodies fit 168 registers without spilling. Measured on B200 per 2^20 states (128 x 2 ->
+# 128 x 3): Mini Cheetah 0.205 -> 0.157 ms, 16-link chain 0.206 -> 0.159, Tello 0.238 -> 0.219; no gain or a loss for the
+# small models (launch / HBM bound) and for MIT humanoid / TelloWithArms (rows too long, bodies too large:
+# profiles/README.md). Forward dynamics needs its registers: 0.313 -> 0.363 ms (Mini Cheetah).
+ID3_VARIANTS = DEFAULT_VARIANTS.replace("id=T,128,2;S,128,2", "id=T,128,3,direct;T,128,2;S,128,2")
 SYNC_EVERY = int(os.environ.get("GRBDA_SYNC_EVERY", "0"))  # alignment barriers measured useless (profiles/)
 MODELS = {
     "tello_with_arms": ("id,fd,fk,h,phi,gfa,gfs,gen", "id=T,128,2;S,128,2|fd=T,128,2,ltl,park;T,128,2,ltl;S,128,2,ltl,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2,park;T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2", True),
-    "tello": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
-    "mini_cheetah": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
+    "tello": ("id,fd,fk,h,phi,gfa,gfs,gen", ID3_VARIANTS, False),
+    "mini_cheetah": ("id,fd,fk,h,gfa,gfs,gen", ID3_VARIANTS, True),
     "mit_humanoid": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "four_bar": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "six_bar": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
@@ -67,7 +73,7 @@ MODELS = {
     # FP32: forward dynamics of the 16-link fixed-base chain (cond(H) ~ 2e4) through the articulated-body sweep:
     # median error 6e-7 instead of 1e-4 with the factorisation (measured, tests/test_gpu_parity.py)
     "revolute_chain_with_rotor_16": ("id,fd,fk,h,gfa,gfs,gen",
-                                     DEFAULT_VARIANTS.replace("fd=T,128,2,auto,park;", "fd=T,128,2,auto,park,f32aba;"), True),
+                                     ID3_VARIANTS.replace("fd=T,128,2,auto,park;", "fd=T,128,2,auto,park,f32aba;"), True),
     "revolute_pair_chain_with_rotor_2": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
     "revolute_pair_chain_with_rotor_4": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
     # the remaining cluster-joint classes of the reference: RevolutePair (RevolutePairChain.cpp) and
