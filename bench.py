@@ -321,6 +321,16 @@ def main():
             "h_hbm_frac_per_gpu": 8 * (mh.nq + mh.nv * mh.nv) * n3h / (ms_h3 * 1e-3) / 1e9 / load_peaks()[0]["hbm_gbs"]}
         del mh, q3, yd3, tau3, out3, H3
         if world == 1:
+            # BASELINE config 2: mini_cheetah, 2^20 states, forward + inverse dynamics on one GPU
+            mc2 = grbda.ClusterTreeModel.from_robot("mini_cheetah", device=local_rank)
+            q2, yd2, tau2, _ = mc2.generateStates(1 << 20)
+            o2 = torch.empty_like(tau2)
+            mc2.forwardDynamics(q2, yd2, tau2, out=o2), mc2.inverseDynamics(q2, yd2, tau2, out=o2)
+            ms_fd2 = timed(lambda: mc2.forwardDynamics(q2, yd2, tau2, out=o2), 10) / 10
+            ms_id2 = timed(lambda: mc2.inverseDynamics(q2, yd2, tau2, out=o2), 10) / 10
+            extras["mini_cheetah_fwd_inv"] = {"states": 1 << 20, "fd_ms": ms_fd2, "id_ms": ms_id2,
+                                              "pairs_per_s": (1 << 20) / ((ms_fd2 + ms_id2) * 1e-3)}
+            del mc2, q2, yd2, tau2, o2
             sweep = []
             for depth in (2, 4, 8, 16, 24):
                 mc = grbda.ClusterTreeModel.from_robot("revolute_chain_with_rotor_%d" % depth, device=local_rank)
