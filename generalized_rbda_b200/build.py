@@ -48,6 +48,13 @@ DEFAULT_VARIANTS = "id=T,128,2;S,128,2|fd=T,128,2,auto,park;T,128,2,ltl,park;T,1
 # small models (launch / HBM bound) and for MIT humanoid / TelloWithArms (rows too long, bodies too large:
 # profiles/README.md). Forward dynamics needs its registers: 0.313 -> 0.363 ms (Mini Cheetah).
 ID3_VARIANTS = DEFAULT_VARIANTS.replace("id=T,128,2;S,128,2", "id=T,128,3,direct;T,128,2;S,128,2")
+# Forward dynamics of the SMALL models: bodies that fit 168 registers do not need parking (it costs them) and gain from
+# a third CTA per SM. Measured per 2^20 states (parked 128 x 2 -> unparked direct 128 x 3; unparked 128 x 2 in brackets):
+# 8-link chain 0.176 -> 0.088 ms (0.100), planar leg linkage 0.033 -> 0.026 (0.032), six-bar 0.045 -> 0.043, MIT
+# humanoid leg 0.069 -> 0.066, 4-link pair chain 0.032 -> 0.030; no change for the 2-4 link chains and the four-bar;
+# slower for everything larger (16-link chain 0.271 -> 0.380, Tello 0.395 -> 0.602, triple chain 0.358 -> 0.639).
+FD3_VARIANTS = DEFAULT_VARIANTS.replace("fd=T,128,2,auto,park;T,128,2,ltl,park;T,128,2;S,128,2",
+                                        "fd=T,128,3,auto,direct;T,128,2,auto,park;T,128,2;S,128,2")
 SYNC_EVERY = int(os.environ.get("GRBDA_SYNC_EVERY", "0"))  # alignment barriers measured useless (profiles/)
 MODELS = {
     "tello_with_arms": ("id,fd,fk,h,phi,gfa,gfs,gen", "id=T,128,2;S,128,2|fd=T,128,2,ltl,park;T,128,2,ltl;S,128,2,ltl,park;S,128,2|fk=T,128,2;S,128,2|h=T,128,2,park;T,128,2;S,128,2|phi=S,128,2|gfa=T,128,2;S,128,2|gfs=T,128,2;S,128,2", True),
@@ -55,9 +62,9 @@ MODELS = {
     "mini_cheetah": ("id,fd,fk,h,gfa,gfs,gen", ID3_VARIANTS, True),
     "mit_humanoid": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "four_bar": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, True),
-    "six_bar": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
-    "planar_leg_linkage": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
-    "mit_humanoid_leg": ("id,fd,fk,h,phi,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    "six_bar": ("id,fd,fk,h,phi,gfa,gfs,gen", FD3_VARIANTS, False),
+    "planar_leg_linkage": ("id,fd,fk,h,phi,gfa,gfs,gen", FD3_VARIANTS, False),
+    "mit_humanoid_leg": ("id,fd,fk,h,phi,gfa,gfs,gen", FD3_VARIANTS, False),
     # 58 bodies: the tile rows of a 128-thread CTA take 163 KB (one CTA per SM); 64-thread CTAs fit twice.
     # Both dynamics kernels spill and are parked (ID 1.01 -> 0.86 ms, FD 3.3-4.2 ms per 2^20 states, L2 dependent).
     # Inverse dynamics: without an output tile ('direct': 38 plain stores per thread) THREE 64-thread CTAs fit, and what
@@ -69,13 +76,13 @@ MODELS = {
     "revolute_chain_with_rotor_2": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, True),
     "revolute_chain_with_rotor_4": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
     # depth sweep of the serial cluster chain (BASELINE config 5: deep-tree latency)
-    "revolute_chain_with_rotor_8": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    "revolute_chain_with_rotor_8": ("id,fd,fk,h,gfa,gfs,gen", FD3_VARIANTS, False),
     # FP32: forward dynamics of the 16-link fixed-base chain (cond(H) ~ 2e4) through the articulated-body sweep:
     # median error 6e-7 instead of 1e-4 with the factorisation (measured, tests/test_gpu_parity.py)
     "revolute_chain_with_rotor_16": ("id,fd,fk,h,gfa,gfs,gen",
                                      ID3_VARIANTS.replace("fd=T,128,2,auto,park;", "fd=T,128,2,auto,park,f32aba;"), True),
     "revolute_pair_chain_with_rotor_2": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
-    "revolute_pair_chain_with_rotor_4": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
+    "revolute_pair_chain_with_rotor_4": ("id,fd,fk,h,gfa,gfs,gen", FD3_VARIANTS, False),
     # the remaining cluster-joint classes of the reference: RevolutePair (RevolutePairChain.cpp) and
     # RevoluteTripleWithRotor (RevoluteTripleChainWithRotor.cpp, seeded parameters)
     "revolute_pair_chain_4": ("id,fd,fk,h,gfa,gfs,gen", DEFAULT_VARIANTS, False),
